@@ -149,12 +149,12 @@ def have_ref():
 
 
 def ref_raycast(rays, mode="closest", ply=None, tris=None, threads=None, simd=0, stride=1,
-                dump_bvh=False, repeat=1):
+                dump_bvh=False, repeat=1, warmup=0):
     """Run oracle/_ref/raycast_ref. Returns (info, prim, t) | (info, occluded) [+ nodes]."""
     assert have_ref(), "oracle/_ref/raycast_ref missing: run `make -C oracle ref` where /root/reference exists"
     with tempfile.TemporaryDirectory() as td:
         cmd = [RAYCAST_REF, "--mode", mode, "--simd", str(simd), "--stride", str(stride),
-               "--repeat", str(repeat)]
+               "--repeat", str(repeat), "--warmup", str(warmup)]
         if threads:
             cmd += ["--threads", str(threads)]
         if ply is not None:

@@ -83,7 +83,7 @@ struct DumpNode {
 int main(int argc, char** argv) {
     std::string ply, tris, raysFile, rayFormat = "f32", mode = "closest", out, dumpBvh;
     int threads = (int)std::thread::hardware_concurrency();
-    int repeat = 1, simd = 0;
+    int repeat = 1, simd = 0, warmup = 0;
     long stride = 1, limit = -1;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
@@ -97,6 +97,7 @@ int main(int argc, char** argv) {
         else if (a == "--dump-bvh") dumpBvh = next();
         else if (a == "--threads") threads = std::atoi(next().c_str());
         else if (a == "--repeat") repeat = std::atoi(next().c_str());
+        else if (a == "--warmup") warmup = std::atoi(next().c_str());
         else if (a == "--simd") simd = std::atoi(next().c_str());
         else if (a == "--stride") stride = std::atol(next().c_str());
         else if (a == "--limit") limit = std::atol(next().c_str());
@@ -193,8 +194,8 @@ int main(int argc, char** argv) {
             }
         };
 
-        double best = 1e30;
-        for (int r = 0; r < repeat; r++) {
+        double best = 1e30, sum = 0.0;
+        for (int r = 0; r < warmup + repeat; r++) {
             double ts = now();
             std::vector<std::thread> pool;
             // dynamic chunks so the timing is not dominated by one slow slice
@@ -210,9 +211,10 @@ int main(int argc, char** argv) {
                 });
             }
             for (auto& th : pool) th.join();
-            best = std::min(best, now() - ts);
+            const double dt = now() - ts;
+            if (r >= warmup) { best = std::min(best, dt); sum += dt; }
         }
-        traceSec = best;
+        traceSec = sum / repeat;   // mean over the timed repeats
         for (long k = 0; k < nUsed; k++) nHit += closest ? (outPrim[k] >= 0) : outAny[k];
 
         if (!out.empty()) {

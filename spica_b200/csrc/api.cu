@@ -1,0 +1,255 @@
+// C ABI: context, geometry upload, acceleration-structure build / import, raw device memory.
+#include <chrono>
+#include <cstring>
+#include <mutex>
+
+#include "context.h"
+
+namespace spb {
+
+static std::mutex g_errMutex;
+static std::string g_lastError;
+
+void setGlobalError(const std::string& msg) {
+    std::lock_guard<std::mutex> lk(g_errMutex);
+    g_lastError = msg;
+}
+
+int fail(spb_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    setGlobalError(msg);
+    return code;
+}
+
+bool cudaOk(spb_ctx* ctx, cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return true;
+    fail(ctx, SPB_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    return false;
+}
+
+static void freeBvhDevice(spb_ctx* ctx) {
+    if (ctx->d_nodes) cudaFree(ctx->d_nodes);
+    if (ctx->d_tris) cudaFree(ctx->d_tris);
+    ctx->d_nodes = ctx->d_tris = nullptr;
+    ctx->bvh_ready = false;
+}
+
+static int uploadBvh(spb_ctx* ctx) {
+    freeBvhDevice(ctx);
+    const HostBVH& b = ctx->bvh;
+    SceneParams& sp = ctx->sp;
+    std::memset(&sp, 0, sizeof(sp));
+    sp.empty = (b.n_tris == 0 || b.nodes.empty()) ? 1 : 0;
+    sp.n_tris = (int32_t)b.n_tris;
+    sp.tri_format = b.tri_format;
+    sp.inflate = (float)b.inflate;
+    for (int k = 0; k < 3; k++) {
+        sp.wlo[k] = b.wlo[k] - 2.0 * b.inflate;
+        sp.whi[k] = b.whi[k] + 2.0 * b.inflate;
+    }
+    if (!sp.empty) {
+        SPB_CUDA(ctx, cudaMalloc(&ctx->d_nodes, b.nodes.size() * sizeof(WideNode)));
+        SPB_CUDA(ctx, cudaMalloc(&ctx->d_tris, b.tris.size()));
+        SPB_CUDA(ctx, cudaMemcpyAsync(ctx->d_nodes, b.nodes.data(), b.nodes.size() * sizeof(WideNode), cudaMemcpyHostToDevice, ctx->stream));
+        SPB_CUDA(ctx, cudaMemcpyAsync(ctx->d_tris, b.tris.data(), b.tris.size(), cudaMemcpyHostToDevice, ctx->stream));
+        SPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    sp.nodes = (const WideNode*)ctx->d_nodes;
+    sp.tris = ctx->d_tris;
+    ctx->bvh_ready = true;
+    return SPB_OK;
+}
+
+}  // namespace spb
+
+using namespace spb;
+
+extern "C" {
+
+int spb_version(void) { return SPB_VERSION; }
+
+const char* spb_last_error(const spb_ctx* ctx) {
+    if (ctx) return ctx->err.c_str();
+    std::lock_guard<std::mutex> lk(g_errMutex);
+    static thread_local std::string copy;
+    copy = g_lastError;
+    return copy.c_str();
+}
+
+int spb_ctx_create(int device, spb_ctx** out) {
+    if (!out) return fail(nullptr, SPB_ERR_INVALID, "spb_ctx_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, SPB_ERR_NO_DEVICE, std::string("no CUDA device (spica_b200 has no CPU path): ") + cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(nullptr, SPB_ERR_INVALID, "spb_ctx_create: device index out of range");
+    spb_ctx* ctx = new spb_ctx();
+    ctx->device = device;
+    auto bail = [&](cudaError_t ce, const char* what) {
+        fail(nullptr, SPB_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(ce));
+        delete ctx;
+        return SPB_ERR_CUDA;
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(e, "cudaSetDevice");
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail(e, "cudaGetDeviceProperties");
+    ctx->sm_count = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    if ((e = cudaStreamCreateWithFlags(&ctx->h2d, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    if ((e = cudaStreamCreateWithFlags(&ctx->d2h, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
+    for (int i = 0; i < 2; i++) {
+        cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming);
+    }
+    if ((e = cudaMalloc(&ctx->d_work, 8 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
+    cudaMemset(ctx->d_work, 0, 8 * sizeof(unsigned long long));
+    std::memset(&ctx->sp, 0, sizeof(ctx->sp));
+    ctx->sp.empty = 1;
+    *out = ctx;
+    return SPB_OK;
+}
+
+void spb_ctx_destroy(spb_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    renderStateDestroy(ctx);
+    freeBvhDevice(ctx);
+    for (int i = 0; i < 2; i++) {
+        if (ctx->d_in[i]) cudaFree(ctx->d_in[i]);
+        if (ctx->d_out[i]) cudaFree(ctx->d_out[i]);
+        cudaEventDestroy(ctx->ev_in[i]); cudaEventDestroy(ctx->ev_k[i]); cudaEventDestroy(ctx->ev_out[i]);
+    }
+    if (ctx->d_work) cudaFree(ctx->d_work);
+    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+    cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->h2d); cudaStreamDestroy(ctx->d2h);
+    delete ctx;
+}
+
+int spb_scene_set_triangles(spb_ctx* ctx, const double* verts, const float* normals,
+                            const int32_t* material_id, const int32_t* light_id, int64_t n) {
+    if (!ctx) return fail(nullptr, SPB_ERR_INVALID, "ctx is NULL");
+    if (n < 0 || (n > 0 && !verts)) return fail(ctx, SPB_ERR_INVALID, "spb_scene_set_triangles: bad arguments");
+    if (n > 0x7fffffff / 2) return fail(ctx, SPB_ERR_UNSUPPORTED, "more than 2^30 triangles");
+    cudaSetDevice(ctx->device);
+    ctx->n_tris = n;
+    ctx->verts.assign(verts, verts + n * 9);
+    if (normals) ctx->normals.assign(normals, normals + n * 9); else ctx->normals.clear();
+    if (material_id) ctx->material_id.assign(material_id, material_id + n); else ctx->material_id.assign((size_t)n, 0);
+    if (light_id) ctx->light_id.assign(light_id, light_id + n); else ctx->light_id.assign((size_t)n, -1);
+    freeBvhDevice(ctx);
+    ctx->bin = BinaryBVH();
+    return SPB_OK;
+}
+
+int spb_bvh_build(spb_ctx* ctx, const spb_build_opts* opts) {
+    if (!ctx) return fail(nullptr, SPB_ERR_INVALID, "ctx is NULL");
+    cudaSetDevice(ctx->device);
+    spb_build_opts o = {0, 3, 32, 0};
+    if (opts) o = *opts;
+    if (o.max_leaf_tris <= 0) o.max_leaf_tris = 3;
+    if (o.sah_bins <= 0) o.sah_bins = 32;
+    if (o.builder != 0) return fail(ctx, SPB_ERR_UNSUPPORTED, "spb_bvh_build: only builder 0 (host binned SAH) is available in this build");
+    const auto t0 = std::chrono::steady_clock::now();
+    build_binary_sah(ctx->verts.data(), ctx->n_tris, o.sah_bins, &ctx->bin);
+    std::string err;
+    if (!encode_wide(ctx->bin, ctx->verts.data(), ctx->n_tris, o.max_leaf_tris, &ctx->bvh, &err))
+        return fail(ctx, SPB_ERR_UNSUPPORTED, "spb_bvh_build: " + err);
+    ctx->build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return uploadBvh(ctx);
+}
+
+int spb_bvh_import_binary(spb_ctx* ctx, const spb_import_node* nodes, int64_t n_nodes, int32_t root) {
+    if (!ctx) return fail(nullptr, SPB_ERR_INVALID, "ctx is NULL");
+    if (!nodes) return fail(ctx, SPB_ERR_INVALID, "spb_bvh_import_binary: nodes is NULL");
+    cudaSetDevice(ctx->device);
+    const auto t0 = std::chrono::steady_clock::now();
+    std::string err;
+    if (!import_binary(nodes, n_nodes, root, ctx->verts.data(), ctx->n_tris, &ctx->bin, &err))
+        return fail(ctx, SPB_ERR_INVALID, "spb_bvh_import_binary: " + err);
+    if (!encode_wide(ctx->bin, ctx->verts.data(), ctx->n_tris, 3, &ctx->bvh, &err))
+        return fail(ctx, SPB_ERR_UNSUPPORTED, "spb_bvh_import_binary: " + err);
+    ctx->build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return uploadBvh(ctx);
+}
+
+int spb_bvh_get_stats(const spb_ctx* ctx, spb_bvh_stats* out) {
+    if (!ctx || !out) return fail(nullptr, SPB_ERR_INVALID, "spb_bvh_get_stats: NULL argument");
+    if (!ctx->bvh_ready) return fail(const_cast<spb_ctx*>(ctx), SPB_ERR_INVALID, "spb_bvh_get_stats: no acceleration structure built");
+    const HostBVH& b = ctx->bvh;
+    std::memset(out, 0, sizeof(*out));
+    out->n_tris = b.n_tris;
+    out->n_wide_nodes = (int64_t)b.nodes.size();
+    out->n_binary_nodes = b.n_binary_nodes;
+    out->node_bytes = (int64_t)(b.nodes.size() * sizeof(WideNode));
+    out->tri_bytes = (int64_t)b.tris.size();
+    out->sah_cost = b.sah_cost;
+    out->build_seconds = ctx->build_seconds;
+    out->tri_format = b.tri_format;
+    out->max_depth = b.max_depth;
+    for (int k = 0; k < 3; k++) { out->world_lo[k] = b.wlo[k]; out->world_hi[k] = b.whi[k]; }
+    return SPB_OK;
+}
+
+int spb_set_option(spb_ctx* ctx, const char* name, int64_t value) {
+    if (!ctx || !name) return fail(ctx, SPB_ERR_INVALID, "spb_set_option: NULL argument");
+    const std::string n(name);
+    if (n == "counters") ctx->opt_counters = value ? 1 : 0;
+    else if (n == "trace_block") {
+        if (value < 32 || value > 1024 || (value % 32)) return fail(ctx, SPB_ERR_INVALID, "trace_block must be a multiple of 32 in [32,1024]");
+        ctx->opt_block = (int)value;
+    } else if (n == "trace_ctas_per_sm") ctx->opt_ctas_per_sm = (int)value;
+    else if (n == "trace_variant") ctx->opt_variant = (int)value;
+    else if (n == "chunk_rays") { if (value < 1024) return fail(ctx, SPB_ERR_INVALID, "chunk_rays too small"); ctx->opt_chunk = value; }
+    else return fail(ctx, SPB_ERR_INVALID, "spb_set_option: unknown option " + n);
+    return SPB_OK;
+}
+
+int spb_get_counters(spb_ctx* ctx, spb_counters* out) {
+    if (!ctx || !out) return fail(ctx, SPB_ERR_INVALID, "spb_get_counters: NULL argument");
+    out->last_kernel_ms = ctx->last_kernel_ms;
+    out->kernel_launches = ctx->kernel_launches;
+    out->rays = ctx->c_rays; out->node_visits = ctx->c_nodes; out->tri_tests = ctx->c_tris;
+    return SPB_OK;
+}
+
+int spb_dev_alloc(spb_ctx* ctx, size_t bytes, void** d_ptr) {
+    if (!ctx || !d_ptr) return fail(ctx, SPB_ERR_INVALID, "spb_dev_alloc: NULL argument");
+    cudaSetDevice(ctx->device);
+    cudaError_t e = cudaMalloc(d_ptr, bytes ? bytes : 16);
+    if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); return fail(ctx, SPB_ERR_OOM, "spb_dev_alloc: out of device memory"); }
+    SPB_CUDA(ctx, e);
+    return SPB_OK;
+}
+int spb_dev_free(spb_ctx* ctx, void* d_ptr) {
+    if (!ctx) return fail(ctx, SPB_ERR_INVALID, "spb_dev_free: NULL ctx");
+    cudaSetDevice(ctx->device);
+    SPB_CUDA(ctx, cudaFree(d_ptr));
+    return SPB_OK;
+}
+int spb_dev_upload(spb_ctx* ctx, void* d_dst, const void* h_src, size_t bytes) {
+    if (!ctx) return fail(ctx, SPB_ERR_INVALID, "spb_dev_upload: NULL ctx");
+    cudaSetDevice(ctx->device);
+    SPB_CUDA(ctx, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    SPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SPB_OK;
+}
+int spb_dev_download(spb_ctx* ctx, void* h_dst, const void* d_src, size_t bytes) {
+    if (!ctx) return fail(ctx, SPB_ERR_INVALID, "spb_dev_download: NULL ctx");
+    cudaSetDevice(ctx->device);
+    SPB_CUDA(ctx, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    SPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SPB_OK;
+}
+int spb_dev_sync(spb_ctx* ctx) {
+    if (!ctx) return fail(ctx, SPB_ERR_INVALID, "spb_dev_sync: NULL ctx");
+    cudaSetDevice(ctx->device);
+    SPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SPB_OK;
+}
+void* spb_ctx_stream(spb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+}  // extern "C"

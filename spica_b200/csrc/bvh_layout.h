@@ -1,0 +1,51 @@
+// Device-resident acceleration-structure layout (shared by the host encoder, the CUDA kernels and
+// the CPU emulation used by the unit tests).
+//
+// 8-wide compressed BVH: 80-byte nodes read as five 128-bit loads.  Child boxes are quantised to
+// 8 bits per plane on a per-node power-of-two grid and are CONSERVATIVE (they contain the exact
+// fp64 child bounds inflated by `inflate`), because they only cull: the winner of a query is
+// always decided by the fp64 Moeller-Trumbore test, which restates core/triangle.cc:98-117 of the
+// reference bit for bit.
+#pragma once
+#include <stdint.h>
+
+namespace spb {
+
+struct alignas(16) WideNode {           // 80 B
+    float    p[3];                      // grid origin (<= every child lo)
+    uint8_t  e[3];                      // biased exponents: plane = p + q * 2^(e-127)
+    uint8_t  imask;                     // bit s set: slot s holds an inner node
+    uint32_t child_base;                // index of the first inner child (children are contiguous, slot order)
+    uint32_t tri_base;                  // index of the first triangle of this node's leaves
+    uint8_t  meta[8];                   // per slot: 0 = empty; inner: (1<<5)|(24+slot); leaf: (unary(n)<<5)|offset
+    uint8_t  qlo[3][8];                 // [axis][slot]
+    uint8_t  qhi[3][8];
+};
+static_assert(sizeof(WideNode) == 80, "WideNode must be 80 bytes");
+
+// Triangle records, stored in leaf order.  id = the caller's primitive index; rank = tie-break key
+// (smaller wins on exactly equal t).
+struct alignas(16) TriF32 {             // 48 B: vertices exactly representable in float32
+    float v0[3]; int32_t id;
+    float v1[3]; int32_t rank;
+    float v2[3]; int32_t pad;
+};
+struct alignas(16) TriF64 {             // 80 B
+    double v[9];
+    int32_t id, rank;
+};
+static_assert(sizeof(TriF32) == 48 && sizeof(TriF64) == 80, "triangle record sizes");
+
+enum { kStackCapacity = 40 };
+
+struct SceneParams {                    // small POD passed to kernels by value
+    const WideNode* nodes;
+    const void*     tris;               // TriF32* or TriF64*
+    double wlo[3], whi[3];              // inflated world box
+    float  inflate;
+    int32_t tri_format;                 // 0 = TriF32, 1 = TriF64
+    int32_t n_tris;
+    int32_t empty;                      // 1: no geometry
+};
+
+}  // namespace spb

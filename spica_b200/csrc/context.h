@@ -1,0 +1,69 @@
+// Internal: the opaque context behind the C ABI (include/spica_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/spica_b200.h"
+#include "bvh_host.h"
+#include "bvh_layout.h"
+
+struct spb_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;       // compute
+    cudaStream_t h2d = nullptr, d2h = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+
+    // host copies of the scene (the builder runs on the host; also the source for re-builds)
+    std::vector<double>  verts;          // 9 per triangle
+    std::vector<float>   normals;        // 9 per triangle or empty
+    std::vector<int32_t> material_id, light_id;
+    int64_t n_tris = 0;
+
+    spb::BinaryBVH bin;
+    spb::HostBVH   bvh;
+    bool bvh_ready = false;
+    double build_seconds = 0.0;
+
+    void* d_nodes = nullptr;
+    void* d_tris = nullptr;
+    spb::SceneParams sp{};
+
+    // grow-only scratch for the host-buffer entry points (double buffered)
+    void* d_in[2] = {nullptr, nullptr};
+    void* d_out[2] = {nullptr, nullptr};
+    size_t in_cap = 0, out_cap = 0;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    unsigned long long* d_work = nullptr;   // persistent-kernel work counter + traversal counters (4 x u64)
+
+    // options
+    int opt_counters = 0;
+    int opt_block = 128;
+    int opt_ctas_per_sm = 0;             // 0 = occupancy query
+    int opt_variant = 1;                 // 0 = one thread per ray, 1 = persistent dynamic fetch
+    int64_t opt_chunk = 1 << 21;         // rays per pipelined chunk on the host-buffer path
+
+    // counters
+    double last_kernel_ms = 0.0;
+    int64_t kernel_launches = 0;
+    int64_t c_rays = 0, c_nodes = 0, c_tris = 0;
+
+    // integrator state lives in integrator.cu
+    struct RenderState* render = nullptr;
+};
+
+namespace spb {
+int  fail(spb_ctx* ctx, int code, const std::string& msg);
+bool cudaOk(spb_ctx* ctx, cudaError_t e, const char* what);
+void setGlobalError(const std::string& msg);
+void renderStateDestroy(spb_ctx* ctx);   // integrator.cu
+}  // namespace spb
+
+#define SPB_CUDA(ctx, call)                                                      \
+    do {                                                                         \
+        if (!spb::cudaOk((ctx), (call), #call)) return SPB_ERR_CUDA;             \
+    } while (0)

@@ -1,0 +1,305 @@
+// Per-ray traversal of the 8-wide compressed BVH.  __host__ __device__ so that the very same code
+// is (a) inlined into the sm_100a kernels (trace.cu, integrator.cu) and (b) compiled by g++ into
+// the unit-test emulation (tests/emul), where the node decoding, stack handling, ordering and the
+// exact triangle test are checked against the oracle without a GPU.  The emulation is test
+// infrastructure; the product never runs this on the CPU.
+//
+// Two arithmetic domains:
+//   culling  : float32, conservative (quantised boxes inflated by SceneParams::inflate, ray clipped
+//              to the world box so every float32 magnitude is bounded by the scene size);
+//   deciding : float64 Moeller-Trumbore in the reference's operation order with no FMA
+//              contraction (core/triangle.cc:98-117), on the reference's own ray representation
+//              (core/ray.cc:11-19).  Only this domain determines (prim, t, u, v).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "bvh_layout.h"
+
+#if defined(__CUDACC__)
+#define SPB_HD __host__ __device__ __forceinline__
+#else
+#define SPB_HD inline
+#endif
+
+namespace spb {
+
+// ---- exact double arithmetic: never contracted into FMA --------------------------------------
+#if defined(__CUDA_ARCH__)
+SPB_HD double dmul(double a, double b) { return __dmul_rn(a, b); }
+SPB_HD double dadd(double a, double b) { return __dadd_rn(a, b); }
+SPB_HD double dsub(double a, double b) { return __dadd_rn(a, -b); }
+SPB_HD double drcp(double a) { return __drcp_rn(a); }            // == 1.0 / a, correctly rounded
+SPB_HD double dsqrt(double a) { return __dsqrt_rn(a); }
+SPB_HD float  ffma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+SPB_HD int    clz32(uint32_t x) { return __clz((int)x); }
+SPB_HD int    ctz32(uint32_t x) { return __ffs((int)x) - 1; }
+SPB_HD int    popc32(uint32_t x) { return __popc(x); }
+#else
+// host emulation: compiled with -ffp-contract=off on x86-64 (no FMA unless asked)
+SPB_HD double dmul(double a, double b) { return a * b; }
+SPB_HD double dadd(double a, double b) { return a + b; }
+SPB_HD double dsub(double a, double b) { return a - b; }
+SPB_HD double drcp(double a) { return 1.0 / a; }
+SPB_HD double dsqrt(double a) { return sqrt(a); }
+SPB_HD float  ffma(float a, float b, float c) { return fmaf(a, b, c); }
+SPB_HD int    clz32(uint32_t x) { return x ? __builtin_clz(x) : 32; }
+SPB_HD int    ctz32(uint32_t x) { return x ? __builtin_ctz(x) : -1; }
+SPB_HD int    popc32(uint32_t x) { return __builtin_popcount(x); }
+#endif
+
+struct U4 { uint32_t x, y, z, w; };
+struct U2 { uint32_t x, y; };
+
+SPB_HD float asFloat(uint32_t u) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    float f; __builtin_memcpy(&f, &u, 4); return f;
+#endif
+}
+SPB_HD uint32_t byteOf(uint32_t w, int i) { return (w >> (8 * i)) & 0xffu; }
+
+#if defined(__CUDA_ARCH__)
+SPB_HD U4 ldg4(const void* p) { const uint4 v = __ldg((const uint4*)p); return U4{v.x, v.y, v.z, v.w}; }
+#else
+SPB_HD U4 ldg4(const void* p) { U4 v; __builtin_memcpy(&v, p, 16); return v; }
+#endif
+
+const double kRefEps = 1.0e-12;     // reference core/common.h:55
+const double kRefInfty = 1.0e32;    // reference core/common.h:54
+
+struct TraceCounters { unsigned long long nodes, tris; };
+
+struct RayState {
+    // deciding domain
+    double ox, oy, oz, dx, dy, dz;
+    double best_t;                  // the reference's shrinking ray.maxDist (core/primitive.cc:52)
+    double t_shift;                 // culling origin = o + t_shift * d
+    // culling domain
+    float cox, coy, coz, idx, idy, idz, ctmax;
+    uint32_t oct_inv;
+    // result
+    int32_t best_prim, best_rank;
+    float best_u, best_v;
+};
+
+SPB_HD float cullTmax(const RayState& r, double t) {
+    // distance along the culling ray, rounded up with slack
+    return (float)((t - r.t_shift) * 1.000002) + 1e-30f;
+}
+
+// Applies the reference's Ray constructor (core/ray.cc:11-19: dir = d * (1.0/|d|)) and derives the
+// float32 culling ray.  Returns false when the ray cannot hit anything (zero direction, or it
+// misses the inflated world box / the box lies beyond tmax).
+SPB_HD bool rayBegin(const SceneParams& sp, double ox, double oy, double oz, double dx, double dy,
+                     double dz, double tmax, RayState& r) {
+    r.best_prim = -1; r.best_rank = 0x7fffffff; r.best_u = 0.f; r.best_v = 0.f;
+    r.best_t = tmax;
+    r.ox = ox; r.oy = oy; r.oz = oz;
+    const double sq = dadd(dadd(dmul(dx, dx), dmul(dy, dy)), dmul(dz, dz));
+    const double nrm = dsqrt(sq);
+    if (!(nrm > 0.0) || sp.empty) { r.dx = r.dy = r.dz = 0.0; return false; }
+    const double s = drcp(nrm);
+    r.dx = dmul(dx, s); r.dy = dmul(dy, s); r.dz = dmul(dz, s);
+
+    // clip against the inflated world box in double (not part of the parity arithmetic)
+    double t0 = 0.0, t1 = tmax;
+    const double o[3] = {ox, oy, oz}, d[3] = {r.dx, r.dy, r.dz};
+    for (int k = 0; k < 3; k++) {
+        if (d[k] == 0.0) {
+            if (o[k] < sp.wlo[k] || o[k] > sp.whi[k]) return false;
+        } else {
+            const double inv = 1.0 / d[k];
+            double ta = (sp.wlo[k] - o[k]) * inv, tb = (sp.whi[k] - o[k]) * inv;
+            if (ta > tb) { const double tt = ta; ta = tb; tb = tt; }
+            // widen by a relative slack: this test only prunes
+            ta -= fabs(ta) * 1e-12; tb += fabs(tb) * 1e-12;
+            if (ta > t0) t0 = ta;
+            if (tb < t1) t1 = tb;
+        }
+    }
+    if (!(t0 <= t1)) return false;
+    r.t_shift = t0 > 0.0 ? t0 * 0.999999 : 0.0;
+    r.cox = (float)(ox + r.t_shift * r.dx);
+    r.coy = (float)(oy + r.t_shift * r.dy);
+    r.coz = (float)(oz + r.t_shift * r.dz);
+    const float fdx = (float)r.dx, fdy = (float)r.dy, fdz = (float)r.dz;
+    const float tiny = 8.6736174e-19f;  // 2^-60: keeps 1/d finite; far below the culling slack
+    r.idx = 1.0f / (fabsf(fdx) < tiny ? (fdx < 0.f ? -tiny : tiny) : fdx);
+    r.idy = 1.0f / (fabsf(fdy) < tiny ? (fdy < 0.f ? -tiny : tiny) : fdy);
+    r.idz = 1.0f / (fabsf(fdz) < tiny ? (fdz < 0.f ? -tiny : tiny) : fdz);
+    // bit set where the direction is non-negative (slot ^ oct_inv == 7 for the nearest corner)
+    r.oct_inv = (fdx < 0.f ? 0u : 1u) | (fdy < 0.f ? 0u : 2u) | (fdz < 0.f ? 0u : 4u);
+    r.ctmax = cullTmax(r, t1 < tmax ? t1 : tmax);
+    return true;
+}
+
+// fp64 Moeller-Trumbore, same operations in the same order as core/triangle.cc:100-117.
+SPB_HD bool triTestExact(const RayState& r, const double p0[3], const double p1[3], const double p2[3],
+                         double* tOut, double* uOut, double* vOut) {
+    const double e1x = dsub(p1[0], p0[0]), e1y = dsub(p1[1], p0[1]), e1z = dsub(p1[2], p0[2]);
+    const double e2x = dsub(p2[0], p0[0]), e2y = dsub(p2[1], p0[1]), e2z = dsub(p2[2], p0[2]);
+    const double px = dsub(dmul(r.dy, e2z), dmul(r.dz, e2y));
+    const double py = dsub(dmul(r.dz, e2x), dmul(r.dx, e2z));
+    const double pz = dsub(dmul(r.dx, e2y), dmul(r.dy, e2x));
+    const double det = dadd(dadd(dmul(e1x, px), dmul(e1y, py)), dmul(e1z, pz));
+    if (det > -kRefEps && det < kRefEps) return false;
+    const double invdet = drcp(det);
+    const double tx = dsub(r.ox, p0[0]), ty = dsub(r.oy, p0[1]), tz = dsub(r.oz, p0[2]);
+    const double u = dmul(dadd(dadd(dmul(tx, px), dmul(ty, py)), dmul(tz, pz)), invdet);
+    if (u < 0.0 || u > 1.0) return false;
+    const double qx = dsub(dmul(ty, e1z), dmul(tz, e1y));
+    const double qy = dsub(dmul(tz, e1x), dmul(tx, e1z));
+    const double qz = dsub(dmul(tx, e1y), dmul(ty, e1x));
+    const double v = dmul(dadd(dadd(dmul(r.dx, qx), dmul(r.dy, qy)), dmul(r.dz, qz)), invdet);
+    if (v < 0.0 || dadd(u, v) > 1.0) return false;
+    const double t = dmul(dadd(dadd(dmul(e2x, qx), dmul(e2y, qy)), dmul(e2z, qz)), invdet);
+    if (t <= kRefEps || t > r.best_t) return false;
+    *tOut = t; *uOut = u; *vOut = v;
+    return true;
+}
+
+template <int TRI_FMT>
+SPB_HD bool triTestRecord(const SceneParams& sp, const RayState& r, uint32_t index, double* t, double* u,
+                          double* v, int32_t* id, int32_t* rank) {
+    double p0[3], p1[3], p2[3];
+    if (TRI_FMT == 0) {
+        const TriF32* tp = (const TriF32*)sp.tris + index;
+        const U4 a = ldg4(&tp->v0[0]), b = ldg4(&tp->v1[0]), c = ldg4(&tp->v2[0]);
+        p0[0] = (double)asFloat(a.x); p0[1] = (double)asFloat(a.y); p0[2] = (double)asFloat(a.z);
+        p1[0] = (double)asFloat(b.x); p1[1] = (double)asFloat(b.y); p1[2] = (double)asFloat(b.z);
+        p2[0] = (double)asFloat(c.x); p2[1] = (double)asFloat(c.y); p2[2] = (double)asFloat(c.z);
+        *id = (int32_t)a.w; *rank = (int32_t)b.w;
+    } else {
+        const TriF64* tp = (const TriF64*)sp.tris + index;
+        const U4 a = ldg4(&tp->v[0]), b = ldg4(&tp->v[2]), c = ldg4(&tp->v[4]), d = ldg4(&tp->v[6]),
+                 e = ldg4(&tp->v[8]);
+        auto mk = [](uint32_t lo, uint32_t hi) {
+            const unsigned long long bits = ((unsigned long long)hi << 32) | lo;
+            double x;
+#if defined(__CUDA_ARCH__)
+            x = __longlong_as_double((long long)bits);
+#else
+            __builtin_memcpy(&x, &bits, 8);
+#endif
+            return x;
+        };
+        p0[0] = mk(a.x, a.y); p0[1] = mk(a.z, a.w); p0[2] = mk(b.x, b.y);
+        p1[0] = mk(b.z, b.w); p1[1] = mk(c.x, c.y); p1[2] = mk(c.z, c.w);
+        p2[0] = mk(d.x, d.y); p2[1] = mk(d.z, d.w); p2[2] = mk(e.x, e.y);
+        *id = (int32_t)e.z; *rank = (int32_t)e.w;
+    }
+    return triTestExact(r, p0, p1, p2, t, u, v);
+}
+
+// Tests the 8 quantised child boxes of one node; returns the hit mask in traversal layout:
+// bits 24..31 inner children at priority (slot ^ oct_inv), bits 0..23 triangles of hit leaves.
+SPB_HD uint32_t nodeHitMask(const U4& n0, const U4& n1, const U4& n2, const U4& n3, const U4& n4,
+                            const RayState& r) {
+    const float adx = r.idx * asFloat(byteOf(n0.w, 0) << 23);
+    const float ady = r.idy * asFloat(byteOf(n0.w, 1) << 23);
+    const float adz = r.idz * asFloat(byteOf(n0.w, 2) << 23);
+    const float aox = (asFloat(n0.x) - r.cox) * r.idx;
+    const float aoy = (asFloat(n0.y) - r.coy) * r.idy;
+    const float aoz = (asFloat(n0.z) - r.coz) * r.idz;
+    const bool nx = r.idx < 0.f, ny = r.idy < 0.f, nz = r.idz < 0.f;
+    uint32_t hitmask = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int h = 0; h < 2; h++) {
+        const uint32_t meta4 = h ? n1.w : n1.z;
+        const uint32_t lox = h ? n2.y : n2.x, loy = h ? n2.w : n2.z, loz = h ? n3.y : n3.x;
+        const uint32_t hix = h ? n3.w : n3.z, hiy = h ? n4.y : n4.x, hiz = h ? n4.w : n4.z;
+        const uint32_t nearx = nx ? hix : lox, farx = nx ? lox : hix;
+        const uint32_t neary = ny ? hiy : loy, fary = ny ? loy : hiy;
+        const uint32_t nearz = nz ? hiz : loz, farz = nz ? loz : hiz;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int j = 0; j < 4; j++) {
+            const uint32_t m = byteOf(meta4, j);
+            const float tnx = ffma((float)byteOf(nearx, j), adx, aox);
+            const float tny = ffma((float)byteOf(neary, j), ady, aoy);
+            const float tnz = ffma((float)byteOf(nearz, j), adz, aoz);
+            const float tfx = ffma((float)byteOf(farx, j), adx, aox);
+            const float tfy = ffma((float)byteOf(fary, j), ady, aoy);
+            const float tfz = ffma((float)byteOf(farz, j), adz, aoz);
+            const float tmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
+            const float tmax = fminf(fminf(tfx, tfy), fminf(tfz, r.ctmax));
+            if (m != 0u && tmin <= tmax) {
+                uint32_t pos = m & 31u;
+                if (pos >= 24u) pos ^= r.oct_inv;
+                hitmask |= (m >> 5) << pos;
+            }
+        }
+    }
+    return hitmask;
+}
+
+// The traversal state machine.  step() consumes one node group entry: it visits one inner node
+// (tests its 8 child boxes) and then tests the triangles of the leaves that were hit.
+template <int TRI_FMT, bool ANY_HIT>
+struct Traverser {
+    U2 stack[kStackCapacity];
+    int sp_;
+    U2 ngroup;       // x: child base index, y: [31..24] pending inner hits, [7..0] imask
+    bool finished;
+
+    SPB_HD void begin(bool valid) {
+        sp_ = 0;
+        ngroup.x = 0u; ngroup.y = 0x80000000u;   // the root as a one-node group
+        finished = !valid;
+    }
+
+    SPB_HD void step(const SceneParams& sp, RayState& r, TraceCounters* ctr) {
+        U2 tgroup;
+        {
+            const uint32_t hits = ngroup.y;
+            const int bit = 31 - clz32(hits);
+            ngroup.y &= ~(1u << bit);
+            if (ngroup.y & 0xff000000u) stack[sp_++] = ngroup;
+            const uint32_t slot = (uint32_t)(bit - 24) ^ r.oct_inv;
+            const uint32_t rel = (uint32_t)popc32(hits & ~(0xffffffffu << slot) & 0xffu);
+            const WideNode* np = sp.nodes + (ngroup.x + rel);
+            const U4 n0 = ldg4((const char*)np), n1 = ldg4((const char*)np + 16), n2 = ldg4((const char*)np + 32),
+                     n3 = ldg4((const char*)np + 48), n4 = ldg4((const char*)np + 64);
+            const uint32_t hm = nodeHitMask(n0, n1, n2, n3, n4, r);
+            if (ctr) ctr->nodes++;
+            ngroup.x = n1.x;
+            ngroup.y = (hm & 0xff000000u) | (n0.w >> 24);
+            tgroup.x = n1.y;
+            tgroup.y = hm & 0x00ffffffu;
+        }
+        while (tgroup.y) {
+            const int i = ctz32(tgroup.y);
+            tgroup.y &= tgroup.y - 1u;
+            double t, u, v; int32_t id, rank;
+            if (ctr) ctr->tris++;
+            if (triTestRecord<TRI_FMT>(sp, r, tgroup.x + (uint32_t)i, &t, &u, &v, &id, &rank)) {
+                if (ANY_HIT) { r.best_prim = id; r.best_t = t; finished = true; return; }
+                // t <= best_t here.  Exact tie: the smaller rank wins (see spica_b200.h,
+                // spb_bvh_import_binary); a first hit at t == tmax is accepted.
+                if (t < r.best_t || r.best_prim < 0 || rank < r.best_rank) {
+                    r.best_t = t; r.best_prim = id; r.best_rank = rank;
+                    r.best_u = (float)u; r.best_v = (float)v;
+                    r.ctmax = fminf(r.ctmax, cullTmax(r, t));
+                }
+            }
+        }
+        if (!(ngroup.y & 0xff000000u)) {
+            if (sp_ == 0) { finished = true; return; }
+            ngroup = stack[--sp_];
+        }
+    }
+};
+
+template <int TRI_FMT, bool ANY_HIT>
+SPB_HD void traceRay(const SceneParams& sp, RayState& r, bool valid, TraceCounters* ctr) {
+    Traverser<TRI_FMT, ANY_HIT> tr;
+    tr.begin(valid);
+    while (!tr.finished) tr.step(sp, r, ctr);
+}
+
+}  // namespace spb

@@ -1,0 +1,84 @@
+// TEST INFRASTRUCTURE ONLY.  g++ build of the product's host-side builder (bvh_host.cpp) plus the
+// __host__ instantiation of the per-ray traversal (trace_core.h), so that node encoding, octant
+// ordering, stack handling and the exact triangle test can be checked against the oracle on a
+// machine without a GPU.  Nothing in the product loads this library.
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../spica_b200/csrc/bvh_host.h"
+#include "../../spica_b200/csrc/trace_core.h"
+
+using namespace spb;
+
+struct Emul {
+    std::vector<double> verts;
+    int64_t n = 0;
+    BinaryBVH bin;
+    HostBVH bvh;
+    SceneParams sp{};
+    std::string err;
+};
+
+extern "C" {
+
+Emul* emul_create(const double* verts, int64_t n, int max_leaf, int bins, const spb_import_node* imp,
+                  int64_t n_imp, int32_t root) {
+    Emul* e = new Emul();
+    e->verts.assign(verts, verts + n * 9);
+    e->n = n;
+    bool ok = true;
+    if (imp) ok = import_binary(imp, n_imp, root, e->verts.data(), n, &e->bin, &e->err);
+    else build_binary_sah(e->verts.data(), n, bins, &e->bin);
+    if (ok) ok = encode_wide(e->bin, e->verts.data(), n, max_leaf, &e->bvh, &e->err);
+    if (!ok) return e;
+    SceneParams& sp = e->sp;
+    std::memset(&sp, 0, sizeof(sp));
+    sp.nodes = e->bvh.nodes.data();
+    sp.tris = e->bvh.tris.data();
+    sp.empty = (n == 0 || e->bvh.nodes.empty()) ? 1 : 0;
+    sp.n_tris = (int32_t)n;
+    sp.tri_format = e->bvh.tri_format;
+    sp.inflate = (float)e->bvh.inflate;
+    for (int k = 0; k < 3; k++) { sp.wlo[k] = e->bvh.wlo[k] - 2 * e->bvh.inflate; sp.whi[k] = e->bvh.whi[k] + 2 * e->bvh.inflate; }
+    return e;
+}
+const char* emul_error(Emul* e) { return e->err.c_str(); }
+void emul_destroy(Emul* e) { delete e; }
+void emul_stats(Emul* e, int64_t* out) {
+    out[0] = (int64_t)e->bvh.nodes.size(); out[1] = e->bvh.tri_format; out[2] = e->bvh.max_depth;
+    out[3] = (int64_t)e->bin.nodes.size();
+}
+double emul_sah(Emul* e) { return e->bvh.sah_cost; }
+
+// rays: n x 8 (f32 or f64); out: prim i32[n], t f64[n], u f32[n], v f32[n]; counters u64[2]
+void emul_trace(Emul* e, const void* rays, int f64, int64_t n, int any, int32_t* prim, double* t, float* u,
+                float* v, unsigned long long* counters, int threads) {
+    if (threads < 1) threads = 1;
+    std::vector<std::thread> pool;
+    std::vector<TraceCounters> ctrs((size_t)threads, TraceCounters{0, 0});
+    for (int th = 0; th < threads; th++) {
+        pool.emplace_back([&, th]() {
+            const int64_t b = n * th / threads, en = n * (th + 1) / threads;
+            for (int64_t i = b; i < en; i++) {
+                double o[3], d[3], tmax;
+                if (f64) { const double* p = (const double*)rays + i * 8; for (int k = 0; k < 3; k++) { o[k] = p[k]; d[k] = p[3 + k]; } tmax = p[7]; }
+                else { const float* p = (const float*)rays + i * 8; for (int k = 0; k < 3; k++) { o[k] = p[k]; d[k] = p[3 + k]; } tmax = p[7]; }
+                RayState r;
+                const bool valid = rayBegin(e->sp, o[0], o[1], o[2], d[0], d[1], d[2], tmax, r);
+                if (e->sp.tri_format == 0) { if (any) traceRay<0, true>(e->sp, r, valid, &ctrs[th]); else traceRay<0, false>(e->sp, r, valid, &ctrs[th]); }
+                else { if (any) traceRay<1, true>(e->sp, r, valid, &ctrs[th]); else traceRay<1, false>(e->sp, r, valid, &ctrs[th]); }
+                prim[i] = r.best_prim;
+                t[i] = r.best_prim >= 0 ? r.best_t : 0.0;
+                u[i] = r.best_u; v[i] = r.best_v;
+            }
+        });
+    }
+    for (auto& th : pool) th.join();
+    counters[0] = counters[1] = 0;
+    for (auto& c : ctrs) { counters[0] += c.nodes; counters[1] += c.tris; }
+}
+
+}  // extern "C"

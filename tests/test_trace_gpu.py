@@ -1,0 +1,177 @@
+"""Parity tests proper: the CUDA ray-cast path, called through the C ABI (include/spica_b200.h),
+against the oracle and the committed golden vectors of the real reference.
+
+Bar: primitive ids bit-exact; t bit-exact in double (and <= 1e-5 relative through the float32 hit
+record, the tolerance BASELINE.json states); any-hit flags equal."""
+import numpy as np
+import pytest
+
+from oracle import binding as ob
+from spica_b200 import capi, scenes
+
+pytestmark = pytest.mark.gpu
+
+T_RTOL = 1e-5   # BASELINE.json north_star: "hit distance t must match within 1e-5 relative"
+
+
+def _as64(rays32):
+    return np.ascontiguousarray(rays32.astype(np.float64))
+
+
+def _check_closest(ctx, tris, rays, prim_ref, t_ref, max_ties=0):
+    hits = ctx.trace_closest(rays)
+    ties = np.nonzero(hits["prim"] != prim_ref)[0]
+    for i in ties:      # only genuine exact-t ties may differ (own-built tree)
+        r = rays[i].astype(np.float64)
+        ok, d, _ = ob.ray_init(r[:3], r[3:6])
+        hit, t_other, _, _ = ob.triangle_intersect(tris[hits["prim"][i]], r[:3], d, r[7])
+        assert hit and t_other == t_ref[i], "ray %d: wrong primitive" % i
+    assert len(ties) <= max_ties
+    h = prim_ref >= 0
+    assert np.allclose(hits["t"][h], t_ref[h], rtol=T_RTOL, atol=0)
+    assert (hits["t"][~h] == 0).all()
+    # float64 entry point on the same rays: t bit-exact
+    h64 = ctx.trace_closest(_as64(rays))
+    same = h64["prim"] == prim_ref
+    assert same.sum() >= len(rays) - max_ties
+    assert np.array_equal(h64["t"][same & h], t_ref[same & h])
+    return hits
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("max_leaf", [1, 3])
+def test_golden_torus(gpu_ctx, golden_torus, variant, max_leaf):
+    g = golden_torus
+    gpu_ctx.set_option("trace_variant", variant)
+    gpu_ctx.set_triangles(g["tris"])
+    gpu_ctx.build(max_leaf_tris=max_leaf)
+    _check_closest(gpu_ctx, g["tris"], g["rays"], g["prim"], g["t"])
+    assert np.array_equal(gpu_ctx.trace_any(g["any_rays"]), g["occluded"])
+    h64 = gpu_ctx.trace_closest(g["rays64"])
+    assert np.array_equal(h64["prim"], g["prim64"]) and np.array_equal(h64["t"], g["t64"])
+    assert np.array_equal(gpu_ctx.trace_any(_as64(g["any_rays"])), g["occluded"])
+    gpu_ctx.set_option("trace_variant", 1)
+
+
+def test_golden_cube_own_and_imported_tree(gpu_ctx, golden_cube):
+    g = golden_cube
+    gpu_ctx.set_triangles(g["tris"])
+    gpu_ctx.build()
+    _check_closest(gpu_ctx, g["tris"], g["rays"], g["prim"], g["t"])
+    gpu_ctx.import_binary(g["bvh_nodes"])
+    _check_closest(gpu_ctx, g["tris"], g["rays"], g["prim"], g["t"])
+    assert np.array_equal(gpu_ctx.trace_any(g["any_rays"]), g["occluded"])
+
+
+def test_golden_f64_vertices(gpu_ctx, golden_f64verts):
+    g = golden_f64verts
+    gpu_ctx.set_triangles(g["tris"])
+    gpu_ctx.build()
+    assert gpu_ctx.stats()["tri_format"] == 1
+    _check_closest(gpu_ctx, g["tris"], g["rays"], g["prim"], g["t"])
+
+
+def test_medium_torus_vs_oracle_with_import(gpu_ctx):
+    v, f = scenes.torus_mesh(200, 100)
+    tris = scenes.mesh_triangles(v, f)
+    rays = np.concatenate([scenes.incoherent_rays(60000, v.min(0), v.max(0), seed=3), scenes.primary_rays(128, 128)], 0)
+    nodes = ob.bvh_build(tris)
+    p0, t0, _, _ = ob.trace_closest(nodes, tris, rays)
+    gpu_ctx.set_triangles(tris)
+    gpu_ctx.build()
+    _check_closest(gpu_ctx, tris, rays, p0, t0, max_ties=32)     # diagonal primary rays: genuine ties
+    gpu_ctx.import_binary(nodes.view(capi.IMPORT_NODE))
+    _check_closest(gpu_ctx, tris, rays, p0, t0, max_ties=0)      # imported tree: reference tie order
+    anyr = scenes.incoherent_rays(40000, v.min(0), v.max(0), seed=4, anyhit=True)
+    assert np.array_equal(gpu_ctx.trace_any(anyr), ob.trace_any(nodes, tris, anyr))
+
+
+def test_edge_cases(gpu_ctx, golden_torus):
+    g = golden_torus
+    gpu_ctx.set_triangles(g["tris"])
+    gpu_ctx.build()
+    # empty batch and ragged sizes (not a multiple of the warp / block size)
+    assert len(gpu_ctx.trace_closest(np.zeros((0, 8), np.float32))) == 0
+    for n in (1, 31, 33, 1000):
+        h = gpu_ctx.trace_closest(g["rays"][:n])
+        assert np.array_equal(h["prim"], g["prim"][:n])
+    # zero-direction rays miss (the reference aborts there); tmax exactly at the hit distance
+    rays = g["rays"][:2000].copy()
+    hit = g["prim"][:2000] >= 0
+    rays[hit, 7] = g["t"][:2000][hit].astype(np.float32)
+    rays[::5, 3:6] = 0
+    nodes = ob.bvh_build(g["tris"])
+    p0, t0, _, _ = ob.trace_closest(nodes, g["tris"], rays)
+    h = gpu_ctx.trace_closest(rays)
+    assert np.array_equal(h["prim"], p0)
+    assert (h["prim"][::5] == -1).all()
+    # far-away origins exercise the re-origined culling ray
+    rng = np.random.default_rng(1)
+    far = np.zeros((4000, 8), np.float32)
+    far[:, :3] = rng.uniform(-1, 1, (4000, 3)) * 1e4
+    far[:, 3:6] = -far[:, :3] + rng.normal(size=(4000, 3)) * 0.5
+    far[:, 7] = 1e32
+    p0, t0, _, _ = ob.trace_closest(nodes, g["tris"], far)
+    h = gpu_ctx.trace_closest(far)
+    assert np.array_equal(h["prim"], p0) and (p0 >= 0).sum() > 100
+
+
+def test_empty_scene_and_errors(gpu_ctx):
+    gpu_ctx.set_triangles(np.zeros((0, 9)))
+    gpu_ctx.build()
+    rays = scenes.incoherent_rays(100, [-1, -1, -1], [1, 1, 1])
+    assert (gpu_ctx.trace_closest(rays)["prim"] == -1).all()
+    assert (gpu_ctx.trace_any(rays) == 0).all()
+    gpu_ctx.set_triangles(np.array([[0, 0, 0, 1, 0, 0, 0, 1, 0]], dtype=np.float64))
+    with pytest.raises(capi.SpbError):      # trace before build
+        gpu_ctx.trace_closest(rays)
+    with pytest.raises(capi.SpbError):
+        gpu_ctx.set_option("no_such_option", 1)
+
+
+def test_device_resident_path_and_counters(gpu_ctx, golden_torus):
+    g = golden_torus
+    gpu_ctx.set_triangles(g["tris"])
+    gpu_ctx.build()
+    n = len(g["rays"])
+    d_rays = gpu_ctx.dev_alloc(n * 32)
+    d_hits = gpu_ctx.dev_alloc(n * 16)
+    gpu_ctx.dev_upload(d_rays, g["rays"])
+    gpu_ctx.set_option("counters", 1)
+    before = gpu_ctx.counters()
+    gpu_ctx.trace_closest_dev(d_rays, n, d_hits)
+    after = gpu_ctx.counters()
+    gpu_ctx.set_option("counters", 0)
+    hits = np.empty(n, dtype=capi.HIT)
+    gpu_ctx.dev_download(hits, d_hits)
+    assert np.array_equal(hits["prim"], g["prim"])
+    assert after["kernel_launches"] == before["kernel_launches"] + 1
+    assert after["last_kernel_ms"] > 0 and after["node_visits"] > before["node_visits"]
+    gpu_ctx.dev_free(d_rays); gpu_ctx.dev_free(d_hits)
+
+
+def test_full_size_properties_1m_triangles(gpu_ctx):
+    """BASELINE config 2 geometry (1M-triangle torus) with size-independent properties:
+    a strided subset against the oracle, hit points lie on the mesh, closest t never exceeds the
+    any-hit witness, and re-tracing with tmax just below t finds nothing closer."""
+    v, f = scenes.torus_mesh(1000, 500)
+    tris = scenes.mesh_triangles(v, f)
+    gpu_ctx.set_triangles(tris)
+    gpu_ctx.build()
+    n = 1 << 20
+    rays = scenes.incoherent_rays(n, v.min(0), v.max(0), seed=2)
+    hits = gpu_ctx.trace_closest(rays)
+    sub = slice(0, n, 64)
+    nodes = ob.bvh_build(tris)
+    p0, t0, _, _ = ob.trace_closest(nodes, tris, rays[sub])
+    assert np.array_equal(hits["prim"][sub], p0)
+    h = p0 >= 0
+    assert np.allclose(hits["t"][sub][h], t0[h], rtol=T_RTOL, atol=0)
+    # idempotence / minimality: shrinking tmax below the closest hit leaves no hit
+    hit = hits["prim"] >= 0
+    r2 = rays[hit][:200000].copy()
+    r2[:, 7] = hits["t"][hit][:200000] * np.float32(1 - 1e-4)
+    assert (gpu_ctx.trace_closest(r2)["prim"] == -1).all()
+    assert (gpu_ctx.trace_any(r2) == 0).all()
+    # any-hit agrees with closest-hit existence on the same rays
+    assert np.array_equal(gpu_ctx.trace_any(rays[:200000]), (hits["prim"][:200000] >= 0).astype(np.uint8))

@@ -1,0 +1,135 @@
+"""Host build (g++) of the product's builder + per-ray traversal (tests/emul) against the oracle:
+node encoding, octant ordering, stack handling, conservative culling and the exact triangle test,
+checked without a GPU.  The CUDA kernels inline the same trace_core.h; tests/test_trace_gpu.py
+repeats these comparisons through the C ABI on the device."""
+import numpy as np
+import pytest
+
+from oracle import binding as ob
+from spica_b200 import scenes
+from tests.emul import Emul
+
+
+def _cmp(e, tris, rays, nodes=None, max_ties=0):
+    """Bit-exact (prim, t) against the oracle. With an own-built tree an EXACT tie in t between
+    two triangles may resolve to the other triangle (lower index wins here; the reference's winner
+    depends on its tree): such rays are counted, verified to be genuine ties, and bounded."""
+    nodes = ob.bvh_build(tris) if nodes is None else nodes
+    p0, t0, u0, v0 = ob.trace_closest(nodes, tris, rays)
+    p, t, u, v = e.trace(rays)
+    assert np.array_equal(t, t0)                      # the deciding arithmetic is the reference's
+    ties = verify_ties(tris, rays, p, p0, t0)
+    assert ties <= max_ties, "%d exact-tie rays" % ties
+    same = p == p0
+    assert np.allclose(u[same], u0[same], atol=1e-6) and np.allclose(v[same], v0[same], atol=1e-6)
+    return ties
+
+
+def verify_ties(tris, rays, p, p0, t0):
+    bad = np.nonzero(p != p0)[0]
+    for i in bad:
+        assert p[i] >= 0 and p0[i] >= 0
+        r = rays[i].astype(np.float64)
+        ok, d, _ = ob.ray_init(r[:3], r[3:6])
+        hit, t_other, _, _ = ob.triangle_intersect(tris[p[i]], r[:3], d, r[7])
+        assert hit and t_other == t0[i], "ray %d: different primitive without an exact tie" % i
+    return len(bad)
+
+
+@pytest.mark.parametrize("max_leaf", [1, 2, 3])
+def test_golden_torus(golden_torus, max_leaf):
+    g = golden_torus
+    e = Emul(g["tris"], max_leaf=max_leaf)
+    assert e.tri_format == 0
+    p, t, _, _ = e.trace(g["rays"])
+    assert np.array_equal(p, g["prim"]) and np.array_equal(t, g["t"])
+    occ, _, _, _ = e.trace(g["any_rays"], any_hit=True)
+    assert np.array_equal((occ >= 0).astype(np.uint8), g["occluded"])
+    p, t, _, _ = e.trace(g["rays64"])
+    assert np.array_equal(p, g["prim64"]) and np.array_equal(t, g["t64"])
+
+
+def test_golden_cube_and_import(golden_cube):
+    g = golden_cube
+    for e in (Emul(g["tris"]), Emul(g["tris"], import_nodes=g["bvh_nodes"])):
+        p, t, _, _ = e.trace(g["rays"])
+        assert np.array_equal(p, g["prim"]) and np.array_equal(t, g["t"])
+
+
+def test_golden_f64_vertices(golden_f64verts):
+    g = golden_f64verts
+    e = Emul(g["tris"])
+    assert e.tri_format == 1
+    p, t, _, _ = e.trace(g["rays"])
+    assert np.array_equal(p, g["prim"]) and np.array_equal(t, g["t"])
+
+
+def test_medium_torus_incoherent_and_primary():
+    v, f = scenes.torus_mesh(200, 100)
+    tris = scenes.mesh_triangles(v, f)
+    rays = np.concatenate([scenes.incoherent_rays(30000, v.min(0), v.max(0), seed=3),
+                           scenes.primary_rays(96, 96)], 0)
+    e = Emul(tris)
+    # the primary rays on the diagonals |dx| == |dy| pass exactly through mesh edges of this
+    # symmetric torus: a handful of genuine exact ties
+    ties = _cmp(e, tris, rays, max_ties=16)
+    assert e.node_visits < 40
+    # with the reference's tree imported, ties resolve as in the reference: no mismatch at all
+    nodes = ob.bvh_build(tris)
+    assert _cmp(Emul(tris, import_nodes=nodes), tris, rays, nodes=nodes) == 0
+
+
+def test_far_origins_and_axis_aligned_rays():
+    v, f = scenes.torus_mesh(60, 30)
+    tris = scenes.mesh_triangles(v, f)
+    rng = np.random.default_rng(7)
+    n = 6000
+    rays = np.zeros((n, 8), np.float32)
+    rays[:, :3] = rng.uniform(-1, 1, (n, 3)) * np.float32(1e4)          # far outside
+    rays[:, 3:6] = -rays[:, :3] + rng.normal(size=(n, 3)).astype(np.float32) * 0.5
+    rays[:, 7] = 1e32
+    ax = np.zeros((600, 8), np.float32)                                    # zero direction components
+    ax[:, :3] = rng.uniform(-1.5, 1.5, (600, 3))
+    ax[np.arange(600), 3 + (np.arange(600) % 3)] = np.where(np.arange(600) % 2, 1.0, -1.0)
+    ax[:, 7] = 1e32
+    e = Emul(tris)
+    _cmp(e, tris, np.concatenate([rays, ax], 0))
+
+
+def test_tmax_limits_and_zero_direction(golden_torus):
+    g = golden_torus
+    rays = g["rays"][:3000].copy()
+    t_ref = g["t"][:3000]
+    hit = g["prim"][:3000] >= 0
+    # tmax exactly at, just below and just above the reference t (as float32)
+    rays[hit, 7] = t_ref[hit].astype(np.float32)
+    rays[::7, 3:6] = 0.0
+    e = Emul(g["tris"])
+    _cmp(e, g["tris"], rays)
+
+
+def test_duplicate_triangles_tie_break():
+    # exact-t ties: two coincident triangles. Imported tree -> the reference's winner (leftmost
+    # leaf); own tree -> lower primitive index.
+    base = np.array([[0, 0, 0, 1, 0, 0, 0, 1, 0]], dtype=np.float64)
+    far = np.array([[0, 0, -1, 1, 0, -1, 0, 1, -1]], dtype=np.float64)
+    tris = np.concatenate([far, base, base, base + 5.0], 0)
+    rays = np.array([[0.25, 0.25, 1, 0, 0, -1, 0, 1e32]], dtype=np.float32)
+    nodes = ob.bvh_build(tris)
+    p_ref, t_ref, _, _ = ob.trace_closest(nodes, tris, rays)
+    p_imp, t_imp, _, _ = Emul(tris, import_nodes=nodes).trace(rays)
+    assert p_imp[0] == p_ref[0] and t_imp[0] == t_ref[0] == 1.0
+    p_own, _, _, _ = Emul(tris).trace(rays)
+    assert p_own[0] == 1
+
+
+def test_degenerate_inputs():
+    # all centroids identical, zero-area triangles, a single triangle
+    one = np.array([[0, 0, 0, 1, 0, 0, 0, 1, 0]], dtype=np.float64)
+    stack = np.repeat(one, 20, 0)
+    rays = np.array([[0.25, 0.25, 1, 0, 0, -1, 0, 1e32], [3, 3, 1, 0, 0, -1, 0, 1e32]], dtype=np.float32)
+    for tris in (one, stack, np.concatenate([one, np.zeros((3, 9))], 0)):
+        e = Emul(tris)
+        p, t, _, _ = e.trace(rays)
+        assert p[0] >= 0 and t[0] == 1.0 and p[1] == -1
+    assert Emul(stack).trace(rays)[0][0] == 0          # lowest index among 20 exact ties
