@@ -67,12 +67,105 @@ int spb_version(void);
 
 /* World-space triangle soup, 9 doubles per triangle (p0, p1, p2), exactly the points_ the
  * reference's Triangle stores after applying objectToWorld (core/triangle.cc:17-22).
- * normals (9 floats per triangle, per-vertex, may be NULL = face normal; core/triangle.cc:25-30),
- * material_id / light_id (per triangle, may be NULL = 0 / -1) are only used by spb_render.
+ * normals (9 floats per triangle, per-vertex, world space, may be NULL = face normal;
+ * core/triangle.cc:25-30,40-42), uvs (6 floats per triangle, may be NULL = all zero; core/triangle.cc:64),
+ * material_id / light_id (per triangle, may be NULL = 0 / -1; index into spb_scene_set_materials /
+ * spb_scene_set_lights) are only used by spb_render_*.
  * Replaces: the std::vector<std::shared_ptr<Primitive>> handed to the accelerator factory
  * (core/cobject.h:66-75, core/accelerator.h:26-27). */
-int spb_scene_set_triangles(spb_ctx* ctx, const double* verts, const float* normals,
+int spb_scene_set_triangles(spb_ctx* ctx, const double* verts, const float* normals, const float* uvs,
                             const int32_t* material_id, const int32_t* light_id, int64_t n_tris);
+
+/* ---- materials, lights (device PODs of the reference's bsdf / emitter plugins) ------------------ */
+
+enum {
+    SPB_MAT_NONE = -1,            /* no BSDF: the path passes straight through (integrators/path/path.cc:71-75) */
+    SPB_MAT_DIFFUSE = 0,          /* bsdfs/diffuse.cc:23-32      -> LambertianReflection (core/bxdf.cc:34-58)   */
+    SPB_MAT_DIELECTRIC = 1,       /* bsdfs/dielectric.cc:30-42   -> FresnelSpecular (core/bxdf.cc:156-248)      */
+    SPB_MAT_ROUGHCONDUCTOR = 2,   /* bsdfs/roughconductor.cc:38-75 -> MicrofacetReflection (core/bxdf.cc:255-297) */
+    SPB_MAT_ROUGHDIELECTRIC = 3,  /* bsdfs/roughdielectric.cc:41-83 -> MicrofacetTransmission (core/bxdf.cc:304-424) */
+    SPB_MAT_CONDUCTOR = 4         /* alpha == 0 roughconductor / bsdfs/conductor.cc -> SpecularReflection        */
+};
+enum { SPB_DISTR_BECKMANN = 0, SPB_DISTR_GGX = 1 };
+
+typedef struct spb_material {
+    int32_t type;           /* SPB_MAT_*                                                              */
+    int32_t distribution;   /* SPB_DISTR_* (rough materials; default "beckmann")                       */
+    float   kr[3];          /* diffuse: reflectance; dielectrics: specularReflectance; conductors: 1   */
+    float   kt[3];          /* dielectrics: specularTransmittance                                      */
+    float   eta[3];         /* conductors: eta (rgb); dielectrics: intIOR in eta[0] (extIOR is 1.0)    */
+    float   k[3];           /* conductors: absorption k (rgb)                                          */
+    float   alpha_u, alpha_v; /* microfacet roughness (no remap, bsdfs/roughconductor.cc:33)           */
+} spb_material;             /* 64 B */
+int spb_scene_set_materials(spb_ctx* ctx, const spb_material* mats, int32_t n);
+
+enum { SPB_LIGHT_AREA = 0, SPB_LIGHT_ENVMAP = 1 };
+/* One entry per light in Scene::lights() order (spica/sceneparser.cc:168-179: ONE AreaLight per
+ * emitter triangle; lights/area.cc).  The list order only matters for the uniform light pick
+ * (core/mis.cc:27).  An SPB_LIGHT_ENVMAP entry refers to the map given to spb_scene_set_envmap. */
+typedef struct spb_light {
+    int32_t type;           /* SPB_LIGHT_*                                                            */
+    int32_t prim;           /* area: the emitter triangle (index into the triangle array)              */
+    float   radiance[3];    /* area: Lemit                                                             */
+    float   pad_;
+} spb_light;                /* 24 B */
+int spb_scene_set_lights(spb_ctx* ctx, const spb_light* lights, int32_t n);
+
+/* lat-long environment map (lights/envmap.cc:17-58): rgb = w*h*3 floats, row-major, already
+ * multiplied by nothing (scale is applied here); light_to_world = the XML toWorld matrix (row-major
+ * 4x4; the reference transposes it, envmap.cc:19); world_radius bounds shadow rays (envmap.cc:75). */
+int spb_scene_set_envmap(spb_ctx* ctx, const float* rgb, int32_t w, int32_t h, const double light_to_world[16],
+                         double scale, const double world_center[3], double world_radius);
+
+/* ---- the path-tracing integrator ------------------------------------------------------------------ */
+
+enum { SPB_FILTER_BOX = 0, SPB_FILTER_TENT = 1, SPB_FILTER_GAUSSIAN = 2 };
+
+/* Everything SamplerIntegrator::render (core/integrator.cc:46-110) + PathIntegrator::Li
+ * (integrators/path/path.cc:42-125) read from the camera / film / sampler / params objects,
+ * resolved once into a POD. Matrices are row-major 4x4 doubles. */
+typedef struct spb_render_desc {
+    int32_t width, height;          /* film resolution (films/hdrfilm.cc:15-18)                        */
+    int32_t max_depth;              /* "maxDepth", default 16 (spica/sceneparser.cc:63)                */
+    int32_t filter;                 /* SPB_FILTER_* ; weight of the sample's own pixel (core/film.cc:65-74) */
+    double  filter_radius[2];       /* filters: box.cc:22, tent.cc:27, gaussian.cc:34                    */
+    double  filter_sigma;
+    double  camera_to_world[16];    /* cameras/perspective.cc:53-74, core/camera.cc:20-38              */
+    double  raster_to_camera[16];
+    double  lens_radius, focal_distance;
+    uint64_t seed;                  /* counter-based sampler key (replaces time(0) seeding, core/integrator.cc:51,71) */
+    int32_t rr_start_bounce;        /* Russian roulette applies when bounces > this; reference: 3 (path.cc:117) */
+    int32_t reserved_;
+} spb_render_desc;
+
+/* Allocates (or re-uses) and clears the device film and the wavefront queues. */
+int spb_render_begin(spb_ctx* ctx, const spb_render_desc* desc);
+/* Renders sample indices first, first+stride, ... (count of them) for every pixel and accumulates
+ * them into the device film: one iteration of the spp loop of SamplerIntegrator::render per index.
+ * A rank of an N-GPU job passes (first = rank, stride = N). Stream-ordered; returns after the
+ * work is enqueued and complete (synchronous). */
+int spb_render_samples(spb_ctx* ctx, int32_t first, int32_t count, int32_t stride);
+/* Raw accumulators, height x width x 4 floats {sum w*r, sum w*g, sum w*b, sum w}, pixel (x, y) as
+ * Film::addPixel indexed them (the horizontal flip of core/integrator.cc:88 already applied). */
+int spb_film_read(spb_ctx* ctx, float* rgbw);
+/* Film::save's normalisation (core/film.cc:23-29): rgb = sum / (wsum + 1e-12); height x width x 3. */
+int spb_film_resolve(spb_ctx* ctx, float* rgb);
+/* Adds raw accumulators (same layout as spb_film_read) into the device film: resume / merge. */
+int spb_film_add(spb_ctx* ctx, const float* rgbw);
+
+typedef struct spb_render_stats {
+    int64_t paths, rays_closest, rays_shadow, rays_mis;   /* rays traced since spb_render_begin   */
+    int64_t kernel_launches;
+    double  render_ms;                                    /* device time of all spb_render_samples */
+} spb_render_stats;
+int spb_render_get_stats(spb_ctx* ctx, spb_render_stats* out);
+
+/* ---- multi-GPU: one context per GPU, films summed with one NCCL all-reduce over NVLink ----------- */
+#define SPB_COMM_ID_BYTES 128
+int spb_comm_get_unique_id(char id[SPB_COMM_ID_BYTES]);                 /* rank 0; ship to the others */
+int spb_comm_init(spb_ctx* ctx, const char id[SPB_COMM_ID_BYTES], int32_t n_ranks, int32_t rank);
+int spb_film_allreduce(spb_ctx* ctx);   /* ncclAllReduce(sum, float32) of the RGBW film, in place     */
+int spb_comm_destroy(spb_ctx* ctx);
 
 /* ---- acceleration structure ---------------------------------------------------------------- */
 
@@ -137,7 +230,8 @@ typedef struct spb_counters {
 int spb_get_counters(spb_ctx* ctx, spb_counters* out);
 
 /* Tunables: "counters" (0/1), "trace_block" (threads per CTA), "trace_ctas_per_sm",
- * "trace_variant" (kernel variant id). Unknown names return SPB_ERR_INVALID. */
+ * "trace_variant" (kernel variant id), "chunk_rays" (rays per pipelined chunk of the host-buffer
+ * calls), "wave_slots" (paths in flight per integrator wave). Unknown names return SPB_ERR_INVALID. */
 int spb_set_option(spb_ctx* ctx, const char* name, int64_t value);
 
 /* raw device memory helpers so that a host without the CUDA runtime (a plugin, ctypes) can keep

@@ -38,6 +38,33 @@ class Counters(C.Structure):
                 ("node_visits", C.c_int64), ("tri_tests", C.c_int64)]
 
 
+class Material(C.Structure):
+    _fields_ = [("type", C.c_int32), ("distribution", C.c_int32), ("kr", C.c_float * 3), ("kt", C.c_float * 3),
+                ("eta", C.c_float * 3), ("k", C.c_float * 3), ("alpha_u", C.c_float), ("alpha_v", C.c_float)]
+
+
+class Light(C.Structure):
+    _fields_ = [("type", C.c_int32), ("prim", C.c_int32), ("radiance", C.c_float * 3), ("pad_", C.c_float)]
+
+
+class RenderDesc(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("max_depth", C.c_int32), ("filter", C.c_int32),
+                ("filter_radius", C.c_double * 2), ("filter_sigma", C.c_double),
+                ("camera_to_world", C.c_double * 16), ("raster_to_camera", C.c_double * 16),
+                ("lens_radius", C.c_double), ("focal_distance", C.c_double), ("seed", C.c_uint64),
+                ("rr_start_bounce", C.c_int32), ("reserved_", C.c_int32)]
+
+
+class RenderStats(C.Structure):
+    _fields_ = [("paths", C.c_int64), ("rays_closest", C.c_int64), ("rays_shadow", C.c_int64),
+                ("rays_mis", C.c_int64), ("kernel_launches", C.c_int64), ("render_ms", C.c_double)]
+
+
+MAT_TYPES = {"none": -1, "diffuse": 0, "dielectric": 1, "roughconductor": 2, "roughdielectric": 3, "conductor": 4}
+FILTERS = {"box": 0, "tent": 1, "gaussian": 2}
+assert C.sizeof(Material) == 64 and C.sizeof(Light) == 24
+
+
 class SpbError(RuntimeError):
     pass
 
@@ -52,6 +79,9 @@ SYMBOLS = [
     "spb_trace_closest_dev", "spb_trace_any_dev", "spb_get_counters", "spb_set_option",
     "spb_dev_alloc", "spb_dev_free", "spb_dev_upload", "spb_dev_download", "spb_dev_sync",
     "spb_ctx_stream",
+    "spb_scene_set_materials", "spb_scene_set_lights", "spb_scene_set_envmap",
+    "spb_render_begin", "spb_render_samples", "spb_film_read", "spb_film_resolve", "spb_film_add",
+    "spb_render_get_stats", "spb_comm_get_unique_id", "spb_comm_init", "spb_film_allreduce", "spb_comm_destroy",
 ]
 
 
@@ -68,7 +98,7 @@ def load():
     L.spb_last_error.restype = C.c_char_p; L.spb_last_error.argtypes = [vp]
     L.spb_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
     L.spb_ctx_destroy.argtypes = [vp]; L.spb_ctx_destroy.restype = None
-    L.spb_scene_set_triangles.argtypes = [vp, vp, vp, vp, vp, i64]
+    L.spb_scene_set_triangles.argtypes = [vp, vp, vp, vp, vp, vp, i64]
     L.spb_bvh_build.argtypes = [vp, C.POINTER(BuildOpts)]
     L.spb_bvh_import_binary.argtypes = [vp, vp, i64, i32]
     L.spb_bvh_get_stats.argtypes = [vp, C.POINTER(BvhStats)]
@@ -83,6 +113,19 @@ def load():
     L.spb_dev_download.argtypes = [vp, vp, vp, C.c_size_t]
     L.spb_dev_sync.argtypes = [vp]
     L.spb_ctx_stream.argtypes = [vp]; L.spb_ctx_stream.restype = vp
+    L.spb_scene_set_materials.argtypes = [vp, C.POINTER(Material), i32]
+    L.spb_scene_set_lights.argtypes = [vp, C.POINTER(Light), i32]
+    L.spb_scene_set_envmap.argtypes = [vp, vp, i32, i32, vp, C.c_double, vp, C.c_double]
+    L.spb_render_begin.argtypes = [vp, C.POINTER(RenderDesc)]
+    L.spb_render_samples.argtypes = [vp, i32, i32, i32]
+    L.spb_film_read.argtypes = [vp, vp]
+    L.spb_film_resolve.argtypes = [vp, vp]
+    L.spb_film_add.argtypes = [vp, vp]
+    L.spb_render_get_stats.argtypes = [vp, C.POINTER(RenderStats)]
+    L.spb_comm_get_unique_id.argtypes = [C.c_char_p]
+    L.spb_comm_init.argtypes = [vp, C.c_char_p, i32, i32]
+    L.spb_film_allreduce.argtypes = [vp]
+    L.spb_comm_destroy.argtypes = [vp]
     _lib = L
     return L
 
@@ -125,13 +168,14 @@ class Context:
             raise SpbError("spica_b200 error %d: %s" % (rc, self.L.spb_last_error(self.h).decode()))
 
     # ---- scene / BVH
-    def set_triangles(self, tris, normals=None, material_id=None, light_id=None):
+    def set_triangles(self, tris, normals=None, material_id=None, light_id=None, uvs=None):
         tris = np.ascontiguousarray(tris, dtype=np.float64).reshape(-1, 9)
         n = tris.shape[0]
         nm = None if normals is None else np.ascontiguousarray(normals, dtype=np.float32).reshape(n, 9)
+        uv = None if uvs is None else np.ascontiguousarray(uvs, dtype=np.float32).reshape(n, 6)
         mi = None if material_id is None else np.ascontiguousarray(material_id, dtype=np.int32)
         li = None if light_id is None else np.ascontiguousarray(light_id, dtype=np.int32)
-        self._check(self.L.spb_scene_set_triangles(self.h, _ptr(tris), _ptr(nm), _ptr(mi), _ptr(li), n))
+        self._check(self.L.spb_scene_set_triangles(self.h, _ptr(tris), _ptr(nm), _ptr(uv), _ptr(mi), _ptr(li), n))
 
     def build(self, max_leaf_tris=3, sah_bins=32, builder=0):
         o = BuildOpts(builder, max_leaf_tris, sah_bins, 0)
@@ -208,3 +252,112 @@ class Context:
 
     def sync(self):
         self._check(self.L.spb_dev_sync(self.h))
+
+    # ---- the path tracer
+    def set_materials(self, mats):
+        """mats: list of dicts {type, reflectance | specularReflectance/specularTransmittance/intIOR |
+        eta/k/alpha/distribution} using the reference's XML parameter names."""
+        arr = (Material * max(len(mats), 1))()
+        for i, m in enumerate(mats):
+            a = arr[i]
+            a.type = MAT_TYPES[m["type"]]
+            a.distribution = 1 if m.get("distribution", "beckmann") == "ggx" else 0
+            kr = m.get("reflectance", m.get("specularReflectance", (1.0, 1.0, 1.0)))
+            kt = m.get("specularTransmittance", (1.0, 1.0, 1.0))
+            default_ior = 1.3333 if m["type"] == "roughdielectric" else 1.333
+            eta = m.get("eta", (m.get("intIOR", default_ior),) * 3)
+            k = m.get("k", (0.0, 0.0, 0.0))
+            for j in range(3):
+                a.kr[j] = kr[j]; a.kt[j] = kt[j]; a.eta[j] = eta[j]; a.k[j] = k[j]
+            a.alpha_u = a.alpha_v = m.get("alpha", 0.1)
+        self._check(self.L.spb_scene_set_materials(self.h, arr, len(mats)))
+
+    def set_lights(self, lights, envmap_at=None):
+        """lights: list of (prim, (r, g, b)) area lights; envmap_at: list position of an envmap light."""
+        n = len(lights) + (1 if envmap_at is not None else 0)
+        arr = (Light * max(n, 1))()
+        src = list(lights)
+        j = 0
+        for i in range(n):
+            if envmap_at is not None and i == envmap_at:
+                arr[i].type = 1; arr[i].prim = -1
+                continue
+            prim, rad = src[j]; j += 1
+            arr[i].type = 0; arr[i].prim = int(prim)
+            for c in range(3):
+                arr[i].radiance[c] = rad[c]
+        self._check(self.L.spb_scene_set_lights(self.h, arr, n))
+
+    def set_envmap(self, rgb, to_world=None, scale=1.0, center=(0.0, 0.0, 0.0), radius=2.0):
+        rgb = np.ascontiguousarray(rgb, dtype=np.float32)
+        h, w = rgb.shape[:2]
+        m = np.ascontiguousarray(np.eye(4) if to_world is None else to_world, dtype=np.float64)
+        c = np.ascontiguousarray(center, dtype=np.float64)
+        self._check(self.L.spb_scene_set_envmap(self.h, _ptr(rgb), w, h, _ptr(m), float(scale), _ptr(c), float(radius)))
+
+    def render_begin(self, width, height, camera_to_world, raster_to_camera, max_depth=16, seed=0, filter="box",
+                     filter_radius=(1.0, 1.0), filter_sigma=0.5, lens_radius=0.0, focal_distance=50.0, rr_start=3):
+        d = RenderDesc()
+        d.width, d.height, d.max_depth, d.filter = width, height, max_depth, FILTERS[filter]
+        d.filter_radius[0], d.filter_radius[1], d.filter_sigma = filter_radius[0], filter_radius[1], filter_sigma
+        c2w = np.asarray(camera_to_world, dtype=np.float64).reshape(16)
+        r2c = np.asarray(raster_to_camera, dtype=np.float64).reshape(16)
+        for i in range(16):
+            d.camera_to_world[i] = c2w[i]; d.raster_to_camera[i] = r2c[i]
+        d.lens_radius, d.focal_distance, d.seed, d.rr_start_bounce = lens_radius, focal_distance, seed, rr_start
+        self._film_shape = (height, width)
+        self._check(self.L.spb_render_begin(self.h, C.byref(d)))
+
+    def render_samples(self, first, count, stride=1):
+        self._check(self.L.spb_render_samples(self.h, first, count, stride))
+
+    def film_read(self):
+        out = np.empty(self._film_shape + (4,), dtype=np.float32)
+        self._check(self.L.spb_film_read(self.h, _ptr(out)))
+        return out
+
+    def film_resolve(self):
+        out = np.empty(self._film_shape + (3,), dtype=np.float32)
+        self._check(self.L.spb_film_resolve(self.h, _ptr(out)))
+        return out
+
+    def film_add(self, rgbw):
+        rgbw = np.ascontiguousarray(rgbw, dtype=np.float32)
+        assert rgbw.shape == self._film_shape + (4,)
+        self._check(self.L.spb_film_add(self.h, _ptr(rgbw)))
+
+    def render_stats(self):
+        s = RenderStats()
+        self._check(self.L.spb_render_get_stats(self.h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in s._fields_}
+
+    def comm_init(self, comm_id, n_ranks, rank):
+        self._check(self.L.spb_comm_init(self.h, comm_id, n_ranks, rank))
+
+    def film_allreduce(self):
+        self._check(self.L.spb_film_allreduce(self.h))
+
+
+def comm_unique_id():
+    L = load()
+    buf = C.create_string_buffer(128)
+    rc = L.spb_comm_get_unique_id(buf)
+    if rc != 0:
+        raise SpbError("spb_comm_get_unique_id failed: %s" % L.spb_last_error(None).decode())
+    return buf.raw
+
+
+def cornell_render(ctx, width, height, spp, max_depth=8, variant="diffuse", seed=1, first=0, stride=1, begin=True):
+    """Sets up the Cornell scene of spica_b200.scenes on `ctx` and renders `spp` samples per pixel."""
+    from . import scenes
+    if begin:
+        tris, mid, lid, mats, lights = scenes.cornell_arrays(variant)
+        ctx.set_triangles(tris, material_id=mid, light_id=lid)
+        ctx.set_materials(mats)
+        ctx.set_lights(lights)
+        ctx.build()
+        cam = scenes.CORNELL_CAMERA
+        c2w, r2c = scenes.perspective_camera(scenes.look_at(cam["origin"], cam["target"], cam["up"]), cam["fov"], width, height)
+        ctx.render_begin(width, height, c2w, r2c, max_depth=max_depth, seed=seed)
+    ctx.render_samples(first, spp, stride)
+    return ctx.film_resolve()

@@ -129,7 +129,7 @@ void spb_ctx_destroy(spb_ctx* ctx) {
     delete ctx;
 }
 
-int spb_scene_set_triangles(spb_ctx* ctx, const double* verts, const float* normals,
+int spb_scene_set_triangles(spb_ctx* ctx, const double* verts, const float* normals, const float* uvs,
                             const int32_t* material_id, const int32_t* light_id, int64_t n) {
     if (!ctx) return fail(nullptr, SPB_ERR_INVALID, "ctx is NULL");
     if (n < 0 || (n > 0 && !verts)) return fail(ctx, SPB_ERR_INVALID, "spb_scene_set_triangles: bad arguments");
@@ -138,10 +138,12 @@ int spb_scene_set_triangles(spb_ctx* ctx, const double* verts, const float* norm
     ctx->n_tris = n;
     ctx->verts.assign(verts, verts + n * 9);
     if (normals) ctx->normals.assign(normals, normals + n * 9); else ctx->normals.clear();
+    if (uvs) ctx->uvs.assign(uvs, uvs + n * 6); else ctx->uvs.clear();
     if (material_id) ctx->material_id.assign(material_id, material_id + n); else ctx->material_id.assign((size_t)n, 0);
     if (light_id) ctx->light_id.assign(light_id, light_id + n); else ctx->light_id.assign((size_t)n, -1);
     freeBvhDevice(ctx);
     ctx->bin = BinaryBVH();
+    renderSceneChanged(ctx);
     return SPB_OK;
 }
 
@@ -203,6 +205,7 @@ int spb_set_option(spb_ctx* ctx, const char* name, int64_t value) {
         ctx->opt_block = (int)value;
     } else if (n == "trace_ctas_per_sm") ctx->opt_ctas_per_sm = (int)value;
     else if (n == "trace_variant") ctx->opt_variant = (int)value;
+    else if (n == "wave_slots") { if (value < 1024) return fail(ctx, SPB_ERR_INVALID, "wave_slots too small"); ctx->opt_wave_slots = value; }
     else if (n == "chunk_rays") { if (value < 1024) return fail(ctx, SPB_ERR_INVALID, "chunk_rays too small"); ctx->opt_chunk = value; }
     else return fail(ctx, SPB_ERR_INVALID, "spb_set_option: unknown option " + n);
     return SPB_OK;

@@ -10,6 +10,8 @@
 #include "bvh_host.h"
 #include "bvh_layout.h"
 
+namespace spb { struct RenderState; }
+
 struct spb_ctx {
     int device = 0;
     int sm_count = 0;
@@ -21,6 +23,7 @@ struct spb_ctx {
     // host copies of the scene (the builder runs on the host; also the source for re-builds)
     std::vector<double>  verts;          // 9 per triangle
     std::vector<float>   normals;        // 9 per triangle or empty
+    std::vector<float>   uvs;            // 6 per triangle or empty
     std::vector<int32_t> material_id, light_id;
     int64_t n_tris = 0;
 
@@ -46,6 +49,7 @@ struct spb_ctx {
     int opt_ctas_per_sm = 0;             // 0 = occupancy query
     int opt_variant = 1;                 // 0 = one thread per ray, 1 = persistent dynamic fetch
     int64_t opt_chunk = 1 << 21;         // rays per pipelined chunk on the host-buffer path
+    int64_t opt_wave_slots = 1 << 22;    // paths in flight per wave of the integrator
 
     // counters
     double last_kernel_ms = 0.0;
@@ -53,7 +57,7 @@ struct spb_ctx {
     int64_t c_rays = 0, c_nodes = 0, c_tris = 0;
 
     // integrator state lives in integrator.cu
-    struct RenderState* render = nullptr;
+    spb::RenderState* render = nullptr;
 };
 
 namespace spb {
@@ -61,6 +65,7 @@ int  fail(spb_ctx* ctx, int code, const std::string& msg);
 bool cudaOk(spb_ctx* ctx, cudaError_t e, const char* what);
 void setGlobalError(const std::string& msg);
 void renderStateDestroy(spb_ctx* ctx);   // integrator.cu
+void renderSceneChanged(spb_ctx* ctx);   // integrator.cu
 }  // namespace spb
 
 #define SPB_CUDA(ctx, call)                                                      \

@@ -1,0 +1,191 @@
+// sm_100a ray-cast kernels over the 8-wide compressed BVH, shared by the ray-cast entry points
+// (trace.cu) and the wavefront integrator (integrator.cu).
+//
+// K1 trace_closest / K2 trace_any replace BVHAccel::intersectBVH x2 (reference
+// accelerators/bvh.cc:331-387) + Triangle::intersect x2 (core/triangle.cc:98-178) for whole ray
+// batches.
+//
+// The result sink is a small functor passed by value (`Out::store(i, rayState)`), so the
+// integrator fuses its own epilogues (add an unoccluded shadow contribution, add an MIS emission)
+// into the traversal kernel instead of writing hit records to HBM and reading them back.
+//
+// The ray count may live in device memory (`n_dev`): the integrator's queues are filled by the
+// previous kernel and never round-trip through the host.
+//
+// Variant 1 (default) is a persistent-thread kernel: the grid is sized to the machine
+// (SMs x resident CTAs), every warp pulls rays from a global cursor with one warp-aggregated
+// atomic (ballot + popc + shuffle), and lanes whose ray has terminated are refilled while the
+// rest of the warp keeps traversing ("dynamic fetch"), so incoherent rays do not leave the warp
+// mostly idle while its longest ray finishes.  Variant 0 is the plain one-thread-per-ray kernel
+// kept as the measurement baseline.
+#pragma once
+#include <algorithm>
+
+#include "context.h"
+#include "trace_core.h"
+
+namespace spb {
+
+// ---- ray / result records ----------------------------------------------------------------------
+__device__ __forceinline__ uint4 ldStream(const void* p) {
+    uint4 v;
+    asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void stStream(void* p, uint4 v) {
+    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ double u2d(uint32_t lo, uint32_t hi) {
+    return __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+}
+
+__device__ __forceinline__ bool loadRay(const SceneParams& sp, const spb_ray_f32* rays, int64_t i, RayState& r) {
+    const uint4 a = ldStream(rays + i), b = ldStream((const char*)(rays + i) + 16);
+    return rayBegin(sp, (double)__uint_as_float(a.x), (double)__uint_as_float(a.y), (double)__uint_as_float(a.z),
+                    (double)__uint_as_float(a.w), (double)__uint_as_float(b.x), (double)__uint_as_float(b.y),
+                    (double)__uint_as_float(b.w), r);
+}
+__device__ __forceinline__ bool loadRay(const SceneParams& sp, const spb_ray_f64* rays, int64_t i, RayState& r) {
+    const char* p = (const char*)(rays + i);
+    const uint4 a = ldStream(p), b = ldStream(p + 16), c = ldStream(p + 32), d = ldStream(p + 48);
+    return rayBegin(sp, u2d(a.x, a.y), u2d(a.z, a.w), u2d(b.x, b.y), u2d(b.z, b.w), u2d(c.x, c.y), u2d(c.z, c.w),
+                    u2d(d.z, d.w), r);
+}
+
+// ---- result sinks ---------------------------------------------------------------------------------
+struct HitOut {       // spb_hit records (16 B)
+    spb_hit* out;
+    __device__ __forceinline__ void store(int64_t i, const RayState& r) const {
+        const bool hit = r.best_prim >= 0;
+        uint4 v;
+        v.x = __float_as_uint(hit ? (float)r.best_t : 0.0f);
+        v.y = (uint32_t)r.best_prim;
+        v.z = __float_as_uint(r.best_u);
+        v.w = __float_as_uint(r.best_v);
+        stStream(out + i, v);
+    }
+};
+struct HitOut64 {     // spb_hit_f64 records (32 B)
+    spb_hit_f64* out;
+    __device__ __forceinline__ void store(int64_t i, const RayState& r) const {
+        const bool hit = r.best_prim >= 0;
+        const unsigned long long t = (unsigned long long)__double_as_longlong(hit ? r.best_t : 0.0);
+        const unsigned long long u = (unsigned long long)__double_as_longlong((double)r.best_u);
+        const unsigned long long v = (unsigned long long)__double_as_longlong((double)r.best_v);
+        stStream((char*)(out + i), make_uint4((uint32_t)t, (uint32_t)(t >> 32), (uint32_t)u, (uint32_t)(u >> 32)));
+        stStream((char*)(out + i) + 16, make_uint4((uint32_t)v, (uint32_t)(v >> 32), (uint32_t)r.best_prim, 0u));
+    }
+};
+struct OccOut {       // 1 = occluded
+    uint8_t* out;
+    __device__ __forceinline__ void store(int64_t i, const RayState& r) const { out[i] = r.best_prim >= 0 ? 1 : 0; }
+};
+
+// ---- variant 0: one thread per ray ---------------------------------------------------------------
+template <int FMT, bool ANY, bool COUNT, class RayT, class Out>
+__global__ void __launch_bounds__(256) traceSimpleKernel(SceneParams sp, const RayT* __restrict__ rays, int64_t n,
+                                                       Out out, unsigned long long* ctr) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    RayState r;
+    const bool valid = loadRay(sp, rays, i, r);
+    TraceCounters c = {0ull, 0ull};
+    traceRay<FMT, ANY>(sp, r, valid, COUNT ? &c : nullptr);
+    out.store(i, r);
+    if (COUNT) { atomicAdd(ctr + 1, c.nodes); atomicAdd(ctr + 2, c.tris); }
+}
+
+// ---- variant 1: persistent threads, dynamic fetch ------------------------------------------------
+// REFILL_MIN: a warp goes back to the cursor once at least this many lanes are idle.
+// ctr[0] is the global ray cursor (zeroed before the launch).  n_dev, when non-NULL, overrides n.
+template <int FMT, bool ANY, bool COUNT, class RayT, class Out, int REFILL_MIN, int STEPS>
+__global__ void __launch_bounds__(128) tracePersistentKernel(SceneParams sp, const RayT* __restrict__ rays, int64_t n,
+                                                           const uint32_t* __restrict__ n_dev, Out out,
+                                                           unsigned long long* ctr) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    if (n_dev) n = (int64_t)__ldg(n_dev);
+    Traverser<FMT, ANY> tr;
+    RayState r;
+    TraceCounters c = {0ull, 0ull};
+    int64_t mine = -1;
+    bool active = false, exhausted = (n <= 0);
+
+    for (;;) {
+        const unsigned idle = __ballot_sync(full, !active);
+        const int nIdle = __popc(idle);
+        if (!exhausted && (nIdle >= REFILL_MIN || nIdle == 32)) {
+            const int leader = __ffs(idle) - 1;
+            unsigned long long base = 0;
+            if (lane == leader) base = atomicAdd(ctr, (unsigned long long)nIdle);
+            base = __shfl_sync(full, base, leader);
+            if ((int64_t)base + nIdle >= n) exhausted = true;
+            if (!active) {
+                const int64_t idx = (int64_t)base + __popc(idle & ((1u << lane) - 1u));
+                if (idx < n) {
+                    mine = idx;
+                    const bool valid = loadRay(sp, rays, idx, r);
+                    tr.begin(valid);
+                    if (tr.finished) out.store(mine, r);   // trivial miss
+                    else active = true;
+                }
+            }
+        }
+        if (!__any_sync(full, active)) {
+            if (exhausted) break;
+            continue;
+        }
+#pragma unroll 1
+        for (int s = 0; s < STEPS; s++) {
+            if (active) {
+                tr.step(sp, r, COUNT ? &c : nullptr);
+                if (tr.finished) { out.store(mine, r); active = false; }
+            }
+        }
+    }
+    if (COUNT) { atomicAdd(ctr + 1, c.nodes); atomicAdd(ctr + 2, c.tris); }
+}
+
+// ---- launch ------------------------------------------------------------------------------------
+// `cursor` points at 4 x u64: [0] the ray cursor (zeroed here), [1] node visits, [2] triangle tests.
+template <int FMT, bool ANY, bool COUNT, class RayT, class Out>
+static int launchTraceTyped(spb_ctx* ctx, const RayT* d_rays, int64_t n, const uint32_t* n_dev, Out out,
+                            unsigned long long* cursor, cudaStream_t st) {
+    if (n <= 0) return SPB_OK;     // n is the capacity bound when n_dev is given
+    if (COUNT) { SPB_CUDA(ctx, cudaMemsetAsync(cursor, 0, 4 * sizeof(unsigned long long), st)); }
+    else { SPB_CUDA(ctx, cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), st)); }
+    if (ctx->opt_variant == 0 && !n_dev) {
+        const int block = std::min(ctx->opt_block, 256);
+        const int64_t grid = (n + block - 1) / block;
+        traceSimpleKernel<FMT, ANY, COUNT, RayT, Out><<<(unsigned)grid, block, 0, st>>>(ctx->sp, d_rays, n, out, cursor);
+    } else {
+        auto kern = tracePersistentKernel<FMT, ANY, COUNT, RayT, Out, 8, 2>;
+        const int block = 128;
+        int perSm = ctx->opt_ctas_per_sm;
+        if (perSm <= 0) {
+            SPB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kern, block, 0));
+            if (perSm < 1) perSm = 1;
+        }
+        int64_t grid = (int64_t)ctx->sm_count * perSm;
+        const int64_t need = (n + block - 1) / block;
+        if (grid > need) grid = need;
+        kern<<<(unsigned)grid, block, 0, st>>>(ctx->sp, d_rays, n, n_dev, out, cursor);
+    }
+    SPB_CUDA(ctx, cudaGetLastError());
+    ctx->kernel_launches++;
+    return SPB_OK;
+}
+
+template <bool ANY, class RayT, class Out>
+static int launchTrace(spb_ctx* ctx, const RayT* d_rays, int64_t n, const uint32_t* n_dev, Out out,
+                       unsigned long long* cursor, cudaStream_t st) {
+    const int fmt = ctx->sp.tri_format;
+    if (ctx->opt_counters) {
+        return fmt == 0 ? launchTraceTyped<0, ANY, true>(ctx, d_rays, n, n_dev, out, cursor, st)
+                        : launchTraceTyped<1, ANY, true>(ctx, d_rays, n, n_dev, out, cursor, st);
+    }
+    return fmt == 0 ? launchTraceTyped<0, ANY, false>(ctx, d_rays, n, n_dev, out, cursor, st)
+                    : launchTraceTyped<1, ANY, false>(ctx, d_rays, n, n_dev, out, cursor, st);
+}
+
+}  // namespace spb

@@ -157,3 +157,216 @@ def cube_triangles():
     for a, b, c, d in quads:
         f += [(a, b, c), (a, c, d)]
     return v, np.array(f, dtype=np.int32)
+
+
+# ---------------------------------------------------------------------------------------------
+# Cornell-box scenes (BASELINE.json configs 0, 2, 3): geometry as quads -> OBJ files + a
+# Mitsuba-0.5-style XML the reference's parser accepts (spica/sceneparser.cc:190-334), and the
+# same scene as flat arrays for the C ABI.
+# ---------------------------------------------------------------------------------------------
+
+def _quad(a, b, c, d):
+    return [np.asarray(p, dtype=np.float64) for p in (a, b, c, d)]
+
+
+def _box_quads(cx, cz, sx, sy, sz, y0, angle):
+    """Axis-aligned box of half sizes (sx, sz), height sy standing on y0, rotated about +y by `angle`;
+    outward-facing quads (5: no bottom)."""
+    ca, sa = np.cos(angle), np.sin(angle)
+
+    def P(x, y, z):
+        return (cx + ca * x + sa * z, y0 + y, cz - sa * x + ca * z)
+    x0, x1, z0, z1, y1 = -sx, sx, -sz, sz, sy
+    return [
+        _quad(P(x0, y1, z0), P(x0, y1, z1), P(x1, y1, z1), P(x1, y1, z0)),   # top (+y)
+        _quad(P(x0, 0, z1), P(x1, 0, z1), P(x1, y1, z1), P(x0, y1, z1)),     # +z
+        _quad(P(x1, 0, z0), P(x0, 0, z0), P(x0, y1, z0), P(x1, y1, z0)),     # -z
+        _quad(P(x1, 0, z1), P(x1, 0, z0), P(x1, y1, z0), P(x1, y1, z1)),     # +x
+        _quad(P(x0, 0, z0), P(x0, 0, z1), P(x0, y1, z1), P(x0, y1, z0)),     # -x
+    ]
+
+
+def cornell_parts(variant="diffuse"):
+    """List of parts: (name, bsdf id, quads, radiance or None).
+
+    variant "diffuse": BASELINE config 0 / 2 (all Lambertian + one emitter quad);
+    variant "glossy" : config 3 (tall box rough conductor, short box dielectric)."""
+    parts = [
+        ("floor", "white", [_quad((-1, -1, -1), (-1, -1, 1), (1, -1, 1), (1, -1, -1))], None),
+        ("ceiling", "white", [_quad((-1, 1, -1), (1, 1, -1), (1, 1, 1), (-1, 1, 1))], None),
+        ("back", "white", [_quad((-1, -1, -1), (1, -1, -1), (1, 1, -1), (-1, 1, -1))], None),
+        ("left", "red", [_quad((-1, -1, -1), (-1, 1, -1), (-1, 1, 1), (-1, -1, 1))], None),
+        ("right", "green", [_quad((1, -1, -1), (1, -1, 1), (1, 1, 1), (1, 1, -1))], None),
+        # emitter: faces down (e1 x e2 = -y), just below the ceiling
+        ("light", "black", [_quad((-0.25, 0.995, -0.25), (0.25, 0.995, -0.25), (0.25, 0.995, 0.25), (-0.25, 0.995, 0.25))],
+         (17.0, 12.0, 4.0)),
+        ("tallbox", "metal" if variant == "glossy" else "white", _box_quads(-0.33, -0.3, 0.3, 1.2, 0.3, -1.0, 0.3), None),
+        ("shortbox", "glass" if variant == "glossy" else "white", _box_quads(0.35, 0.3, 0.3, 0.6, 0.3, -1.0, -0.3), None),
+    ]
+    return parts
+
+
+CORNELL_BSDFS = {
+    # id: (plugin type, {param: value})
+    "white": ("diffuse", {"reflectance": (0.75, 0.75, 0.75)}),
+    "red": ("diffuse", {"reflectance": (0.75, 0.25, 0.25)}),
+    "green": ("diffuse", {"reflectance": (0.25, 0.75, 0.25)}),
+    "black": ("diffuse", {"reflectance": (0.0, 0.0, 0.0)}),
+    "metal": ("roughconductor", {"eta": (0.2, 0.92, 1.1), "k": (3.9, 2.45, 2.14), "alpha": 0.1}),
+    "glass": ("dielectric", {"specularReflectance": (1.0, 1.0, 1.0), "specularTransmittance": (1.0, 1.0, 1.0), "intIOR": 1.5}),
+}
+CORNELL_CAMERA = {"origin": (0.0, 0.0, 3.9), "target": (0.0, 0.0, 0.0), "up": (0.0, 1.0, 0.0), "fov": 39.3}
+
+
+def _quads_to_tris(quads):
+    out = []
+    for a, b, c, d in quads:
+        out.append(np.concatenate([a, b, c]))
+        out.append(np.concatenate([a, c, d]))
+    return out
+
+
+def write_cornell(dirpath, width=512, height=512, spp=64, max_depth=8, variant="diffuse", name="cornell"):
+    """Writes <dirpath>/<name>.xml + one OBJ per part; returns the XML path."""
+    os.makedirs(dirpath, exist_ok=True)
+    parts = cornell_parts(variant)
+    used = []
+    for pname, bsdf, quads, rad in parts:
+        with open(os.path.join(dirpath, "%s_%s.obj" % (name, pname)), "w") as f:
+            f.write("# %s\no %s\n" % (pname, pname))
+            nv = 0
+            for q in quads:
+                for p in q:
+                    f.write("v %.9g %.9g %.9g\n" % (np.float32(p[0]), np.float32(p[1]), np.float32(p[2])))
+                f.write("f %d %d %d\nf %d %d %d\n" % (nv + 1, nv + 2, nv + 3, nv + 1, nv + 3, nv + 4))
+                nv += 4
+        if bsdf not in used:
+            used.append(bsdf)
+    cam = CORNELL_CAMERA
+    x = ['<?xml version="1.0" encoding="utf-8"?>', '<scene version="0.5.0">',
+         '  <integrator type="path">', '    <integer name="maxDepth" value="%d"/>' % max_depth, '  </integrator>',
+         '  <sensor type="perspective">', '    <float name="fov" value="%g"/>' % cam["fov"],
+         '    <transform name="toWorld">',
+         '      <lookAt origin="%g, %g, %g" target="%g, %g, %g" up="%g, %g, %g"/>' % (cam["origin"] + cam["target"] + cam["up"]),
+         '    </transform>',
+         '    <sampler type="independent">', '      <integer name="sampleCount" value="%d"/>' % spp, '    </sampler>',
+         '    <film type="hdrfilm">', '      <integer name="width" value="%d"/>' % width,
+         '      <integer name="height" value="%d"/>' % height, '      <rfilter type="box"/>', '    </film>', '  </sensor>']
+    for b in used:
+        typ, prm = CORNELL_BSDFS[b]
+        x.append('  <bsdf type="%s" id="%s">' % (typ, b))
+        for k, v in prm.items():
+            if isinstance(v, tuple):
+                x.append('    <rgb name="%s" value="%g, %g, %g"/>' % ((k,) + v))
+            else:
+                x.append('    <float name="%s" value="%g"/>' % (k, v))
+        x.append('  </bsdf>')
+    for pname, bsdf, quads, rad in parts:
+        x.append('  <shape type="obj">')
+        x.append('    <string name="filename" value="%s_%s.obj"/>' % (name, pname))
+        x.append('    <ref id="%s"/>' % bsdf)
+        if rad is not None:
+            x.append('    <emitter type="area">')
+            x.append('      <rgb name="radiance" value="%g, %g, %g"/>' % rad)
+            x.append('    </emitter>')
+        x.append('  </shape>')
+    x.append('</scene>')
+    path = os.path.join(dirpath, name + ".xml")
+    with open(path, "w") as f:
+        f.write("\n".join(x) + "\n")
+    return path
+
+
+def cornell_arrays(variant="diffuse"):
+    """The same scene flattened for the C ABI: (tris [n,9] float64 (float32-exact), material_id,
+    light_id, materials [list of dict], lights [list of (prim, radiance)])."""
+    parts = cornell_parts(variant)
+    ids = {}
+    mats = []
+    tris, mid, lid, lights = [], [], [], []
+    for pname, bsdf, quads, rad in parts:
+        if bsdf not in ids:
+            ids[bsdf] = len(mats)
+            typ, prm = CORNELL_BSDFS[bsdf]
+            mats.append(dict(type=typ, **prm))
+        for t in _quads_to_tris(quads):
+            t = t.astype(np.float32).astype(np.float64)     # what tinyobjloader hands the reference (meshio.cc:178-205)
+            if rad is not None:
+                lid.append(len(lights))
+                lights.append((len(tris), rad))
+            else:
+                lid.append(-1)
+            tris.append(t)
+            mid.append(ids[bsdf])
+    return (np.asarray(tris, dtype=np.float64), np.asarray(mid, dtype=np.int32), np.asarray(lid, dtype=np.int32),
+            mats, lights)
+
+
+# ---- camera matrices, restating core/transform.cc:165-212 and core/camera.cc:20-38 ----------------
+
+def look_at(origin, target, up):
+    eye = np.asarray(origin, dtype=np.float64)
+    d = np.asarray(target, dtype=np.float64) - eye
+    d /= np.linalg.norm(d)
+    u = np.asarray(up, dtype=np.float64)
+    left = np.cross(u / np.linalg.norm(u), d)
+    left /= np.linalg.norm(left)
+    new_up = np.cross(d, left)
+    m = np.eye(4)
+    m[:3, 0] = left; m[:3, 1] = new_up; m[:3, 2] = d; m[:3, 3] = eye
+    return m
+
+
+def perspective_camera(to_world, fov_deg, width, height):
+    """(camera_to_world, raster_to_camera) as the reference's PerspectiveCamera builds them."""
+    fov = fov_deg * np.pi / 180.0
+    aspect = width / height
+    near, far = 1.0e-2, 1000.0
+    pers = np.array([[1.0 / aspect, 0, 0, 0], [0, 1, 0, 0], [0, 0, far / (far - near), -far * near / (far - near)],
+                     [0, 0, 1, 0]], dtype=np.float64)
+    it = 1.0 / np.tan(fov / 2.0)
+    c2s = np.diag([it, it, 1.0, 1.0]) @ pers
+    # screen = [-1,1]^2: screenToRaster = scale(w,h,1) * scale(1/2,-1/2,1) * translate(1,-1,0)
+    tr = np.eye(4); tr[0, 3] = 1.0; tr[1, 3] = -1.0
+    s2r = np.diag([float(width), float(height), 1.0, 1.0]) @ np.diag([0.5, -0.5, 1.0, 1.0]) @ tr
+    r2c = np.linalg.inv(c2s) @ np.linalg.inv(s2r)
+    return np.ascontiguousarray(to_world, dtype=np.float64), np.ascontiguousarray(r2c)
+
+
+def read_hdr(path):
+    """Radiance RGBE reader for the files the reference writes (core/image.cc:390-435: per-scanline,
+    per-channel literal runs). Decodes mantissa m as (m + 0.5) / 256 to undo the truncation of
+    core/image.cc:72-88 without bias. Returns float32 [h, w, 3]."""
+    with open(path, "rb") as f:
+        data = f.read()
+    pos = data.index(b"\n\n") + 2
+    end = data.index(b"\n", pos)
+    t = data[pos:end].split()
+    h, w = int(t[1]), int(t[3])
+    pos = end + 1
+    buf = np.frombuffer(data, dtype=np.uint8)
+    img = np.zeros((h, w, 4), dtype=np.uint8)
+    for y in range(h):
+        assert buf[pos] == 2 and buf[pos + 1] == 2
+        pos += 4
+        for c in range(4):
+            x = 0
+            while x < w:
+                n = int(buf[pos]); pos += 1
+                if n > 128:          # run
+                    n -= 128
+                    img[y, x:x + n, c] = buf[pos]; pos += 1
+                else:
+                    img[y, x:x + n, c] = buf[pos:pos + n]; pos += n
+                x += n
+    e = img[..., 3].astype(np.float64)
+    scale = np.where(e > 0, np.exp2(e - 128.0 - 8.0), 0.0)
+    rgb = (img[..., :3].astype(np.float64) + 0.5) * scale[..., None]
+    rgb[e == 0] = 0.0
+    return rgb.astype(np.float32)
+
+
+def rel_mse(a, b, ref):
+    """mean over pixels and channels of (a-b)^2 / (ref^2 + 1e-2)."""
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64); ref = np.asarray(ref, dtype=np.float64)
+    return float(np.mean((a - b) ** 2 / (ref ** 2 + 1e-2)))

@@ -1,0 +1,74 @@
+"""Image parity of the wavefront path tracer against the UNMODIFIED reference renderer
+(BASELINE.json: "relMSE against the reference path tracer ... threshold set from the reference's
+own seed-to-seed variance").
+
+Fixtures (tests/golden/cornell_*_ref.npz) hold K reference renders of the same scene at 64 spp,
+made by tests/golden/make_cornell_golden.py; tau = 1.5 x the largest pairwise relMSE between
+reference runs. Everything goes through the C ABI (spb_render_*)."""
+import os
+
+import numpy as np
+import pytest
+
+from spica_b200 import capi, scenes
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _golden(variant):
+    g = np.load(os.path.join(GOLDEN, "cornell_%s_ref.npz" % variant))
+    runs = g["runs"].astype(np.float64)
+    return runs, int(g["spp"]), int(g["width"]), int(g["height"]), int(g["max_depth"]), float(g["pair_relmse"][0])
+
+
+@pytest.mark.parametrize("variant", ["diffuse", "glossy"])
+def test_cornell_relmse_against_reference(gpu_ctx, variant):
+    if not os.path.exists(os.path.join(GOLDEN, "cornell_%s_ref.npz" % variant)):
+        pytest.skip("no fixture for " + variant)
+    runs, spp, w, h, depth, pair_max = _golden(variant)
+    K = len(runs)
+    mean = runs.mean(0)
+    tau = 1.5 * pair_max
+    # (1) equal sample count: the GPU image is as close to a reference run as reference runs are to each other
+    img = capi.cornell_render(gpu_ctx, w, h, spp, max_depth=depth, variant=variant, seed=11)
+    r_equal = max(scenes.rel_mse(img, runs[k], mean) for k in range(K))
+    assert r_equal <= tau, (r_equal, tau)
+    # (2) bias check: a converged GPU image must agree with the reference mean to within the
+    # reference mean's own noise (pairwise / (2K)), with the same 1.5 margin + the GPU's residual
+    hi = capi.cornell_render(gpu_ctx, w, h, 64 * spp, max_depth=depth, variant=variant, seed=12)
+    r_hi = scenes.rel_mse(hi, mean, mean)
+    assert r_hi <= 1.5 * pair_max / (2 * K) * (1.0 + K / 64.0), (r_hi, pair_max / (2 * K))
+    # energy: the mean radiance agrees to 1 %
+    assert abs(hi.mean() / mean.mean() - 1.0) < 0.01, (hi.mean(), mean.mean())
+    out = os.environ.get("SPB_TEST_OUT")
+    if out:
+        np.save(os.path.join(out, "cornell_%s_gpu.npy" % variant), hi.astype(np.float32))
+
+
+def test_sample_partition_is_deterministic(gpu_ctx):
+    """Counter-based sampler: rendering samples {0..7} in one call == two interleaved halves
+    (what two GPUs do) up to float32 summation order."""
+    a = capi.cornell_render(gpu_ctx, 64, 64, 8, seed=5)
+    fa = gpu_ctx.film_read()
+    capi.cornell_render(gpu_ctx, 64, 64, 4, seed=5, first=0, stride=2)
+    gpu_ctx.render_samples(1, 4, 2)
+    fb = gpu_ctx.film_read()
+    assert np.allclose(fa, fb, rtol=1e-4, atol=1e-5)
+    assert np.array_equal(fa[..., 3], np.full((64, 64), 8.0, dtype=np.float32))
+    # small waves (many waves per pass) give the same film
+    gpu_ctx.set_option("wave_slots", 4096)
+    capi.cornell_render(gpu_ctx, 64, 64, 8, seed=5)
+    fc = gpu_ctx.film_read()
+    gpu_ctx.set_option("wave_slots", 1 << 22)
+    assert np.allclose(fa, fc, rtol=1e-4, atol=1e-5)
+    assert np.isfinite(a).all()
+
+
+def test_film_add_and_stats(gpu_ctx):
+    capi.cornell_render(gpu_ctx, 32, 32, 2, seed=3)
+    f = gpu_ctx.film_read()
+    st = gpu_ctx.render_stats()
+    assert st["paths"] == 32 * 32 * 2 and st["rays_closest"] >= st["paths"] and st["rays_shadow"] > 0
+    gpu_ctx.film_add(f)
+    assert np.allclose(gpu_ctx.film_read(), 2 * f)
