@@ -76,6 +76,11 @@ int spb_version(void);
 int spb_scene_set_triangles(spb_ctx* ctx, const double* verts, const float* normals, const float* uvs,
                             const int32_t* material_id, const int32_t* light_id, int64_t n_tris);
 
+/* Replaces only the per-triangle material / light indices (either may be NULL = keep), leaving the
+ * geometry and the acceleration structure untouched: the accelerator is built from the
+ * primitives before the light list is final (spica/sceneparser.cc:91-95). */
+int spb_scene_set_triangle_attributes(spb_ctx* ctx, const int32_t* material_id, const int32_t* light_id, int64_t n_tris);
+
 /* ---- materials, lights (device PODs of the reference's bsdf / emitter plugins) ------------------ */
 
 enum {

@@ -79,7 +79,7 @@ SYMBOLS = [
     "spb_trace_closest_dev", "spb_trace_any_dev", "spb_get_counters", "spb_set_option",
     "spb_dev_alloc", "spb_dev_free", "spb_dev_upload", "spb_dev_download", "spb_dev_sync",
     "spb_ctx_stream",
-    "spb_scene_set_materials", "spb_scene_set_lights", "spb_scene_set_envmap",
+    "spb_scene_set_triangle_attributes", "spb_scene_set_materials", "spb_scene_set_lights", "spb_scene_set_envmap",
     "spb_render_begin", "spb_render_samples", "spb_film_read", "spb_film_resolve", "spb_film_add",
     "spb_render_get_stats", "spb_comm_get_unique_id", "spb_comm_init", "spb_film_allreduce", "spb_comm_destroy",
 ]
@@ -113,6 +113,7 @@ def load():
     L.spb_dev_download.argtypes = [vp, vp, vp, C.c_size_t]
     L.spb_dev_sync.argtypes = [vp]
     L.spb_ctx_stream.argtypes = [vp]; L.spb_ctx_stream.restype = vp
+    L.spb_scene_set_triangle_attributes.argtypes = [vp, vp, vp, i64]
     L.spb_scene_set_materials.argtypes = [vp, C.POINTER(Material), i32]
     L.spb_scene_set_lights.argtypes = [vp, C.POINTER(Light), i32]
     L.spb_scene_set_envmap.argtypes = [vp, vp, i32, i32, vp, C.c_double, vp, C.c_double]

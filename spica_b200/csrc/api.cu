@@ -147,6 +147,15 @@ int spb_scene_set_triangles(spb_ctx* ctx, const double* verts, const float* norm
     return SPB_OK;
 }
 
+int spb_scene_set_triangle_attributes(spb_ctx* ctx, const int32_t* material_id, const int32_t* light_id, int64_t n) {
+    if (!ctx) return fail(nullptr, SPB_ERR_INVALID, "ctx is NULL");
+    if (n != ctx->n_tris) return fail(ctx, SPB_ERR_INVALID, "spb_scene_set_triangle_attributes: triangle count differs from spb_scene_set_triangles");
+    if (material_id) ctx->material_id.assign(material_id, material_id + n);
+    if (light_id) ctx->light_id.assign(light_id, light_id + n);
+    renderSceneChanged(ctx);
+    return SPB_OK;
+}
+
 int spb_bvh_build(spb_ctx* ctx, const spb_build_opts* opts) {
     if (!ctx) return fail(nullptr, SPB_ERR_INVALID, "ctx is NULL");
     cudaSetDevice(ctx->device);

@@ -278,6 +278,11 @@ class SceneParser {
 public:
     explicit SceneParser(const std::string& xmlFile);
     void parse();                       // loads, builds and renders, like SceneParser::parse
+    void load();                        // the first half: XML -> objects (no accelerator, no device)
+    void render();                      // the second half: integrator + accelerator + render
+    const std::vector<std::shared_ptr<Primitive>>& primitives() const;
+    const std::vector<std::shared_ptr<Light>>& lights() const;
+    std::shared_ptr<Camera> camera() const;
 private:
     struct Impl;
     std::shared_ptr<Impl> impl_;
@@ -287,6 +292,7 @@ private:
 struct HostOptions {
     int gpus = 1;                       // --gpus / SPICA_GPUS
     uint64_t seed = 0;                  // 0: seed from time(0) like the reference (core/integrator.cc:51)
+    int sppOverride = 0;                // > 0: replaces the scene's sampleCount (bench / tests)
     bool savePasses = false;            // reference behaviour: save after every spp pass (integrator.cc:100)
     std::function<void(const Image&)> onImage;   // receives the final normalised image
 };

@@ -1,0 +1,230 @@
+// The two plugins that carry the hot path to the GPU, registered under the reference's names:
+//   accelerator "bvh"  (accelerators/bvh.h:57-97)   -> spb_scene_set_triangles + spb_bvh_build, and the
+//                                                      scalar intersect() calls answered from the same tree
+//   integrator  "path" (integrators/path/path.h:21-41) -> spb_render_* ; the finished image goes back
+//                                                      through Film::setImage + Film::save (core/film.cc:23-63)
+// Nothing is computed on the CPU here; a missing device is a FatalError (no fallback).
+#include <chrono>
+#include <cstring>
+#include <ctime>
+#include <map>
+#include <mutex>
+#include <thread>
+
+#include "core.h"
+#include "plugins.h"
+
+namespace spica {
+
+namespace {
+void check(spb_ctx* ctx, int rc, const char* what) {
+    if (rc != SPB_OK) FatalError("%s failed (%d): %s", what, rc, spb_last_error(ctx));
+}
+
+struct FlatScene {              // the primitives as the C ABI takes them
+    std::vector<double> verts;
+    std::vector<float> normals, uvs;
+    std::vector<int32_t> material_id, light_id;
+    std::vector<spb_material> materials;
+    bool anyNormals = false, anyUV = false;
+};
+
+void flatten(const std::vector<std::shared_ptr<Primitive>>& prims, FlatScene* f) {
+    const size_t n = prims.size();
+    f->verts.resize(n * 9); f->normals.assign(n * 9, 0.f); f->uvs.assign(n * 6, 0.f);
+    f->material_id.resize(n); f->light_id.assign(n, -1);
+    std::map<const SurfaceMaterial*, int> matIndex;
+    for (size_t i = 0; i < n; i++) {
+        const Primitive& p = *prims[i];
+        for (int k = 0; k < 3; k++) { f->verts[i * 9 + k * 3] = p.tri.p[k].x; f->verts[i * 9 + k * 3 + 1] = p.tri.p[k].y; f->verts[i * 9 + k * 3 + 2] = p.tri.p[k].z; }
+        if (p.tri.hasNormals) {
+            f->anyNormals = true;
+            for (int k = 0; k < 3; k++) { f->normals[i * 9 + k * 3] = (float)p.tri.n[k].x; f->normals[i * 9 + k * 3 + 1] = (float)p.tri.n[k].y; f->normals[i * 9 + k * 3 + 2] = (float)p.tri.n[k].z; }
+            for (int k = 0; k < 3; k++) { f->uvs[i * 6 + k * 2] = (float)p.tri.uv[k][0]; f->uvs[i * 6 + k * 2 + 1] = (float)p.tri.uv[k][1]; if (p.tri.uv[k][0] != 0.0 || p.tri.uv[k][1] != 0.0) f->anyUV = true; }
+        }
+        if (!p.material) { f->material_id[i] = -1; continue; }        // no bsdf: the path passes through (path.cc:71-75)
+        auto it = matIndex.find(p.material.get());
+        if (it == matIndex.end()) {
+            spb_material m; p.material->describe(&m);
+            it = matIndex.emplace(p.material.get(), (int)f->materials.size()).first;
+            f->materials.push_back(m);
+        }
+        f->material_id[i] = it->second;
+    }
+}
+
+void uploadGeometry(spb_ctx* ctx, const FlatScene& f) {
+    const int64_t n = (int64_t)f.material_id.size();
+    check(ctx, spb_scene_set_triangles(ctx, f.verts.data(), f.anyNormals ? f.normals.data() : nullptr, f.anyUV ? f.uvs.data() : nullptr,
+                                       f.material_id.data(), f.light_id.data(), n), "spb_scene_set_triangles");
+    check(ctx, spb_bvh_build(ctx, nullptr), "spb_bvh_build");
+}
+}  // namespace
+
+class BVHAccel : public Accelerator {
+public:
+    BVHAccel(const std::vector<std::shared_ptr<Primitive>>& prims, RenderParams& params) : Accelerator(prims) {
+        params.getBool("useSIMD", false, true);                         // accelerators/bvh.cc:127-131 (no meaning on the GPU)
+        const char* dev = getenv("SPICA_DEVICE");
+        device_ = dev ? atoi(dev) : 0;
+        check(nullptr, spb_ctx_create(device_, &ctx_), "spb_ctx_create");
+        flatten(prims, &flat_);
+        uploadGeometry(ctx_, flat_);
+        spb_bvh_stats st;
+        check(ctx_, spb_bvh_get_stats(ctx_, &st), "spb_bvh_get_stats");
+        for (int k = 0; k < 3; k++) { lo_[k] = st.world_lo[k]; hi_[k] = st.world_hi[k]; }
+        MsgInfo("BVH: %lld triangles, %lld wide nodes, built in %.3f s", (long long)st.n_tris, (long long)st.n_wide_nodes, st.build_seconds);
+    }
+    ~BVHAccel() override { spb_ctx_destroy(ctx_); }
+    // scalar queries for callers outside the GPU integrator: same tree, same exact arithmetic
+    bool intersect(Ray& ray, SurfaceInteraction* isect) const override {
+        std::lock_guard<std::mutex> lk(mu_);
+        const spb_ray_f64 r = {ray.org.x, ray.org.y, ray.org.z, ray.dir.x, ray.dir.y, ray.dir.z, 0.0, ray.maxDist};
+        spb_hit_f64 h;
+        check(ctx_, spb_trace_closest_f64(ctx_, &r, 1, &h), "spb_trace_closest_f64");
+        if (h.prim < 0) return false;
+        ray.maxDist = h.t;                                              // core/primitive.cc:52
+        if (isect) { isect->pos = ray.org + ray.dir * h.t; isect->u = h.u; isect->v = h.v; isect->primitive = h.prim; }
+        return true;
+    }
+    bool intersect(Ray& ray) const override {
+        std::lock_guard<std::mutex> lk(mu_);
+        const spb_ray_f64 r = {ray.org.x, ray.org.y, ray.org.z, ray.dir.x, ray.dir.y, ray.dir.z, 0.0, ray.maxDist};
+        uint8_t occ = 0;
+        check(ctx_, spb_trace_any_f64(ctx_, &r, 1, &occ), "spb_trace_any_f64");
+        return occ != 0;
+    }
+    void worldBound(double lo[3], double hi[3]) const override { for (int k = 0; k < 3; k++) { lo[k] = lo_[k]; hi[k] = hi_[k]; } }
+    spb_ctx* ctx() const { return ctx_; }
+    int device() const { return device_; }
+    FlatScene& flat() { return flat_; }
+private:
+    spb_ctx* ctx_ = nullptr;
+    int device_ = 0;
+    FlatScene flat_;
+    double lo_[3], hi_[3];
+    mutable std::mutex mu_;
+};
+
+class PathIntegrator : public Integrator {
+public:
+    explicit PathIntegrator(RenderParams& params) : sampler_(std::static_pointer_cast<Sampler>(params.getObject("sampler"))) {}   // path.cc:34-36
+
+    void render(const std::shared_ptr<const Camera>& camera, const Scene& scene, RenderParams& params) override {
+        auto* accel = dynamic_cast<BVHAccel*>(scene.accelerator().get());
+        if (!accel) FatalError("the GPU path integrator needs the GPU `bvh` accelerator");
+        const HostOptions& opt = hostOptions();
+        Film& film = *camera->film;
+        const int width = film.width(), height = film.height();
+        const int numSamples = opt.sppOverride > 0 ? opt.sppOverride : params.getInt("sampleCount");   // core/integrator.cc:63
+        const int maxDepth = params.getInt("maxDepth");                    // path.cc:68
+        FlatScene& flat = accel->flat();
+
+        // lights in Scene::lights() order (sceneparser.cc:172-179,329)
+        std::vector<spb_light> lights;
+        std::map<const Light*, int> lightIndex;
+        const Envmap* env = nullptr;
+        for (const auto& l : scene.lights()) {
+            spb_light d; std::memset(&d, 0, sizeof(d));
+            d.type = l->kind(); d.prim = -1;
+            if (l->kind() == SPB_LIGHT_AREA) { const auto* a = static_cast<const AreaLight*>(l.get()); d.radiance[0] = (float)a->Lemit.r; d.radiance[1] = (float)a->Lemit.g; d.radiance[2] = (float)a->Lemit.b; }
+            else { if (env) FatalError("more than one environment map is outside this host's scope"); env = static_cast<const Envmap*>(l.get()); }
+            lightIndex[l.get()] = (int)lights.size();
+            lights.push_back(d);
+        }
+        const auto& prims = accel->primitives();
+        for (size_t i = 0; i < prims.size(); i++) {
+            flat.light_id[i] = -1;
+            if (prims[i]->light) { const int li = lightIndex.at(prims[i]->light.get()); flat.light_id[i] = li; lights[li].prim = (int32_t)i; }
+        }
+
+        spb_render_desc desc; std::memset(&desc, 0, sizeof(desc));
+        desc.width = width; desc.height = height; desc.max_depth = maxDepth;
+        desc.filter = film.filter()->kind();
+        desc.filter_radius[0] = film.filter()->rx; desc.filter_radius[1] = film.filter()->ry; desc.filter_sigma = film.filter()->sigma;
+        std::memcpy(desc.camera_to_world, camera->cameraToWorld.getMat().m, sizeof(double) * 16);
+        std::memcpy(desc.raster_to_camera, camera->rasterToCamera.getMat().m, sizeof(double) * 16);
+        desc.lens_radius = camera->lensRadius; desc.focal_distance = camera->focalLength;
+        desc.seed = opt.seed ? opt.seed : (uint64_t)time(nullptr);         // the reference seeds from time(0) (integrator.cc:51)
+        desc.rr_start_bounce = 3;                                          // path.cc:117
+
+        const int G = std::max(1, opt.gpus);
+        std::vector<spb_ctx*> ctxs(G, nullptr);
+        ctxs[0] = accel->ctx();
+        char commId[SPB_COMM_ID_BYTES];
+        if (G > 1) check(nullptr, spb_comm_get_unique_id(commId), "spb_comm_get_unique_id");
+
+        auto setup = [&](int g) {
+            spb_ctx* ctx = ctxs[g];
+            if (g > 0) {                                                    // replicas: scene + BVH on every GPU
+                check(nullptr, spb_ctx_create(accel->device() + g, &ctx), "spb_ctx_create");
+                ctxs[g] = ctx;
+                uploadGeometry(ctx, flat);
+            }
+            check(ctx, spb_scene_set_triangle_attributes(ctx, flat.material_id.data(), flat.light_id.data(), (int64_t)flat.material_id.size()), "spb_scene_set_triangle_attributes");
+            check(ctx, spb_scene_set_materials(ctx, flat.materials.data(), (int32_t)flat.materials.size()), "spb_scene_set_materials");
+            check(ctx, spb_scene_set_lights(ctx, lights.data(), (int32_t)lights.size()), "spb_scene_set_lights");
+            if (env) {
+                std::vector<float> rgb(env->image.rgb.begin(), env->image.rgb.end());
+                const double c[3] = {env->worldCenter.x, env->worldCenter.y, env->worldCenter.z};
+                check(ctx, spb_scene_set_envmap(ctx, rgb.data(), env->image.width, env->image.height, &env->toWorld.getMat().m[0][0], env->scale, c, env->worldRadius), "spb_scene_set_envmap");
+            }
+            if (G > 1) check(ctx, spb_comm_init(ctx, commId, G, g), "spb_comm_init");
+            check(ctx, spb_render_begin(ctx, &desc), "spb_render_begin");
+        };
+        auto forEachGpu = [&](const std::function<void(int)>& fn) {
+            std::vector<std::thread> th;
+            for (int g = 1; g < G; g++) th.emplace_back(fn, g);
+            fn(0);
+            for (auto& t : th) t.join();
+        };
+        forEachGpu(setup);
+
+        std::vector<float> rgb((size_t)width * height * 3);
+        auto publish = [&](int id) {
+            check(ctxs[0], spb_film_resolve(ctxs[0], rgb.data()), "spb_film_resolve");
+            Image img(width, height);
+            for (size_t i = 0; i < rgb.size(); i++) img.rgb[i] = rgb[i];
+            film.setImage(img);                                             // core/film.cc:60-63
+            film.save(id);
+            if (opt.onImage) opt.onImage(img);
+        };
+
+        const auto t0 = std::chrono::steady_clock::now();
+        if (opt.savePasses && G == 1) {
+            // reference behaviour: one film save per spp pass (core/integrator.cc:64-105)
+            for (int i = 0; i < numSamples; i++) {
+                check(ctxs[0], spb_render_samples(ctxs[0], i, 1, 1), "spb_render_samples");
+                printf("[ %d / %d ] 100.00 %% processed...\n", i + 1, numSamples);
+                publish(i + 1);
+            }
+        } else {
+            // GPU g renders sample indices g, g+G, ... ; then ONE all-reduce of the RGBW film
+            forEachGpu([&](int g) {
+                const int count = (numSamples - g + G - 1) / G;
+                check(ctxs[g], spb_render_samples(ctxs[g], g, std::max(count, 0), G), "spb_render_samples");
+                if (G > 1) check(ctxs[g], spb_film_allreduce(ctxs[g]), "spb_film_allreduce");
+            });
+            const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            spb_render_stats st;
+            check(ctxs[0], spb_render_get_stats(ctxs[0], &st), "spb_render_get_stats");
+            MsgInfo("rendered %d spp at %dx%d on %d GPU(s) in %.3f s: %.2f Msamples/s; GPU0: %.1f Mrays/s", numSamples, width, height, G, sec,
+                    1e-6 * width * height * (double)numSamples / sec,
+                    st.render_ms > 0 ? 1e-3 * (double)(st.rays_closest + st.rays_shadow + st.rays_mis) / st.render_ms : 0.0);
+            publish(numSamples);
+        }
+        for (int g = 1; g < G; g++) { spb_comm_destroy(ctxs[g]); spb_ctx_destroy(ctxs[g]); }
+        if (G > 1) spb_comm_destroy(ctxs[0]);
+        printf("Finish!!\n");
+    }
+private:
+    std::shared_ptr<Sampler> sampler_;
+};
+
+void registerGpuPlugins() {
+    PluginManager& pm = PluginManager::getInstance();
+    pm.registerAccelerator("bvh", [](const std::vector<std::shared_ptr<Primitive>>& prims, RenderParams& p) -> Accelerator* { return new BVHAccel(prims, p); });
+    pm.registerPlugin("path", [](RenderParams& p) -> CObject* { return new PathIntegrator(p); });
+}
+
+}  // namespace spica

@@ -1,0 +1,95 @@
+"""The C++17 host (spica's plugin surface + Mitsuba-style scene loading + `spica -i scene.xml`).
+CPU tests cover the host logic up to the C-ABI boundary (no device needed); GPU tests render the
+committed scene files through the host library and the CLI and compare with the reference images."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from spica_b200 import host, scenes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SCENES = os.path.join(ROOT, "tests", "golden", "scenes")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def test_host_library_exports():
+    L = host.load()
+    for s in host.SYMBOLS:
+        assert hasattr(L, s)
+    assert os.access(host.CLI_PATH, os.X_OK)
+
+
+@pytest.mark.parametrize("variant", ["diffuse", "glossy"])
+def test_parse_cornell_matches_the_flat_scene(variant):
+    r = host.parse_scene(os.path.join(SCENES, "cornell_%s.xml" % variant))
+    tris, mid, lid, mats, lights = scenes.cornell_arrays(variant)
+    assert r["n_triangles"] == len(tris) == 32
+    assert r["n_lights"] == len(lights) == 2 and r["n_emitter_triangles"] == 2      # one AreaLight per emitter triangle
+    assert (r["width"], r["height"], r["sample_count"], r["max_depth"]) == (128, 128, 64, 8)
+    assert np.array_equal(r["verts"], tris)                                          # float32 positions widened to double
+    cam = scenes.CORNELL_CAMERA
+    c2w, r2c = scenes.perspective_camera(scenes.look_at(cam["origin"], cam["target"], cam["up"]), cam["fov"], 128, 128)
+    assert np.allclose(r["camera_to_world"], c2w, atol=1e-15)
+    assert np.allclose(r["raster_to_camera"], r2c, atol=1e-15)
+
+
+def test_ply_shape_transform_and_defaults(tmp_path):
+    v, f = scenes.torus_mesh(16, 8)
+    scenes.write_ply(str(tmp_path / "t.ply"), v, f)
+    xml = """<?xml version="1.0"?>
+<!-- comment -->
+<scene version="0.5.0">
+  <integrator type="path"/>
+  <sensor type="perspective">
+    <float name="fov" value="45"/>
+    <transform name="toWorld"><lookAt origin="0 0 5" target="0 0 0" up="0 1 0"/></transform>
+    <sampler type="ldsampler"><integer name="sampleCount" value="4"/></sampler>
+    <film type="ldrfilm"><integer name="width" value="40"/><integer name="height" value="20"/><rfilter type="gaussian"/></film>
+  </sensor>
+  <bsdf type="diffuse" id="m"><rgb name="reflectance" value="0.5"/></bsdf>
+  <shape type="ply">
+    <string name="filename" value="t.ply"/>
+    <transform name="toWorld"><scale x="2" y="2" z="2"/><translate x="1" y="0" z="0"/></transform>
+    <ref id="m"/>
+  </shape>
+</scene>"""
+    p = tmp_path / "s.xml"
+    p.write_text(xml)
+    r = host.parse_scene(str(p))
+    assert r["n_triangles"] == 256 and r["n_lights"] == 0
+    assert r["max_depth"] == 16 and r["sample_count"] == 4 and r["filter"] == 2      # parser default maxDepth (sceneparser.cc:63)
+    want = scenes.mesh_triangles(v, f).reshape(-1, 3, 3) * 2.0 + np.array([1.0, 0.0, 0.0])
+    assert np.allclose(r["verts"].reshape(-1, 3, 3), want, atol=1e-12)
+    assert (r["width"], r["height"]) == (40, 20)
+
+
+def test_cli_fails_loudly_without_device_or_scene(tmp_path):
+    import torch
+    r = subprocess.run([host.CLI_PATH, "-i", str(tmp_path / "missing.xml")], capture_output=True, text=True)
+    assert r.returncode != 0 and "Failed to open" in r.stderr
+    if not torch.cuda.is_available():
+        r = host.run_cli(os.path.join(SCENES, "cornell_diffuse.xml"), str(tmp_path / "o"))
+        assert r.returncode != 0 and "no CUDA device" in r.stderr             # no CPU fallback
+
+
+@pytest.mark.gpu
+def test_host_render_matches_reference(tmp_path):
+    g = np.load(os.path.join(GOLDEN, "cornell_diffuse_ref.npz"))
+    runs = g["runs"].astype(np.float64)
+    mean = runs.mean(0)
+    tau = 1.5 * float(g["pair_relmse"][0])
+    img = host.render_scene(os.path.join(SCENES, "cornell_diffuse.xml"), str(tmp_path / "lib_out"), seed=3)
+    assert img.shape == (128, 128, 3)
+    assert max(scenes.rel_mse(img, r, mean) for r in runs) <= tau
+    # the film wrote <prefix>.hdr like the reference's hdrfilm; RGBE keeps 8 mantissa bits
+    hdr = scenes.read_hdr(str(tmp_path / "lib_out.hdr"))
+    assert (np.abs(hdr - img) <= img.max(-1, keepdims=True) / 128 + 1e-6).all()      # shared exponent
+    # the CLI, called as a user of the reference calls it
+    r = host.run_cli(os.path.join(SCENES, "cornell_diffuse.xml"), str(tmp_path / "cli_out"), seed=3)
+    assert r.returncode == 0, r.stderr
+    cli = scenes.read_hdr(str(tmp_path / "cli_out.hdr"))
+    assert np.allclose(cli, hdr)                                              # same seed -> same image
+    assert "Finish!!" in r.stdout
