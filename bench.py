@@ -146,7 +146,8 @@ def main():
     ap.add_argument("--rays", type=int, default=N_RAYS)
     ap.add_argument("--ref-rays", type=int, default=1 << 21)
     ap.add_argument("--variant", type=int, default=-1)
-    ap.add_argument("--max-leaf", type=int, default=3)
+    ap.add_argument("--max-leaf", type=int, default=1)
+    ap.add_argument("--render-spp", type=int, default=32, help="spp per GPU of the side render measurement (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -222,13 +223,51 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_val = world * n / float(t.item()) * 1e-6
 
+    # ---- side measurement on all ranks: the path tracer (BASELINE configs[2] geometry: Cornell box,
+    # 1920x1080, depth 16), spp partitioned over the GPUs, one NCCL all-reduce of the film per frame
+    render = None
+    if args.render_spp > 0:
+        rctx = capi.Context(local)
+        if world > 1:
+            ids = [capi.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(ids, src=0)
+            rctx.comm_init(ids[0], world, rank)
+        W, H, spp = 1920, 1080, args.render_spp
+        capi.cornell_render(rctx, W, H, 1, max_depth=16, seed=7, first=rank, stride=world)     # warm-up pass + setup
+        rctx.render_begin(W, H, *scenes.perspective_camera(scenes.look_at(**{k: scenes.CORNELL_CAMERA[k] for k in ("origin", "target", "up")}),
+                                                          scenes.CORNELL_CAMERA["fov"], W, H), max_depth=16, seed=7)
+        if world > 1:
+            rctx.film_allreduce()       # first collective on a communicator sets up its channels: keep it out of the timed frame
+            rctx.render_begin(W, H, *scenes.perspective_camera(scenes.look_at(**{k: scenes.CORNELL_CAMERA[k] for k in ("origin", "target", "up")}),
+                                                              scenes.CORNELL_CAMERA["fov"], W, H), max_depth=16, seed=7)
+        barrier()
+        t0 = time.perf_counter()
+        rctx.render_samples(rank, spp, world)
+        if world > 1:
+            rctx.film_allreduce()
+        barrier()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        rst = rctx.render_stats()
+        img = rctx.film_resolve() if rank == 0 else None
+        render = {"scene": "cornell diffuse 1920x1080 depth 16", "spp_per_gpu": spp, "spp_total": spp * world,
+                  "seconds": float(t.item()), "msamples_s": W * H * spp * world / float(t.item()) * 1e-6,
+                  "rank0_rays": rst["rays_closest"] + rst["rays_shadow"] + rst["rays_mis"],
+                  "rank0_mrays_s": (rst["rays_closest"] + rst["rays_shadow"] + rst["rays_mis"]) / (rst["render_ms"] * 1e-3) * 1e-6,
+                  "rank0_kernel_launches": rst["kernel_launches"],
+                  "film_weight_per_pixel": float(rctx.film_read()[..., 3].mean()) if rank == 0 else None,
+                  "mean_radiance": float(img.mean()) if rank == 0 else None}
+        rctx.close()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
     # ---- side measurements on rank 0 (not part of `value`)
-    extra = {}
+    extra = {"render": render}
     pri = scenes.primary_rays(4096, 4096)[: n]
     d_rays.copy_(torch.from_numpy(pri)); torch.cuda.synchronize()
     for _ in range(2):

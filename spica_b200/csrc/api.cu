@@ -159,9 +159,9 @@ int spb_scene_set_triangle_attributes(spb_ctx* ctx, const int32_t* material_id, 
 int spb_bvh_build(spb_ctx* ctx, const spb_build_opts* opts) {
     if (!ctx) return fail(nullptr, SPB_ERR_INVALID, "ctx is NULL");
     cudaSetDevice(ctx->device);
-    spb_build_opts o = {0, 3, 32, 0};
+    spb_build_opts o = {0, 1, 32, 0};
     if (opts) o = *opts;
-    if (o.max_leaf_tris <= 0) o.max_leaf_tris = 3;
+    if (o.max_leaf_tris <= 0) o.max_leaf_tris = 1;
     if (o.sah_bins <= 0) o.sah_bins = 32;
     if (o.builder != 0) return fail(ctx, SPB_ERR_UNSUPPORTED, "spb_bvh_build: only builder 0 (host binned SAH) is available in this build");
     const auto t0 = std::chrono::steady_clock::now();

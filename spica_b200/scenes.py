@@ -370,3 +370,107 @@ def rel_mse(a, b, ref):
     """mean over pixels and channels of (a-b)^2 / (ref^2 + 1e-2)."""
     a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64); ref = np.asarray(ref, dtype=np.float64)
     return float(np.mean((a - b) ** 2 / (ref ** 2 + 1e-2)))
+
+
+def write_hdr(path, img):
+    """Radiance RGBE writer in the layout the reference reads and writes (core/image.cc:270-435):
+    0x02 0x02 scanline marker, per-channel literal runs of <= 127."""
+    img = np.asarray(img, dtype=np.float64)
+    h, w = img.shape[:2]
+    d = img.max(-1)
+    m, e = np.frexp(d)
+    scale = np.where(d > 1e-32, m * 256.0 / np.maximum(d, 1e-300), 0.0)
+    rgbe = np.zeros((h, w, 4), dtype=np.uint8)
+    rgbe[..., :3] = np.clip(img * scale[..., None], 0, 255).astype(np.uint8)
+    rgbe[..., 3] = np.where(d > 1e-32, e + 128, 0).astype(np.uint8)
+    out = bytearray()
+    out += b"#?RADIANCE\n# Made with 100% pure HDR Shop\nFORMAT=32-bit_rle_rgbe\nEXPOSURE=1.0000000000000\n\n"
+    out += ("-Y %d +X %d\n" % (h, w)).encode()
+    for y in range(h):
+        out += bytes([2, 2, (w >> 8) & 0xFF, w & 0xFF])
+        for c in range(4):
+            x = 0
+            while x < w:
+                n = min(127, w - x)
+                out.append(n)
+                out += rgbe[y, x:x + n, c].tobytes()
+                x += n
+    with open(path, "wb") as f:
+        f.write(bytes(out))
+
+
+def synthetic_envmap(w=64, h=32):
+    """Small lat-long sky: horizon gradient + a bright sun lobe + a coloured ground."""
+    v = (np.arange(h) + 0.5) / h
+    u = (np.arange(w) + 0.5) / w
+    theta = np.pi * v[:, None]
+    phi = 2 * np.pi * u[None, :]
+    sky = np.stack([0.35 + 0.3 * np.cos(theta) ** 2 + 0 * phi, 0.45 + 0.3 * np.cos(theta) ** 2 + 0 * phi,
+                    0.7 + 0.25 * np.cos(theta) + 0 * phi], -1)
+    sun_dir = np.array([np.sin(0.7) * np.cos(1.0), np.sin(0.7) * np.sin(1.0), np.cos(0.7)])
+    d = np.stack([np.sin(theta) * np.cos(phi), np.sin(theta) * np.sin(phi), np.cos(theta) + 0 * phi], -1)
+    sun = np.exp(np.minimum(0.0, (d @ sun_dir - 1.0) * 60.0))[..., None] * np.array([30.0, 26.0, 20.0])
+    img = np.where(theta[..., None] > np.pi * 0.62, np.array([0.25, 0.2, 0.15]) * (1 + 0 * sky), sky) + sun
+    return np.ascontiguousarray(img, dtype=np.float32)
+
+
+def write_envscene(dirpath, width=128, height=128, spp=64, max_depth=8, name="envtorus", nu=96, nv=48):
+    """Torus (PLY, rough dielectric) over a diffuse ground quad (OBJ) lit ONLY by an environment map
+    (BASELINE config 4 in miniature: env lighting + PLY mesh + roughdielectric). Returns the XML path."""
+    os.makedirs(dirpath, exist_ok=True)
+    v, f = torus_mesh(nu, nv, R=0.6, r=0.25, bump=0.0)
+    write_ply(os.path.join(dirpath, name + "_torus.ply"), v, f)
+    with open(os.path.join(dirpath, name + "_ground.obj"), "w") as fo:
+        fo.write("o ground\nv -2 -2 -0.3\nv 2 -2 -0.3\nv 2 2 -0.3\nv -2 2 -0.3\nf 1 2 3\nf 1 3 4\n")
+    write_hdr(os.path.join(dirpath, name + "_env.hdr"), synthetic_envmap())
+    x = """<?xml version="1.0" encoding="utf-8"?>
+<scene version="0.5.0">
+  <integrator type="path">
+    <integer name="maxDepth" value="%d"/>
+  </integrator>
+  <sensor type="perspective">
+    <float name="fov" value="40"/>
+    <transform name="toWorld">
+      <lookAt origin="0.3, -2.6, 1.5" target="0, 0, 0" up="0, 0, 1"/>
+    </transform>
+    <sampler type="independent">
+      <integer name="sampleCount" value="%d"/>
+    </sampler>
+    <film type="hdrfilm">
+      <integer name="width" value="%d"/>
+      <integer name="height" value="%d"/>
+      <rfilter type="tent"/>
+    </film>
+  </sensor>
+  <emitter type="envmap">
+    <string name="filename" value="%s_env.hdr"/>
+    <float name="worldRadius" value="6.0"/>
+    <float name="scale" value="1.5"/>
+    <transform name="toWorld">
+      <rotate x="0" y="0" z="1" angle="0.4"/>
+    </transform>
+  </emitter>
+  <bsdf type="roughdielectric" id="frosted">
+    <rgb name="specularReflectance" value="1, 1, 1"/>
+    <rgb name="specularTransmittance" value="0.9, 0.95, 1"/>
+    <float name="alpha" value="0.15"/>
+    <float name="intIOR" value="1.5"/>
+    <string name="distribution" value="ggx"/>
+  </bsdf>
+  <bsdf type="diffuse" id="ground">
+    <rgb name="reflectance" value="0.6, 0.55, 0.5"/>
+  </bsdf>
+  <shape type="ply">
+    <string name="filename" value="%s_torus.ply"/>
+    <ref id="frosted"/>
+  </shape>
+  <shape type="obj">
+    <string name="filename" value="%s_ground.obj"/>
+    <ref id="ground"/>
+  </shape>
+</scene>
+""" % (max_depth, spp, width, height, name, name, name)
+    path = os.path.join(dirpath, name + ".xml")
+    with open(path, "w") as fo:
+        fo.write(x)
+    return path

@@ -31,11 +31,14 @@ DEPTH = 8
 
 
 def main():
-    variants = sys.argv[1:] or ["diffuse", "glossy"]
+    variants = sys.argv[1:] or ["diffuse", "glossy", "envtorus"]
     ref_bin = os.path.join(ROOT, "oracle", "_ref", "bin")
     for variant in variants:
         d = os.path.join(ROOT, "tests", "golden", "scenes")
-        xml = scenes.write_cornell(d, W, H, SPP, DEPTH, variant=variant, name="cornell_" + variant)
+        if variant == "envtorus":
+            xml = scenes.write_envscene(d, W, H, SPP, DEPTH, name="envtorus")
+        else:
+            xml = scenes.write_cornell(d, W, H, SPP, DEPTH, variant=variant, name="cornell_" + variant)
         runs = []
         for k in range(K):
             out = "/tmp/spica_golden_%s_%d" % (variant, k)
@@ -49,7 +52,8 @@ def main():
         m = runs.mean(0)
         pair = [scenes.rel_mse(runs[i], runs[j], m) for i, j in itertools.combinations(range(K), 2)]
         print(variant, "pairwise relMSE max %.5f mean %.5f" % (max(pair), np.mean(pair)))
-        np.savez_compressed(os.path.join(ROOT, "tests", "golden", "cornell_%s_ref.npz" % variant),
+        fname = "envtorus_ref.npz" if variant == "envtorus" else "cornell_%s_ref.npz" % variant
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", fname),
                             runs=runs.astype(np.float16), spp=SPP, width=W, height=H, max_depth=DEPTH,
                             pair_relmse=np.array([max(pair), np.mean(pair)]))
 
