@@ -1,5 +1,7 @@
 // C ABI: context, geometry upload, acceleration-structure build / import, raw device memory.
+#include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstring>
 #include <mutex>
 
@@ -46,6 +48,11 @@ static int uploadBvh(spb_ctx* ctx) {
     for (int k = 0; k < 3; k++) {
         sp.wlo[k] = b.wlo[k] - 2.0 * b.inflate;
         sp.whi[k] = b.whi[k] + 2.0 * b.inflate;
+    }
+    {
+        double m = 0.0;
+        for (int k = 0; k < 3; k++) m = std::max(m, std::max(std::abs(sp.wlo[k]), std::abs(sp.whi[k])));
+        sp.max_coord = (float)(m * 1.0000002);
     }
     if (!sp.empty) {
         SPB_CUDA(ctx, cudaMalloc(&ctx->d_nodes, b.nodes.size() * sizeof(WideNode)));

@@ -43,6 +43,7 @@ struct SceneParams {                    // small POD passed to kernels by value
     const void*     tris;               // TriF32* or TriF64*
     double wlo[3], whi[3];              // inflated world box
     float  inflate;
+    float  max_coord;                   // max |coordinate| of the inflated world box (error bounds of the float32 pre-test)
     int32_t tri_format;                 // 0 = TriF32, 1 = TriF64
     int32_t n_tris;
     int32_t empty;                      // 1: no geometry

@@ -69,7 +69,7 @@ SPB_HD U4 ldg4(const void* p) { U4 v; __builtin_memcpy(&v, p, 16); return v; }
 const double kRefEps = 1.0e-12;     // reference core/common.h:55
 const double kRefInfty = 1.0e32;    // reference core/common.h:54
 
-struct TraceCounters { unsigned long long nodes, tris; };
+struct TraceCounters { unsigned long long nodes, tris, exact; };   // node visits, triangle candidates, exact (double) tests
 
 struct RayState {
     // deciding domain
@@ -78,6 +78,7 @@ struct RayState {
     double t_shift;                 // culling origin = o + t_shift * d
     // culling domain
     float cox, coy, coz, idx, idy, idz, ctmax;
+    float fdx, fdy, fdz;            // float32 direction (pre-test only)
     uint32_t oct_inv;
     // result
     int32_t best_prim, best_rank;
@@ -125,6 +126,7 @@ SPB_HD bool rayBegin(const SceneParams& sp, double ox, double oy, double oz, dou
     r.coy = (float)(oy + r.t_shift * r.dy);
     r.coz = (float)(oz + r.t_shift * r.dz);
     const float fdx = (float)r.dx, fdy = (float)r.dy, fdz = (float)r.dz;
+    r.fdx = fdx; r.fdy = fdy; r.fdz = fdz;
     const float tiny = 8.6736174e-19f;  // 2^-60: keeps 1/d finite; far below the culling slack
     r.idx = 1.0f / (fabsf(fdx) < tiny ? (fdx < 0.f ? -tiny : tiny) : fdx);
     r.idy = 1.0f / (fabsf(fdy) < tiny ? (fdy < 0.f ? -tiny : tiny) : fdy);
@@ -160,13 +162,57 @@ SPB_HD bool triTestExact(const RayState& r, const double p0[3], const double p1[
     return true;
 }
 
+
+// Conservative float32 pre-test for float32-exact triangles (TriF32). It may only say "certainly
+// rejected by the exact test"; everything else goes on to triTestExact, which alone decides.
+// Moeller-Trumbore on the culling ray (origin c = fl32(o + t_shift d), direction fl32(d)) with
+// forward error bounds. With E1 = max|e1_k|, E2 = max|e2_k|, TV = max|tv_k|, M = max scene
+// coordinate and u = 2^-24, the float32 results differ from the real-number values by at most
+//   |d det| <=  72 u E1 E2            -> 2^-17 E1 E2
+//   |d U|   <=  90 u E2 (M + TV)      -> 2^-17 E2 (M + TV)
+//   |d V|   <=  72 u E1 (M + TV)      -> 2^-17 E1 (M + TV)
+//   |d T|   <=  72 u E1 E2 (M + TV)   -> 2^-17 E1 E2 (M + TV)
+// (input roundings: |d c_k| <= u (M + TV), |d dir_k| <= u, edges relative u; then the running
+// error of each 3-term product sum; derivation in DESIGN.md "float32 pre-test"). Every comparison is
+// written so that NaN / Inf fall through to the exact test.
+SPB_HD bool triPretestMayHit(const RayState& r, float maxCoord, const U4& a, const U4& b, const U4& c) {
+    const float p0x = asFloat(a.x), p0y = asFloat(a.y), p0z = asFloat(a.z);
+    const float e1x = asFloat(b.x) - p0x, e1y = asFloat(b.y) - p0y, e1z = asFloat(b.z) - p0z;
+    const float e2x = asFloat(c.x) - p0x, e2y = asFloat(c.y) - p0y, e2z = asFloat(c.z) - p0z;
+    const float px = r.fdy * e2z - r.fdz * e2y, py = r.fdz * e2x - r.fdx * e2z, pz = r.fdx * e2y - r.fdy * e2x;
+    const float det = e1x * px + e1y * py + e1z * pz;
+    const float tx = r.cox - p0x, ty = r.coy - p0y, tz = r.coz - p0z;
+    const float U = tx * px + ty * py + tz * pz;
+    const float qx = ty * e1z - tz * e1y, qy = tz * e1x - tx * e1z, qz = tx * e1y - ty * e1x;
+    const float V = r.fdx * qx + r.fdy * qy + r.fdz * qz;
+    const float T = e2x * qx + e2y * qy + e2z * qz;
+    const float E1 = fmaxf(fmaxf(fabsf(e1x), fabsf(e1y)), fabsf(e1z));
+    const float E2 = fmaxf(fmaxf(fabsf(e2x), fabsf(e2y)), fabsf(e2z));
+    const float TV = fmaxf(fmaxf(fabsf(tx), fabsf(ty)), fabsf(tz));
+    const float k = 7.62939453125e-06f;              // 2^-17
+    const float mt = k * (maxCoord + TV);
+    const float eDet = k * E1 * E2, eU = mt * E2, eV = mt * E1, eT = mt * E1 * E2;
+    const float D = fabsf(det);
+    if (!(D > eDet)) return true;                    // sign of det uncertain (or NaN): exact test decides
+    const float sgn = det < 0.f ? -1.f : 1.f;
+    const float Us = sgn * U, Vs = sgn * V, Ts = sgn * T, Dhi = D + eDet;
+    if (Us + eU < 0.f) return false;                 // u < 0
+    if (Us - eU > Dhi) return false;                 // u > 1
+    if (Vs + eV < 0.f) return false;                 // v < 0
+    if ((Us + Vs) - (eU + eV) > Dhi) return false;   // u + v > 1
+    if (Ts + eT < 0.f) return false;                 // t below the culling origin (outside the world box)
+    if (Ts - eT > r.ctmax * Dhi) return false;       // t > current maxDist
+    return true;
+}
+
 template <int TRI_FMT>
 SPB_HD bool triTestRecord(const SceneParams& sp, const RayState& r, uint32_t index, double* t, double* u,
-                          double* v, int32_t* id, int32_t* rank) {
+                          double* v, int32_t* id, int32_t* rank, TraceCounters* ctr = nullptr) {
     double p0[3], p1[3], p2[3];
     if (TRI_FMT == 0) {
         const TriF32* tp = (const TriF32*)sp.tris + index;
         const U4 a = ldg4(&tp->v0[0]), b = ldg4(&tp->v1[0]), c = ldg4(&tp->v2[0]);
+        if (!triPretestMayHit(r, sp.max_coord, a, b, c)) return false;
         p0[0] = (double)asFloat(a.x); p0[1] = (double)asFloat(a.y); p0[2] = (double)asFloat(a.z);
         p1[0] = (double)asFloat(b.x); p1[1] = (double)asFloat(b.y); p1[2] = (double)asFloat(b.z);
         p2[0] = (double)asFloat(c.x); p2[1] = (double)asFloat(c.y); p2[2] = (double)asFloat(c.z);
@@ -190,6 +236,7 @@ SPB_HD bool triTestRecord(const SceneParams& sp, const RayState& r, uint32_t ind
         p2[0] = mk(d.x, d.y); p2[1] = mk(d.z, d.w); p2[2] = mk(e.x, e.y);
         *id = (int32_t)e.z; *rank = (int32_t)e.w;
     }
+    if (ctr) ctr->exact++;
     return triTestExact(r, p0, p1, p2, t, u, v);
 }
 
@@ -277,7 +324,7 @@ struct Traverser {
             tgroup.y &= tgroup.y - 1u;
             double t, u, v; int32_t id, rank;
             if (ctr) ctr->tris++;
-            if (triTestRecord<TRI_FMT>(sp, r, tgroup.x + (uint32_t)i, &t, &u, &v, &id, &rank)) {
+            if (triTestRecord<TRI_FMT>(sp, r, tgroup.x + (uint32_t)i, &t, &u, &v, &id, &rank, ctr)) {
                 if (ANY_HIT) { r.best_prim = id; r.best_t = t; finished = true; return; }
                 // t <= best_t here.  Exact tie: the smaller rank wins (see spica_b200.h,
                 // spb_bvh_import_binary); a first hit at t == tmax is accepted.
@@ -294,6 +341,8 @@ struct Traverser {
         }
     }
 };
+
+
 
 template <int TRI_FMT, bool ANY_HIT>
 SPB_HD void traceRay(const SceneParams& sp, RayState& r, bool valid, TraceCounters* ctr) {

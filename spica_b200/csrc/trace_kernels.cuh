@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(256) traceSimpleKernel(SceneParams sp, const R
     if (i >= n) return;
     RayState r;
     const bool valid = loadRay(sp, rays, i, r);
-    TraceCounters c = {0ull, 0ull};
+    TraceCounters c = {0ull, 0ull, 0ull};
     traceRay<FMT, ANY>(sp, r, valid, COUNT ? &c : nullptr);
     out.store(i, r);
     if (COUNT) { atomicAdd(ctr + 1, c.nodes); atomicAdd(ctr + 2, c.tris); }
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(256) traceSimpleKernel(SceneParams sp, const R
 // REFILL_MIN: a warp goes back to the cursor once at least this many lanes are idle.
 // ctr[0] is the global ray cursor (zeroed before the launch).  n_dev, when non-NULL, overrides n.
 template <int FMT, bool ANY, bool COUNT, class RayT, class Out, int REFILL_MIN, int STEPS>
-__global__ void __launch_bounds__(128) tracePersistentKernel(SceneParams sp, const RayT* __restrict__ rays, int64_t n,
+__global__ void __launch_bounds__(128, 7) tracePersistentKernel(SceneParams sp, const RayT* __restrict__ rays, int64_t n,
                                                            const uint32_t* __restrict__ n_dev, Out out,
                                                            unsigned long long* ctr) {
     const unsigned full = 0xffffffffu;
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(128) tracePersistentKernel(SceneParams sp, con
     if (n_dev) n = (int64_t)__ldg(n_dev);
     Traverser<FMT, ANY> tr;
     RayState r;
-    TraceCounters c = {0ull, 0ull};
+    TraceCounters c = {0ull, 0ull, 0ull};
     int64_t mine = -1;
     bool active = false, exhausted = (n <= 0);
 
@@ -146,6 +146,7 @@ __global__ void __launch_bounds__(128) tracePersistentKernel(SceneParams sp, con
     if (COUNT) { atomicAdd(ctr + 1, c.nodes); atomicAdd(ctr + 2, c.tris); }
 }
 
+
 // ---- launch ------------------------------------------------------------------------------------
 // `cursor` points at 4 x u64: [0] the ray cursor (zeroed here), [1] node visits, [2] triangle tests.
 template <int FMT, bool ANY, bool COUNT, class RayT, class Out>
@@ -159,7 +160,7 @@ static int launchTraceTyped(spb_ctx* ctx, const RayT* d_rays, int64_t n, const u
         const int64_t grid = (n + block - 1) / block;
         traceSimpleKernel<FMT, ANY, COUNT, RayT, Out><<<(unsigned)grid, block, 0, st>>>(ctx->sp, d_rays, n, out, cursor);
     } else {
-        auto kern = tracePersistentKernel<FMT, ANY, COUNT, RayT, Out, 8, 2>;
+        void (*kern)(SceneParams, const RayT*, int64_t, const uint32_t*, Out, unsigned long long*) = tracePersistentKernel<FMT, ANY, COUNT, RayT, Out, 8, 2>;
         const int block = 128;
         int perSm = ctx->opt_ctas_per_sm;
         if (perSm <= 0) {

@@ -20,7 +20,7 @@ def lib():
         L.emul_destroy.argtypes = [C.c_void_p]
         L.emul_stats.argtypes = [C.c_void_p, C.c_void_p]
         L.emul_sah.restype = C.c_double; L.emul_sah.argtypes = [C.c_void_p]
-        L.emul_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int] + [C.c_void_p] * 5 + [C.c_int]
+        L.emul_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_int]
         _lib = L
     return _lib
 
@@ -40,16 +40,17 @@ class Emul:
         self.n_wide, self.tri_format, self.max_depth, self.n_binary = [int(x) for x in st]
         self.sah = lib().emul_sah(self.h)
 
-    def trace(self, rays, any_hit=False, threads=os.cpu_count() or 1):
+    def trace(self, rays, any_hit=False, threads=os.cpu_count() or 1, mode=0):
         rays = np.ascontiguousarray(rays)
         n = rays.shape[0]
         prim = np.empty(n, np.int32); t = np.empty(n, np.float64)
         u = np.empty(n, np.float32); v = np.empty(n, np.float32)
-        ctr = np.zeros(2, np.uint64)
+        ctr = np.zeros(3, np.uint64)
         lib().emul_trace(self.h, rays.ctypes.data, int(rays.dtype == np.float64), n, int(any_hit),
-                         prim.ctypes.data, t.ctypes.data, u.ctypes.data, v.ctypes.data, ctr.ctypes.data, threads)
+                         prim.ctypes.data, t.ctypes.data, u.ctypes.data, v.ctypes.data, ctr.ctypes.data, threads, mode)
         self.node_visits = int(ctr[0]) / max(n, 1)
         self.tri_tests = int(ctr[1]) / max(n, 1)
+        self.exact_tests = int(ctr[2]) / max(n, 1)
         return prim, t, u, v
 
     def __del__(self):

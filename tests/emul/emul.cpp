@@ -2,6 +2,8 @@
 // __host__ instantiation of the per-ray traversal (trace_core.h), so that node encoding, octant
 // ordering, stack handling and the exact triangle test can be checked against the oracle on a
 // machine without a GPU.  Nothing in the product loads this library.
+#include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <string>
@@ -43,6 +45,7 @@ Emul* emul_create(const double* verts, int64_t n, int max_leaf, int bins, const 
     sp.tri_format = e->bvh.tri_format;
     sp.inflate = (float)e->bvh.inflate;
     for (int k = 0; k < 3; k++) { sp.wlo[k] = e->bvh.wlo[k] - 2 * e->bvh.inflate; sp.whi[k] = e->bvh.whi[k] + 2 * e->bvh.inflate; }
+    { double m = 0.0; for (int k = 0; k < 3; k++) m = std::max(m, std::max(std::abs(sp.wlo[k]), std::abs(sp.whi[k]))); sp.max_coord = (float)(m * 1.0000002); }
     return e;
 }
 const char* emul_error(Emul* e) { return e->err.c_str(); }
@@ -53,12 +56,12 @@ void emul_stats(Emul* e, int64_t* out) {
 }
 double emul_sah(Emul* e) { return e->bvh.sah_cost; }
 
-// rays: n x 8 (f32 or f64); out: prim i32[n], t f64[n], u f32[n], v f32[n]; counters u64[2]
+// rays: n x 8 (f32 or f64); out: prim i32[n], t f64[n], u f32[n], v f32[n]; counters u64[3]
 void emul_trace(Emul* e, const void* rays, int f64, int64_t n, int any, int32_t* prim, double* t, float* u,
-                float* v, unsigned long long* counters, int threads) {
+                float* v, unsigned long long* counters, int threads, int mode) {
     if (threads < 1) threads = 1;
     std::vector<std::thread> pool;
-    std::vector<TraceCounters> ctrs((size_t)threads, TraceCounters{0, 0});
+    std::vector<TraceCounters> ctrs((size_t)threads, TraceCounters{0, 0, 0});
     for (int th = 0; th < threads; th++) {
         pool.emplace_back([&, th]() {
             const int64_t b = n * th / threads, en = n * (th + 1) / threads;
@@ -68,6 +71,7 @@ void emul_trace(Emul* e, const void* rays, int f64, int64_t n, int any, int32_t*
                 else { const float* p = (const float*)rays + i * 8; for (int k = 0; k < 3; k++) { o[k] = p[k]; d[k] = p[3 + k]; } tmax = p[7]; }
                 RayState r;
                 const bool valid = rayBegin(e->sp, o[0], o[1], o[2], d[0], d[1], d[2], tmax, r);
+                (void)mode;
                 if (e->sp.tri_format == 0) { if (any) traceRay<0, true>(e->sp, r, valid, &ctrs[th]); else traceRay<0, false>(e->sp, r, valid, &ctrs[th]); }
                 else { if (any) traceRay<1, true>(e->sp, r, valid, &ctrs[th]); else traceRay<1, false>(e->sp, r, valid, &ctrs[th]); }
                 prim[i] = r.best_prim;
@@ -77,8 +81,8 @@ void emul_trace(Emul* e, const void* rays, int f64, int64_t n, int any, int32_t*
         });
     }
     for (auto& th : pool) th.join();
-    counters[0] = counters[1] = 0;
-    for (auto& c : ctrs) { counters[0] += c.nodes; counters[1] += c.tris; }
+    counters[0] = counters[1] = counters[2] = 0;
+    for (auto& c : ctrs) { counters[0] += c.nodes; counters[1] += c.tris; counters[2] += c.exact; }
 }
 
 }  // extern "C"

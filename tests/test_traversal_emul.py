@@ -133,3 +133,28 @@ def test_degenerate_inputs():
         p, t, _, _ = e.trace(rays)
         assert p[0] >= 0 and t[0] == 1.0 and p[1] == -1
     assert Emul(stack).trace(rays)[0][0] == 0          # lowest index among 20 exact ties
+
+
+
+def test_float32_pretest_is_conservative_under_bad_conditioning():
+    """The float32 pre-test (trace_core.h triPretestMayHit) may only drop candidates the exact test
+    rejects. Scaled / translated copies of the mesh and far ray origins stress its error bounds:
+    results stay bit-exact while the fraction of candidates reaching the double test varies."""
+    v, f = scenes.torus_mesh(120, 60)
+    frac = {}
+    for scale, shift in [(1.0, 0.0), (1e-3, 0.0), (1e3, 0.0), (1.0, 1000.0), (1e-2, 50.0), (100.0, -7000.0)]:
+        vv = (v.astype(np.float64) * scale + shift).astype(np.float32)
+        tris = scenes.mesh_triangles(vv, f)
+        rays = scenes.incoherent_rays(6000, vv.min(0), vv.max(0), seed=7)
+        far = rays.copy()
+        far[:, :3] -= far[:, 3:6] * np.float32(abs(scale) * 50)
+        allr = np.concatenate([rays, far])
+        e = Emul(tris, max_leaf=1)
+        nodes = ob.bvh_build(tris)
+        p0, t0, _, _ = ob.trace_closest(nodes, tris, allr)
+        p, t, _, _ = e.trace(allr)
+        assert np.array_equal(t, t0)
+        verify_ties(tris, allr, p, p0, t0)
+        frac[(scale, shift)] = e.exact_tests / max(e.tri_tests, 1e-9)
+    assert frac[(1.0, 0.0)] < 0.45          # well-conditioned: most candidates never reach the double test
+    assert frac[(1e-2, 50.0)] > 0.9         # coordinates >> triangle size: the pre-test abstains, still exact
