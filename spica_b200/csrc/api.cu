@@ -170,9 +170,14 @@ int spb_bvh_build(spb_ctx* ctx, const spb_build_opts* opts) {
     if (opts) o = *opts;
     if (o.max_leaf_tris <= 0) o.max_leaf_tris = 1;
     if (o.sah_bins <= 0) o.sah_bins = 32;
-    if (o.builder != 0) return fail(ctx, SPB_ERR_UNSUPPORTED, "spb_bvh_build: only builder 0 (host binned SAH) is available in this build");
+    if (o.builder != 0 && o.builder != 1) return fail(ctx, SPB_ERR_UNSUPPORTED, "spb_bvh_build: builder must be 0 (host binned SAH) or 1 (GPU LBVH)");
     const auto t0 = std::chrono::steady_clock::now();
-    build_binary_sah(ctx->verts.data(), ctx->n_tris, o.sah_bins, &ctx->bin);
+    if (o.builder == 1) {
+        const int rc = buildLbvhDevice(ctx, &ctx->bin);
+        if (rc) return rc;
+    } else {
+        build_binary_sah(ctx->verts.data(), ctx->n_tris, o.sah_bins, &ctx->bin);
+    }
     std::string err;
     if (!encode_wide(ctx->bin, ctx->verts.data(), ctx->n_tris, o.max_leaf_tris, &ctx->bvh, &err))
         return fail(ctx, SPB_ERR_UNSUPPORTED, "spb_bvh_build: " + err);

@@ -66,6 +66,7 @@ bool cudaOk(spb_ctx* ctx, cudaError_t e, const char* what);
 void setGlobalError(const std::string& msg);
 void renderStateDestroy(spb_ctx* ctx);   // integrator.cu
 void renderSceneChanged(spb_ctx* ctx);   // integrator.cu
+int  buildLbvhDevice(spb_ctx* ctx, BinaryBVH* out);   // lbvh.cu
 }  // namespace spb
 
 #define SPB_CUDA(ctx, call)                                                      \

@@ -175,3 +175,34 @@ def test_full_size_properties_1m_triangles(gpu_ctx):
     assert (gpu_ctx.trace_any(r2) == 0).all()
     # any-hit agrees with closest-hit existence on the same rays
     assert np.array_equal(gpu_ctx.trace_any(rays[:200000]), (hits["prim"][:200000] >= 0).astype(np.uint8))
+
+
+def test_gpu_lbvh_builder_gives_identical_hits(gpu_ctx, golden_torus, golden_cube):
+    """builder = 1: Morton sort + Karras hierarchy + refit on the device (replaces the reference's
+    top-down BVHAccel::constructRec). Any valid tree must return the reference's (prim, t)."""
+    for g in (golden_torus, golden_cube):
+        gpu_ctx.set_triangles(g["tris"])
+        gpu_ctx.build(builder=1)
+        _check_closest(gpu_ctx, g["tris"], g["rays"], g["prim"], g["t"])
+        assert np.array_equal(gpu_ctx.trace_any(g["any_rays"]), g["occluded"])
+    # single triangle and duplicated triangles (equal Morton codes)
+    one = np.array([[0, 0, 0, 1, 0, 0, 0, 1, 0]], dtype=np.float64)
+    gpu_ctx.set_triangles(one)
+    gpu_ctx.build(builder=1)
+    r = np.array([[0.2, 0.2, 1, 0, 0, -1, 0, 1e32]], dtype=np.float32)
+    assert gpu_ctx.trace_closest(r)["prim"][0] == 0
+    dup = np.repeat(one, 9, axis=0)
+    gpu_ctx.set_triangles(dup)
+    gpu_ctx.build(builder=1)
+    assert gpu_ctx.trace_closest(r)["prim"][0] == 0          # exact tie -> lowest index
+    # medium mesh against the oracle, plus the build statistics
+    v, f = scenes.torus_mesh(300, 150)
+    tris = scenes.mesh_triangles(v, f)
+    rays = scenes.incoherent_rays(50000, v.min(0), v.max(0), seed=6)
+    nodes = ob.bvh_build(tris)
+    p0, t0, _, _ = ob.trace_closest(nodes, tris, rays)
+    gpu_ctx.set_triangles(tris)
+    gpu_ctx.build(builder=1)
+    _check_closest(gpu_ctx, tris, rays, p0, t0, max_ties=4)
+    st = gpu_ctx.stats()
+    assert st["n_binary_nodes"] == 2 * len(tris) - 1 and st["n_tris"] == len(tris)
