@@ -155,7 +155,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from spica_b200 import capi, scenes
+    from spica_b200 import capi, partition, scenes
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -175,7 +175,7 @@ def main():
 
     n = args.rays
     # weak scaling: every rank traces its own n rays of the same distribution (distinct counters)
-    rays = scenes.incoherent_rays(n, lo, hi, seed=2, start=rank * n)
+    rays = scenes.incoherent_rays(n, lo, hi, seed=2, start=partition.ray_shard(n, rank)[0])
     pin_rays = torch.empty((n, 8), dtype=torch.float32, pin_memory=True)
     pin_rays.numpy()[:] = rays
     pin_hits = torch.empty((n, 4), dtype=torch.float32, pin_memory=True)
@@ -242,7 +242,7 @@ def main():
                                                               scenes.CORNELL_CAMERA["fov"], W, H), max_depth=16, seed=7)
         barrier()
         t0 = time.perf_counter()
-        rctx.render_samples(rank, spp, world)
+        rctx.render_samples(*partition.sample_partition(spp * world, rank, world))
         if world > 1:
             rctx.film_allreduce()
         barrier()

@@ -359,6 +359,7 @@ def cornell_render(ctx, width, height, spp, max_depth=8, variant="diffuse", seed
         ctx.build()
         cam = scenes.CORNELL_CAMERA
         c2w, r2c = scenes.perspective_camera(scenes.look_at(cam["origin"], cam["target"], cam["up"]), cam["fov"], width, height)
-        ctx.render_begin(width, height, c2w, r2c, max_depth=max_depth, seed=seed)
+        kw = dict(filter="gaussian", lens_radius=scenes.ZOO_LENS[0], focal_distance=scenes.ZOO_LENS[1]) if variant == "zoo" else {}
+        ctx.render_begin(width, height, c2w, r2c, max_depth=max_depth, seed=seed, **kw)
     ctx.render_samples(first, spp, stride)
     return ctx.film_resolve()

@@ -190,18 +190,20 @@ def cornell_parts(variant="diffuse"):
     """List of parts: (name, bsdf id, quads, radiance or None).
 
     variant "diffuse": BASELINE config 0 / 2 (all Lambertian + one emitter quad);
-    variant "glossy" : config 3 (tall box rough conductor, short box dielectric)."""
+    variant "glossy" : config 3 (tall box rough conductor, short box dielectric);
+    variant "zoo"    : specular conductor, Beckmann rough dielectric, GGX rough conductor back wall; its
+                       XML also uses a thin-lens camera and a Gaussian filter."""
     parts = [
         ("floor", "white", [_quad((-1, -1, -1), (-1, -1, 1), (1, -1, 1), (1, -1, -1))], None),
         ("ceiling", "white", [_quad((-1, 1, -1), (1, 1, -1), (1, 1, 1), (-1, 1, 1))], None),
-        ("back", "white", [_quad((-1, -1, -1), (1, -1, -1), (1, 1, -1), (-1, 1, -1))], None),
+        ("back", "brushed" if variant == "zoo" else "white", [_quad((-1, -1, -1), (1, -1, -1), (1, 1, -1), (-1, 1, -1))], None),
         ("left", "red", [_quad((-1, -1, -1), (-1, 1, -1), (-1, 1, 1), (-1, -1, 1))], None),
         ("right", "green", [_quad((1, -1, -1), (1, -1, 1), (1, 1, 1), (1, 1, -1))], None),
         # emitter: faces down (e1 x e2 = -y), just below the ceiling
         ("light", "black", [_quad((-0.25, 0.995, -0.25), (0.25, 0.995, -0.25), (0.25, 0.995, 0.25), (-0.25, 0.995, 0.25))],
          (17.0, 12.0, 4.0)),
-        ("tallbox", "metal" if variant == "glossy" else "white", _box_quads(-0.33, -0.3, 0.3, 1.2, 0.3, -1.0, 0.3), None),
-        ("shortbox", "glass" if variant == "glossy" else "white", _box_quads(0.35, 0.3, 0.3, 0.6, 0.3, -1.0, -0.3), None),
+        ("tallbox", {"glossy": "metal", "zoo": "mirror"}.get(variant, "white"), _box_quads(-0.33, -0.3, 0.3, 1.2, 0.3, -1.0, 0.3), None),
+        ("shortbox", {"glossy": "glass", "zoo": "frosted"}.get(variant, "white"), _box_quads(0.35, 0.3, 0.3, 0.6, 0.3, -1.0, -0.3), None),
     ]
     return parts
 
@@ -213,8 +215,14 @@ CORNELL_BSDFS = {
     "green": ("diffuse", {"reflectance": (0.25, 0.75, 0.25)}),
     "black": ("diffuse", {"reflectance": (0.0, 0.0, 0.0)}),
     "metal": ("roughconductor", {"eta": (0.2, 0.92, 1.1), "k": (3.9, 2.45, 2.14), "alpha": 0.1}),
+    # variant "zoo": the lobes / options the other scenes do not touch
+    "mirror": ("conductor", {"eta": (0.2, 0.92, 1.1), "k": (3.9, 2.45, 2.14)}),
+    "frosted": ("roughdielectric", {"specularReflectance": (1.0, 1.0, 1.0), "specularTransmittance": (1.0, 1.0, 1.0),
+                                    "alpha": 0.2, "intIOR": 1.5, "distribution": "beckmann"}),
+    "brushed": ("roughconductor", {"eta": (0.2, 0.92, 1.1), "k": (3.9, 2.45, 2.14), "alpha": 0.3, "distribution": "ggx"}),
     "glass": ("dielectric", {"specularReflectance": (1.0, 1.0, 1.0), "specularTransmittance": (1.0, 1.0, 1.0), "intIOR": 1.5}),
 }
+ZOO_LENS = (0.04, 3.4)      # apertureRadius, focusDistance of the "zoo" variant
 CORNELL_CAMERA = {"origin": (0.0, 0.0, 3.9), "target": (0.0, 0.0, 0.0), "up": (0.0, 1.0, 0.0), "fov": 39.3}
 
 
@@ -251,13 +259,19 @@ def write_cornell(dirpath, width=512, height=512, spp=64, max_depth=8, variant="
          '    </transform>',
          '    <sampler type="independent">', '      <integer name="sampleCount" value="%d"/>' % spp, '    </sampler>',
          '    <film type="hdrfilm">', '      <integer name="width" value="%d"/>' % width,
-         '      <integer name="height" value="%d"/>' % height, '      <rfilter type="box"/>', '    </film>', '  </sensor>']
+         '      <integer name="height" value="%d"/>' % height,
+         '      <rfilter type="gaussian"/>' if variant == "zoo" else '      <rfilter type="box"/>', '    </film>', '  </sensor>']
+    if variant == "zoo":
+        i = x.index('    <float name="fov" value="%g"/>' % cam["fov"])
+        x[i + 1:i + 1] = ['    <float name="apertureRadius" value="%g"/>' % ZOO_LENS[0], '    <float name="focusDistance" value="%g"/>' % ZOO_LENS[1]]
     for b in used:
         typ, prm = CORNELL_BSDFS[b]
         x.append('  <bsdf type="%s" id="%s">' % (typ, b))
         for k, v in prm.items():
             if isinstance(v, tuple):
                 x.append('    <rgb name="%s" value="%g, %g, %g"/>' % ((k,) + v))
+            elif isinstance(v, str):
+                x.append('    <string name="%s" value="%s"/>' % (k, v))
             else:
                 x.append('    <float name="%s" value="%g"/>' % (k, v))
         x.append('  </bsdf>')

@@ -31,7 +31,7 @@ DEPTH = 8
 
 
 def main():
-    variants = sys.argv[1:] or ["diffuse", "glossy", "envtorus"]
+    variants = sys.argv[1:] or ["diffuse", "glossy", "zoo", "envtorus"]
     ref_bin = os.path.join(ROOT, "oracle", "_ref", "bin")
     for variant in variants:
         d = os.path.join(ROOT, "tests", "golden", "scenes")
