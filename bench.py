@@ -98,6 +98,43 @@ def make_scene():
     return v, f, scenes.mesh_triangles(v, f)
 
 
+def cornell_c1_side_by_side():
+    import tempfile
+    from spica_b200 import host, scenes
+    d = tempfile.mkdtemp(prefix="spb_c1_")
+    out = {"config": "Cornell box 512x512, 64 spp, max depth 8 (BASELINE configs[0])"}
+    xml = scenes.write_cornell(d, 512, 512, 64, 8)
+    # the host logs to stdout like the reference CLI; bench.py's stdout carries exactly one JSON line
+    sys.stdout.flush()
+    saved = os.dup(1)
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    os.dup2(devnull, 1)
+    try:
+        host.render_scene(xml, os.path.join(d, "warm"), seed=1, spp=1)
+        t0 = time.perf_counter()
+        img = host.render_scene(xml, os.path.join(d, "gpu"), seed=1)
+        dt = time.perf_counter() - t0
+    finally:
+        os.dup2(saved, 1)
+        os.close(saved)
+        os.close(devnull)
+    out["gpu_seconds_scene_file_to_image"] = dt
+    out["gpu_msamples_s"] = 512 * 512 * 64 / dt * 1e-6
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "bin")
+    if os.path.exists(os.path.join(ref_bin, "spica")):
+        cores = os.cpu_count() or 1
+        xml4 = scenes.write_cornell(d, 512, 512, 4, 8, name="cornell4")
+        t0 = time.perf_counter()
+        subprocess.run(["./spica", "-i", xml4, "-t", str(cores), "-o", os.path.join(d, "cpu")], cwd=ref_bin, check=True,
+                       stdout=subprocess.DEVNULL, timeout=600)
+        dt = time.perf_counter() - t0
+        ref = scenes.read_hdr(os.path.join(d, "cpu.hdr"))
+        out.update({"cpu_reference_msamples_s": 512 * 512 * 4 / dt * 1e-6, "cpu_cores": cores,
+                    "cpu_sample": "4 of 64 spp (every pass is identical work, core/integrator.cc:64); includes scene load and per-pass .hdr save like the reference CLI",
+                    "mean_radiance_gpu": float(img.mean()), "mean_radiance_cpu_4spp": float(ref.mean())})
+    return out
+
+
 def reference_arm(args):
     """The reference's own CPU implementation of the path (oracle/_ref), all host threads, on a
     bounded sample per step."""
@@ -149,6 +186,7 @@ def main():
     ap.add_argument("--max-leaf", type=int, default=1)
     ap.add_argument("--render-spp", type=int, default=32, help="spp per GPU of the side render measurement (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--chunk", type=int, default=0, help="rays per pipelined chunk of the host-buffer call (0 = library default)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -171,6 +209,8 @@ def main():
     ctx.build(max_leaf_tris=args.max_leaf)
     if args.variant >= 0:
         ctx.set_option("trace_variant", args.variant)
+    if args.chunk > 0:
+        ctx.set_option("chunk_rays", args.chunk)
     st = ctx.stats()
 
     n = args.rays
@@ -279,6 +319,14 @@ def main():
     for _ in range(2):
         ctx.trace_any_dev(d_rays, n, d_occ)
     extra["anyhit_mrays_s"] = n / (ctx.counters()["last_kernel_ms"] * 1e-3) * 1e-6
+
+    # ---- BASELINE configs[0] (Cornell box 512x512, 64 spp, depth 8): GPU through the reference-facing host
+    # (scene file -> C++ plugin surface -> C ABI) next to the reference's own CPU renderer on a bounded sample
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            extra["cornell_c1"] = cornell_c1_side_by_side()
+        except Exception as exc:                # a side measurement must not sink the headline number
+            extra["cornell_c1"] = {"error": repr(exc)}
 
     # ---- roofline (dominant kernel = the closest-hit traversal kernel; one launch per step)
     vis = visits()["incoherent"]

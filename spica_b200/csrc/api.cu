@@ -105,14 +105,16 @@ int spb_ctx_create(int device, spb_ctx** out) {
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     if ((e = cudaStreamCreateWithFlags(&ctx->h2d, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     if ((e = cudaStreamCreateWithFlags(&ctx->d2h, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    for (int i = 0; i < spb_ctx::kPipe; i++)
+        if ((e = cudaStreamCreateWithFlags(&ctx->kstream[i], cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < spb_ctx::kPipe; i++) {
         cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming);
     }
-    if ((e = cudaMalloc(&ctx->d_work, 8 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
-    cudaMemset(ctx->d_work, 0, 8 * sizeof(unsigned long long));
+    if ((e = cudaMalloc(&ctx->d_work, 4 * (spb_ctx::kPipe + 1) * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
+    cudaMemset(ctx->d_work, 0, 4 * (spb_ctx::kPipe + 1) * sizeof(unsigned long long));
     std::memset(&ctx->sp, 0, sizeof(ctx->sp));
     ctx->sp.empty = 1;
     *out = ctx;
@@ -125,7 +127,7 @@ void spb_ctx_destroy(spb_ctx* ctx) {
     cudaDeviceSynchronize();
     renderStateDestroy(ctx);
     freeBvhDevice(ctx);
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < spb_ctx::kPipe; i++) {
         if (ctx->d_in[i]) cudaFree(ctx->d_in[i]);
         if (ctx->d_out[i]) cudaFree(ctx->d_out[i]);
         cudaEventDestroy(ctx->ev_in[i]); cudaEventDestroy(ctx->ev_k[i]); cudaEventDestroy(ctx->ev_out[i]);
@@ -133,6 +135,7 @@ void spb_ctx_destroy(spb_ctx* ctx) {
     if (ctx->d_work) cudaFree(ctx->d_work);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->h2d); cudaStreamDestroy(ctx->d2h);
+    for (int i = 0; i < spb_ctx::kPipe; i++) cudaStreamDestroy(ctx->kstream[i]);
     delete ctx;
 }
 

@@ -17,6 +17,7 @@ struct spb_ctx {
     int sm_count = 0;
     cudaStream_t stream = nullptr;       // compute
     cudaStream_t h2d = nullptr, d2h = nullptr;
+    cudaStream_t kstream[4] = {};        // one per pipeline slot: the next chunk's CTAs fill SM slots as the previous kernel's tail drains
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string err;
 
@@ -36,19 +37,20 @@ struct spb_ctx {
     void* d_tris = nullptr;
     spb::SceneParams sp{};
 
-    // grow-only scratch for the host-buffer entry points (double buffered)
-    void* d_in[2] = {nullptr, nullptr};
-    void* d_out[2] = {nullptr, nullptr};
+    // grow-only scratch for the host-buffer entry points (kPipe-deep ring)
+    static constexpr int kPipe = 4;      // chunks in flight: H2D, kernel and D2H of neighbouring chunks overlap
+    void* d_in[kPipe] = {};
+    void* d_out[kPipe] = {};
     size_t in_cap = 0, out_cap = 0;
-    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
-    unsigned long long* d_work = nullptr;   // persistent-kernel work counter + traversal counters (4 x u64)
+    cudaEvent_t ev_in[kPipe] = {}, ev_k[kPipe] = {}, ev_out[kPipe] = {};
+    unsigned long long* d_work = nullptr;   // persistent-kernel work counter + traversal counters (4 x u64), one set per pipeline slot
 
     // options
     int opt_counters = 0;
     int opt_block = 128;
     int opt_ctas_per_sm = 0;             // 0 = occupancy query
     int opt_variant = 1;                 // 0 = one thread per ray, 1 = persistent dynamic fetch
-    int64_t opt_chunk = 1 << 21;         // rays per pipelined chunk on the host-buffer path
+    int64_t opt_chunk = 1 << 20;         // rays per pipelined chunk on the host-buffer path
     int64_t opt_wave_slots = 1 << 22;    // paths in flight per wave of the integrator
 
     // counters

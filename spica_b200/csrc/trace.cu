@@ -43,19 +43,19 @@ static int traceDev(spb_ctx* ctx, const RayT* d_rays, int64_t n, Out d_out) {
 
 static int ensureScratch(spb_ctx* ctx, size_t inBytes, size_t outBytes) {
     if (inBytes > ctx->in_cap) {
-        for (int i = 0; i < 2; i++) { if (ctx->d_in[i]) cudaFree(ctx->d_in[i]); ctx->d_in[i] = nullptr; }
-        for (int i = 0; i < 2; i++) SPB_CUDA(ctx, cudaMalloc(&ctx->d_in[i], inBytes));
+        for (int i = 0; i < spb_ctx::kPipe; i++) { if (ctx->d_in[i]) cudaFree(ctx->d_in[i]); ctx->d_in[i] = nullptr; }
+        for (int i = 0; i < spb_ctx::kPipe; i++) SPB_CUDA(ctx, cudaMalloc(&ctx->d_in[i], inBytes));
         ctx->in_cap = inBytes;
     }
     if (outBytes > ctx->out_cap) {
-        for (int i = 0; i < 2; i++) { if (ctx->d_out[i]) cudaFree(ctx->d_out[i]); ctx->d_out[i] = nullptr; }
-        for (int i = 0; i < 2; i++) SPB_CUDA(ctx, cudaMalloc(&ctx->d_out[i], outBytes));
+        for (int i = 0; i < spb_ctx::kPipe; i++) { if (ctx->d_out[i]) cudaFree(ctx->d_out[i]); ctx->d_out[i] = nullptr; }
+        for (int i = 0; i < spb_ctx::kPipe; i++) SPB_CUDA(ctx, cudaMalloc(&ctx->d_out[i], outBytes));
         ctx->out_cap = outBytes;
     }
     return SPB_OK;
 }
 
-// host buffers: chunked, double buffered; H2D, kernel and D2H of neighbouring chunks overlap
+// host buffers: chunked, kPipe buffers in a ring; H2D, kernel and D2H of neighbouring chunks overlap
 template <bool ANY, class Out, class RayT, class OutT>
 static int traceHost(spb_ctx* ctx, const RayT* rays, int64_t n, OutT* out) {
     if (!ctx) return fail(nullptr, SPB_ERR_INVALID, "ctx is NULL");
@@ -67,24 +67,28 @@ static int traceHost(spb_ctx* ctx, const RayT* rays, int64_t n, OutT* out) {
     int rc = ensureScratch(ctx, (size_t)chunk * sizeof(RayT), (size_t)chunk * sizeof(OutT));
     if (rc) return rc;
     SPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const bool serial = ctx->opt_counters != 0;       // counters are read back per chunk
     int64_t off = 0;
     for (int c = 0; off < n; c++, off += chunk) {
-        const int b = c & 1;
+        const int b = c % spb_ctx::kPipe;
         const int64_t m = std::min(chunk, n - off);
+        cudaStream_t ks = serial ? ctx->stream : ctx->kstream[b];
+        unsigned long long* cursor = serial ? ctx->d_work : ctx->d_work + 4 * (b + 1);
         SPB_CUDA(ctx, cudaStreamWaitEvent(ctx->h2d, ctx->ev_k[b], 0));        // buffer b consumed
         SPB_CUDA(ctx, cudaMemcpyAsync(ctx->d_in[b], rays + off, (size_t)m * sizeof(RayT), cudaMemcpyHostToDevice, ctx->h2d));
         SPB_CUDA(ctx, cudaEventRecord(ctx->ev_in[b], ctx->h2d));
-        SPB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[b], 0));
-        SPB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_out[b], 0));   // previous results drained
-        rc = launchTrace<ANY>(ctx, (const RayT*)ctx->d_in[b], m, nullptr, Out{(OutT*)ctx->d_out[b]}, ctx->d_work, ctx->stream);
+        SPB_CUDA(ctx, cudaStreamWaitEvent(ks, ctx->ev_in[b], 0));
+        SPB_CUDA(ctx, cudaStreamWaitEvent(ks, ctx->ev_out[b], 0));            // previous results drained
+        rc = launchTrace<ANY>(ctx, (const RayT*)ctx->d_in[b], m, nullptr, Out{(OutT*)ctx->d_out[b]}, cursor, ks);
         if (rc) return rc;
-        SPB_CUDA(ctx, cudaEventRecord(ctx->ev_k[b], ctx->stream));
+        SPB_CUDA(ctx, cudaEventRecord(ctx->ev_k[b], ks));
         SPB_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h, ctx->ev_k[b], 0));
         SPB_CUDA(ctx, cudaMemcpyAsync(out + off, ctx->d_out[b], (size_t)m * sizeof(OutT), cudaMemcpyDeviceToHost, ctx->d2h));
         SPB_CUDA(ctx, cudaEventRecord(ctx->ev_out[b], ctx->d2h));
-        if (ctx->opt_counters) { SPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); rc = readCounters(ctx, m); if (rc) return rc; }
+        if (serial) { SPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); rc = readCounters(ctx, m); if (rc) return rc; }
     }
     SPB_CUDA(ctx, cudaStreamSynchronize(ctx->d2h));
+    for (int i = 0; i < spb_ctx::kPipe; i++) SPB_CUDA(ctx, cudaStreamSynchronize(ctx->kstream[i]));
     SPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     SPB_CUDA(ctx, cudaStreamSynchronize(ctx->h2d));
     ctx->last_kernel_ms = -1.0;

@@ -164,8 +164,12 @@ static int launchTraceTyped(spb_ctx* ctx, const RayT* d_rays, int64_t n, const u
         const int block = 128;
         int perSm = ctx->opt_ctas_per_sm;
         if (perSm <= 0) {
-            SPB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kern, block, 0));
-            if (perSm < 1) perSm = 1;
+            static int cached = 0;           // one per kernel instantiation; the query is slow enough to matter per chunk
+            if (cached <= 0) {
+                SPB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cached, kern, block, 0));
+                if (cached < 1) cached = 1;
+            }
+            perSm = cached;
         }
         int64_t grid = (int64_t)ctx->sm_count * perSm;
         const int64_t need = (n + block - 1) / block;
