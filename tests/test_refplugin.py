@@ -124,7 +124,8 @@ def test_reference_host_envmap_scene_and_reference_accelerator(tmp_path):
         r = refhost.run(xml, out, str(tmp_path / "run"), REF, env={"SPICA_SEED": 21}, gpu_plugins=plugins)
         assert r.returncode == 0, r.stderr
         imgs.append(scenes.read_hdr(out + ".hdr"))
-    assert np.array_equal(imgs[0], imgs[1])
+    # same seed, same samples; the film's float atomics may add in a different order, so allow one RGBE step
+    assert (np.abs(imgs[0] - imgs[1]) <= imgs[0].max(-1, keepdims=True) / 128 + 1e-6).all()
     assert max(scenes.rel_mse(imgs[0], run, mean) for run in runs) <= 1.5 * float(g["pair_relmse"][0])
 
 
