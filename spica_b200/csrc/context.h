@@ -49,7 +49,7 @@ struct spb_ctx {
     int opt_counters = 0;
     int opt_block = 128;
     int opt_ctas_per_sm = 0;             // 0 = occupancy query
-    int opt_variant = 1;                 // 0 = one thread per ray, 1 = persistent dynamic fetch
+    int opt_variant = 2;                 // 0 = one thread per ray, 1 = persistent dynamic fetch, 2 = 1 + warp-cooperative pre-test
     int64_t opt_chunk = 1 << 20;         // rays per pipelined chunk on the host-buffer path
     int64_t opt_wave_slots = 1 << 22;    // paths in flight per wave of the integrator
 

@@ -32,6 +32,7 @@ SPB_HD double dsub(double a, double b) { return __dadd_rn(a, -b); }
 SPB_HD double drcp(double a) { return __drcp_rn(a); }            // == 1.0 / a, correctly rounded
 SPB_HD double dsqrt(double a) { return __dsqrt_rn(a); }
 SPB_HD float  ffma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+SPB_HD float  frcpApprox(float a) { return __fdividef(1.0f, a); }   // MUFU.RCP, <= 2 ulp for |a| < 2^126
 SPB_HD int    clz32(uint32_t x) { return __clz((int)x); }
 SPB_HD int    ctz32(uint32_t x) { return __ffs((int)x) - 1; }
 SPB_HD int    popc32(uint32_t x) { return __popc(x); }
@@ -43,6 +44,7 @@ SPB_HD double dsub(double a, double b) { return a - b; }
 SPB_HD double drcp(double a) { return 1.0 / a; }
 SPB_HD double dsqrt(double a) { return sqrt(a); }
 SPB_HD float  ffma(float a, float b, float c) { return fmaf(a, b, c); }
+SPB_HD float  frcpApprox(float a) { return 1.0f / a; }
 SPB_HD int    clz32(uint32_t x) { return x ? __builtin_clz(x) : 32; }
 SPB_HD int    ctz32(uint32_t x) { return x ? __builtin_ctz(x) : -1; }
 SPB_HD int    popc32(uint32_t x) { return __builtin_popcount(x); }
@@ -110,12 +112,13 @@ SPB_HD bool rayBegin(const SceneParams& sp, double ox, double oy, double oz, dou
     for (int k = 0; k < 3; k++) {
         if (d[k] == 0.0) {
             if (o[k] < sp.wlo[k] || o[k] > sp.whi[k]) return false;
-        } else {
-            const double inv = 1.0 / d[k];
+        } else if (fabs(d[k]) > 1e-30) {                 // below that the slab gives no usable bound: skip it
+            // float32 reciprocal (relative error < 2^-21 incl. the rounding of d): an IEEE double
+            // division costs ~15 instructions per axis and this test only prunes, so it is widened instead
+            const double inv = (double)frcpApprox((float)d[k]);
             double ta = (sp.wlo[k] - o[k]) * inv, tb = (sp.whi[k] - o[k]) * inv;
             if (ta > tb) { const double tt = ta; ta = tb; tb = tt; }
-            // widen by a relative slack: this test only prunes
-            ta -= fabs(ta) * 1e-12; tb += fabs(tb) * 1e-12;
+            ta -= fabs(ta) * 1e-6; tb += fabs(tb) * 1e-6;
             if (ta > t0) t0 = ta;
             if (tb < t1) t1 = tb;
         }
@@ -175,7 +178,9 @@ SPB_HD bool triTestExact(const RayState& r, const double p0[3], const double p1[
 // (input roundings: |d c_k| <= u (M + TV), |d dir_k| <= u, edges relative u; then the running
 // error of each 3-term product sum; derivation in DESIGN.md "float32 pre-test"). Every comparison is
 // written so that NaN / Inf fall through to the exact test.
-SPB_HD bool triPretestMayHit(const RayState& r, float maxCoord, const U4& a, const U4& b, const U4& c) {
+struct CullRay { float cox, coy, coz, fdx, fdy, fdz, ctmax; };   // what the pre-test reads of a ray (7 floats: cheap to hand to another lane)
+
+SPB_HD bool triPretestMayHit(const CullRay& r, float maxCoord, const U4& a, const U4& b, const U4& c) {
     const float p0x = asFloat(a.x), p0y = asFloat(a.y), p0z = asFloat(a.z);
     const float e1x = asFloat(b.x) - p0x, e1y = asFloat(b.y) - p0y, e1z = asFloat(b.z) - p0z;
     const float e2x = asFloat(c.x) - p0x, e2y = asFloat(c.y) - p0y, e2z = asFloat(c.z) - p0z;
@@ -205,14 +210,20 @@ SPB_HD bool triPretestMayHit(const RayState& r, float maxCoord, const U4& a, con
     return true;
 }
 
-template <int TRI_FMT>
+SPB_HD bool triPretestMayHit(const RayState& r, float maxCoord, const U4& a, const U4& b, const U4& c) {
+    const CullRay cr = {r.cox, r.coy, r.coz, r.fdx, r.fdy, r.fdz, r.ctmax};
+    return triPretestMayHit(cr, maxCoord, a, b, c);
+}
+
+// PRETEST = false: the candidate already passed the pre-test (cooperative kernel), go straight to the exact test
+template <int TRI_FMT, bool PRETEST = true>
 SPB_HD bool triTestRecord(const SceneParams& sp, const RayState& r, uint32_t index, double* t, double* u,
                           double* v, int32_t* id, int32_t* rank, TraceCounters* ctr = nullptr) {
     double p0[3], p1[3], p2[3];
     if (TRI_FMT == 0) {
         const TriF32* tp = (const TriF32*)sp.tris + index;
         const U4 a = ldg4(&tp->v0[0]), b = ldg4(&tp->v1[0]), c = ldg4(&tp->v2[0]);
-        if (!triPretestMayHit(r, sp.max_coord, a, b, c)) return false;
+        if (PRETEST && !triPretestMayHit(r, sp.max_coord, a, b, c)) return false;
         p0[0] = (double)asFloat(a.x); p0[1] = (double)asFloat(a.y); p0[2] = (double)asFloat(a.z);
         p1[0] = (double)asFloat(b.x); p1[1] = (double)asFloat(b.y); p1[2] = (double)asFloat(b.z);
         p2[0] = (double)asFloat(c.x); p2[1] = (double)asFloat(c.y); p2[2] = (double)asFloat(c.z);
@@ -285,8 +296,10 @@ SPB_HD uint32_t nodeHitMask(const U4& n0, const U4& n1, const U4& n2, const U4& 
     return hitmask;
 }
 
-// The traversal state machine.  step() consumes one node group entry: it visits one inner node
-// (tests its 8 child boxes) and then tests the triangles of the leaves that were hit.
+// The traversal state machine.  One step consumes one node group entry: nodePhase (visit one inner
+// node, test its 8 child boxes) -> triPhase (test the triangles of the leaves that were hit) ->
+// popPhase (next node group).  The cooperative kernel runs its own warp-wide pre-test between
+// nodePhase and triPhase<false>.
 template <int TRI_FMT, bool ANY_HIT>
 struct Traverser {
     U2 stack[kStackCapacity];
@@ -300,31 +313,34 @@ struct Traverser {
         finished = !valid;
     }
 
-    SPB_HD void step(const SceneParams& sp, RayState& r, TraceCounters* ctr) {
+    SPB_HD U2 nodePhase(const SceneParams& sp, const RayState& r, TraceCounters* ctr) {
+        const uint32_t hits = ngroup.y;
+        const int bit = 31 - clz32(hits);
+        ngroup.y &= ~(1u << bit);
+        if (ngroup.y & 0xff000000u) stack[sp_++] = ngroup;
+        const uint32_t slot = (uint32_t)(bit - 24) ^ r.oct_inv;
+        const uint32_t rel = (uint32_t)popc32(hits & ~(0xffffffffu << slot) & 0xffu);
+        const WideNode* np = sp.nodes + (ngroup.x + rel);
+        const U4 n0 = ldg4((const char*)np), n1 = ldg4((const char*)np + 16), n2 = ldg4((const char*)np + 32),
+                 n3 = ldg4((const char*)np + 48), n4 = ldg4((const char*)np + 64);
+        const uint32_t hm = nodeHitMask(n0, n1, n2, n3, n4, r);
+        if (ctr) ctr->nodes++;
+        ngroup.x = n1.x;
+        ngroup.y = (hm & 0xff000000u) | (n0.w >> 24);
         U2 tgroup;
-        {
-            const uint32_t hits = ngroup.y;
-            const int bit = 31 - clz32(hits);
-            ngroup.y &= ~(1u << bit);
-            if (ngroup.y & 0xff000000u) stack[sp_++] = ngroup;
-            const uint32_t slot = (uint32_t)(bit - 24) ^ r.oct_inv;
-            const uint32_t rel = (uint32_t)popc32(hits & ~(0xffffffffu << slot) & 0xffu);
-            const WideNode* np = sp.nodes + (ngroup.x + rel);
-            const U4 n0 = ldg4((const char*)np), n1 = ldg4((const char*)np + 16), n2 = ldg4((const char*)np + 32),
-                     n3 = ldg4((const char*)np + 48), n4 = ldg4((const char*)np + 64);
-            const uint32_t hm = nodeHitMask(n0, n1, n2, n3, n4, r);
-            if (ctr) ctr->nodes++;
-            ngroup.x = n1.x;
-            ngroup.y = (hm & 0xff000000u) | (n0.w >> 24);
-            tgroup.x = n1.y;
-            tgroup.y = hm & 0x00ffffffu;
-        }
+        tgroup.x = n1.y;
+        tgroup.y = hm & 0x00ffffffu;
+        return tgroup;
+    }
+
+    template <bool PRETEST>
+    SPB_HD void triPhase(const SceneParams& sp, RayState& r, U2 tgroup, TraceCounters* ctr) {
         while (tgroup.y) {
             const int i = ctz32(tgroup.y);
             tgroup.y &= tgroup.y - 1u;
             double t, u, v; int32_t id, rank;
-            if (ctr) ctr->tris++;
-            if (triTestRecord<TRI_FMT>(sp, r, tgroup.x + (uint32_t)i, &t, &u, &v, &id, &rank, ctr)) {
+            if (ctr && PRETEST) ctr->tris++;
+            if (triTestRecord<TRI_FMT, PRETEST>(sp, r, tgroup.x + (uint32_t)i, &t, &u, &v, &id, &rank, ctr)) {
                 if (ANY_HIT) { r.best_prim = id; r.best_t = t; finished = true; return; }
                 // t <= best_t here.  Exact tie: the smaller rank wins (see spica_b200.h,
                 // spb_bvh_import_binary); a first hit at t == tmax is accepted.
@@ -335,10 +351,20 @@ struct Traverser {
                 }
             }
         }
+    }
+
+    SPB_HD void popPhase() {
+        if (finished) return;
         if (!(ngroup.y & 0xff000000u)) {
             if (sp_ == 0) { finished = true; return; }
             ngroup = stack[--sp_];
         }
+    }
+
+    SPB_HD void step(const SceneParams& sp, RayState& r, TraceCounters* ctr) {
+        const U2 tgroup = nodePhase(sp, r, ctr);
+        triPhase<true>(sp, r, tgroup, ctr);
+        popPhase();
     }
 };
 

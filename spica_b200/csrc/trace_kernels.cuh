@@ -147,6 +147,110 @@ __global__ void __launch_bounds__(128, 7) tracePersistentKernel(SceneParams sp, 
 }
 
 
+// ---- variant 2: persistent threads + warp-cooperative triangle pre-test --------------------------
+// In variant 1 every lane walks ITS OWN candidate list after a node visit, so the warp runs
+// max-over-lanes rounds of the float32 pre-test with 3-6 lanes alive (mean 0.5 candidates per lane
+// and node visit; profiles/r01c: 37 % of all issue slots).  Here the candidates of the whole warp are
+// pooled: an inclusive scan of the per-lane counts numbers them, lane j takes pooled candidate j
+// (owner found by a 5-step shuffle search over the scan, culling ray fetched from the owner with
+// seven shuffles), and the survivors go back to the owner as a bit mask through shared memory.
+// One full-width round usually covers the warp.  Only the owner runs the exact double test.
+template <int FMT, bool ANY, bool COUNT, class RayT, class Out, int REFILL_MIN>
+__global__ void __launch_bounds__(128, 7) traceCoopKernel(SceneParams sp, const RayT* __restrict__ rays, int64_t n,
+                                                          const uint32_t* __restrict__ n_dev, Out out,
+                                                          unsigned long long* ctr) {
+    __shared__ uint32_t s_filt[4][32];
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    uint32_t* filt = s_filt[threadIdx.x >> 5];
+    if (n_dev) n = (int64_t)__ldg(n_dev);
+    Traverser<FMT, ANY> tr;
+    RayState r;
+    r.cox = r.coy = r.coz = r.fdx = r.fdy = r.fdz = r.ctmax = 0.f;
+    TraceCounters c = {0ull, 0ull, 0ull};
+    int64_t mine = -1;
+    bool active = false, exhausted = (n <= 0);
+
+    for (;;) {
+        const unsigned idle = __ballot_sync(full, !active);
+        const int nIdle = __popc(idle);
+        if (!exhausted && (nIdle >= REFILL_MIN || nIdle == 32)) {
+            const int leader = __ffs(idle) - 1;
+            unsigned long long base = 0;
+            if (lane == leader) base = atomicAdd(ctr, (unsigned long long)nIdle);
+            base = __shfl_sync(full, base, leader);
+            if ((int64_t)base + nIdle >= n) exhausted = true;
+            if (!active) {
+                const int64_t idx = (int64_t)base + __popc(idle & ((1u << lane) - 1u));
+                if (idx < n) {
+                    mine = idx;
+                    const bool valid = loadRay(sp, rays, idx, r);
+                    tr.begin(valid);
+                    if (tr.finished) out.store(mine, r);   // trivial miss
+                    else active = true;
+                }
+            }
+        }
+        if (!__any_sync(full, active)) {
+            if (exhausted) break;
+            continue;
+        }
+        U2 tg; tg.x = 0u; tg.y = 0u;
+        if (active) tg = tr.nodePhase(sp, r, COUNT ? &c : nullptr);
+        if (__any_sync(full, tg.y != 0u)) {
+            if (FMT == 0) {
+                const int cnt = __popc(tg.y);
+                if (COUNT) c.tris += (unsigned long long)cnt;
+                int incl = cnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int v = __shfl_up_sync(full, incl, d);
+                    if (lane >= d) incl += v;
+                }
+                const int total = __shfl_sync(full, incl, 31);
+                filt[lane] = 0u;
+                __syncwarp();
+                for (int base = 0; base < total; base += 32) {
+                    const int j = base + lane;
+                    int L = 0;                      // number of lanes whose candidates all come before j = the owner of j
+#pragma unroll
+                    for (int s = 16; s >= 1; s >>= 1) {
+                        const int v = __shfl_sync(full, incl, L + s - 1);
+                        if (v <= j) L += s;
+                    }
+                    const int inclL = __shfl_sync(full, incl, L);
+                    const uint32_t maskL = __shfl_sync(full, tg.y, L);
+                    const uint32_t baseL = __shfl_sync(full, tg.x, L);
+                    CullRay cr;
+                    cr.cox = __shfl_sync(full, r.cox, L); cr.coy = __shfl_sync(full, r.coy, L); cr.coz = __shfl_sync(full, r.coz, L);
+                    cr.fdx = __shfl_sync(full, r.fdx, L); cr.fdy = __shfl_sync(full, r.fdy, L); cr.fdz = __shfl_sync(full, r.fdz, L);
+                    cr.ctmax = __shfl_sync(full, r.ctmax, L);
+                    if (j < total) {
+                        int k = j - (inclL - __popc(maskL));
+                        uint32_t m = maskL;
+                        for (; k > 0; k--) m &= m - 1u;
+                        const int bit = __ffs((int)m) - 1;
+                        const TriF32* tp = (const TriF32*)sp.tris + (baseL + (uint32_t)bit);
+                        const U4 a = ldg4(&tp->v0[0]), b = ldg4(&tp->v1[0]), cc = ldg4(&tp->v2[0]);
+                        if (triPretestMayHit(cr, sp.max_coord, a, b, cc)) atomicOr(&filt[L], 1u << bit);
+                    }
+                }
+                __syncwarp();
+                tg.y = filt[lane];
+                if (tg.y) tr.template triPhase<false>(sp, r, tg, COUNT ? &c : nullptr);
+            } else {
+                if (tg.y) tr.template triPhase<true>(sp, r, tg, COUNT ? &c : nullptr);
+            }
+        }
+        if (active) {
+            tr.popPhase();
+            if (tr.finished) { out.store(mine, r); active = false; }
+        }
+    }
+    if (COUNT) { atomicAdd(ctr + 1, c.nodes); atomicAdd(ctr + 2, c.tris); }
+}
+
+
 // ---- launch ------------------------------------------------------------------------------------
 // `cursor` points at 4 x u64: [0] the ray cursor (zeroed here), [1] node visits, [2] triangle tests.
 template <int FMT, bool ANY, bool COUNT, class RayT, class Out>
@@ -160,16 +264,18 @@ static int launchTraceTyped(spb_ctx* ctx, const RayT* d_rays, int64_t n, const u
         const int64_t grid = (n + block - 1) / block;
         traceSimpleKernel<FMT, ANY, COUNT, RayT, Out><<<(unsigned)grid, block, 0, st>>>(ctx->sp, d_rays, n, out, cursor);
     } else {
-        void (*kern)(SceneParams, const RayT*, int64_t, const uint32_t*, Out, unsigned long long*) = tracePersistentKernel<FMT, ANY, COUNT, RayT, Out, 8, 2>;
+        const int coop = ctx->opt_variant == 2 ? 1 : 0;
+        void (*kern)(SceneParams, const RayT*, int64_t, const uint32_t*, Out, unsigned long long*) =
+            coop ? traceCoopKernel<FMT, ANY, COUNT, RayT, Out, 8> : tracePersistentKernel<FMT, ANY, COUNT, RayT, Out, 8, 2>;
         const int block = 128;
         int perSm = ctx->opt_ctas_per_sm;
         if (perSm <= 0) {
-            static int cached = 0;           // one per kernel instantiation; the query is slow enough to matter per chunk
-            if (cached <= 0) {
-                SPB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cached, kern, block, 0));
-                if (cached < 1) cached = 1;
+            static int cached[2] = {0, 0};   // one per kernel instantiation; the query is slow enough to matter per chunk
+            if (cached[coop] <= 0) {
+                SPB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cached[coop], kern, block, 0));
+                if (cached[coop] < 1) cached[coop] = 1;
             }
-            perSm = cached;
+            perSm = cached[coop];
         }
         int64_t grid = (int64_t)ctx->sm_count * perSm;
         const int64_t need = (n + block - 1) / block;

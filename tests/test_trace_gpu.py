@@ -38,7 +38,7 @@ def _check_closest(ctx, tris, rays, prim_ref, t_ref, max_ties=0):
     return hits
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 @pytest.mark.parametrize("max_leaf", [1, 3])
 def test_golden_torus(gpu_ctx, golden_torus, variant, max_leaf):
     g = golden_torus
@@ -50,7 +50,7 @@ def test_golden_torus(gpu_ctx, golden_torus, variant, max_leaf):
     h64 = gpu_ctx.trace_closest(g["rays64"])
     assert np.array_equal(h64["prim"], g["prim64"]) and np.array_equal(h64["t"], g["t64"])
     assert np.array_equal(gpu_ctx.trace_any(_as64(g["any_rays"])), g["occluded"])
-    gpu_ctx.set_option("trace_variant", 1)
+    gpu_ctx.set_option("trace_variant", 2)
 
 
 def test_golden_cube_own_and_imported_tree(gpu_ctx, golden_cube):
