@@ -89,18 +89,20 @@ enum {
     SPB_MAT_DIELECTRIC = 1,       /* bsdfs/dielectric.cc:30-42   -> FresnelSpecular (core/bxdf.cc:156-248)      */
     SPB_MAT_ROUGHCONDUCTOR = 2,   /* bsdfs/roughconductor.cc:38-75 -> MicrofacetReflection (core/bxdf.cc:255-297) */
     SPB_MAT_ROUGHDIELECTRIC = 3,  /* bsdfs/roughdielectric.cc:41-83 -> MicrofacetTransmission (core/bxdf.cc:304-424) */
-    SPB_MAT_CONDUCTOR = 4         /* alpha == 0 roughconductor / bsdfs/conductor.cc -> SpecularReflection        */
+    SPB_MAT_CONDUCTOR = 4,        /* alpha == 0 roughconductor / bsdfs/conductor.cc -> SpecularReflection        */
+    SPB_MAT_PLASTIC = 5,          /* bsdfs/plastic.cc:20-128       -> PlasticBRDF (smooth coating over a diffuse base) */
+    SPB_MAT_ROUGHPLASTIC = 6      /* bsdfs/roughplastic.cc:20-165  -> RoughPlasticBRDF (microfacet coating)          */
 };
 enum { SPB_DISTR_BECKMANN = 0, SPB_DISTR_GGX = 1 };
 
 typedef struct spb_material {
     int32_t type;           /* SPB_MAT_*                                                              */
     int32_t distribution;   /* SPB_DISTR_* (rough materials; default "beckmann")                       */
-    float   kr[3];          /* diffuse: reflectance; dielectrics: specularReflectance; conductors: 1   */
-    float   kt[3];          /* dielectrics: specularTransmittance                                      */
-    float   eta[3];         /* conductors: eta (rgb); dielectrics: intIOR in eta[0] (extIOR is 1.0)    */
+    float   kr[3];          /* diffuse: reflectance; dielectrics, plastics: specularReflectance; conductors: 1 */
+    float   kt[3];          /* dielectrics: specularTransmittance; plastics: diffuseReflectance        */
+    float   eta[3];         /* conductors: eta (rgb); dielectrics, plastics: intIOR in eta[0] (extIOR is 1.0) */
     float   k[3];           /* conductors: absorption k (rgb)                                          */
-    float   alpha_u, alpha_v; /* microfacet roughness (no remap, bsdfs/roughconductor.cc:33)           */
+    float   alpha_u, alpha_v; /* microfacet roughness (no remap, bsdfs/roughconductor.cc:33); roughplastic: alpha_u */
 } spb_material;             /* 64 B */
 int spb_scene_set_materials(spb_ctx* ctx, const spb_material* mats, int32_t n);
 

@@ -60,7 +60,8 @@ class RenderStats(C.Structure):
                 ("rays_mis", C.c_int64), ("kernel_launches", C.c_int64), ("render_ms", C.c_double)]
 
 
-MAT_TYPES = {"none": -1, "diffuse": 0, "dielectric": 1, "roughconductor": 2, "roughdielectric": 3, "conductor": 4}
+MAT_TYPES = {"none": -1, "diffuse": 0, "dielectric": 1, "roughconductor": 2, "roughdielectric": 3, "conductor": 4,
+             "plastic": 5, "roughplastic": 6}
 FILTERS = {"box": 0, "tent": 1, "gaussian": 2}
 assert C.sizeof(Material) == 64 and C.sizeof(Light) == 24
 
@@ -264,8 +265,8 @@ class Context:
             a.type = MAT_TYPES[m["type"]]
             a.distribution = 1 if m.get("distribution", "beckmann") == "ggx" else 0
             kr = m.get("reflectance", m.get("specularReflectance", (1.0, 1.0, 1.0)))
-            kt = m.get("specularTransmittance", (1.0, 1.0, 1.0))
-            default_ior = 1.3333 if m["type"] == "roughdielectric" else 1.333
+            kt = m.get("specularTransmittance", m.get("diffuseReflectance", (1.0, 1.0, 1.0)))
+            default_ior = {"roughdielectric": 1.3333, "plastic": 1.5, "roughplastic": 1.5}.get(m["type"], 1.333)
             eta = m.get("eta", (m.get("intIOR", default_ior),) * 3)
             k = m.get("k", (0.0, 0.0, 0.0))
             for j in range(3):

@@ -392,10 +392,41 @@ SPB_SHD Bsdf makeBsdf(const spb_material& m) {
         else if (m.alpha_u == 0.f && m.alpha_v == 0.f) { b.type = SPB_MAT_DIELECTRIC; b.flags = kBxReflection | kBxTransmission | kBxSpecular; }
         else b.flags = kBxReflection | kBxTransmission | kBxGlossy;
         break;
+    case SPB_MAT_PLASTIC:                                                         // bsdfs/plastic.cc:22-33,118-128: kr = Ks, kt = Kd
+        b.flags = kBxReflection | kBxSpecular | kBxDiffuse;
+        break;
+    case SPB_MAT_ROUGHPLASTIC: {                                                  // bsdfs/roughplastic.cc:22-33,130-165
+        const float rough = fmaxf(0.001f, m.alpha_u);
+        b.mf.ax = b.mf.ay = rough;
+        if (isBlack(b.kr)) { b.type = SPB_MAT_DIFFUSE; b.kr = b.kt; b.flags = kBxReflection | kBxDiffuse; }   // LambertianReflection(kd), added even when kd is black
+        else b.flags = kBxReflection | kBxDiffuse | kBxGlossy;
+        break;
+    }
     default: b.type = SPB_MAT_NONE; break;
     }
     return b;
 }
+
+// core/fresnel.cc:87-95
+SPB_SHD float frDiffuseReflectance(float eta) {
+    if (eta >= 1.f) return -1.4399f / (eta * eta) + 0.7099f / eta + 0.6681f + 0.0636f * eta;
+    return -0.4399f + 0.7099f / eta - 0.3319f / (eta * eta) + 0.0636f / (eta * eta * eta);
+}
+// PlasticBRDF / RoughPlasticBRDF (bsdfs/plastic.cc:20-88, bsdfs/roughplastic.cc:20-98): kr = Ks, kt = Kd, etaA = 1, etaB = ior.
+// Their f / pdf / sample are kept as the reference wrote them, including what looks unintended: the
+// "specular" test of PlasticBRDF::f/pdf mirrors wi about the normal and compares it with wi itself
+// (true only for wi exactly along the normal), and the diffuse branches sample the +z hemisphere
+// whatever side wo is on.
+SPB_SHD float plasticProbSpecular(const Bsdf& b, float Fo) {
+    const float w = gray(b.kr) / (gray(b.kt) + gray(b.kr));
+    return (Fo * w) / (Fo * w + (1.f - Fo) * (1.f - w));
+}
+SPB_SHD V3 plasticDiffuse(const Bsdf& b, float Fo, float cosI) {
+    const float invEta = 1.f / b.ior;
+    const float Fi = frDielectric(cosI, 1.f, b.ior);
+    return b.kt * ((1.f - Fo) * (1.f - Fi) * invEta * invEta * kInvPi / (1.f - frDiffuseReflectance(b.ior)));
+}
+SPB_SHD bool plasticAlongNormal(V3 wi) { return wi.z * wi.z - wi.x * wi.x - wi.y * wi.y > 1.f; }   // > 1 - 1e-12 in float
 
 // BSDF::numComponents (core/bsdf.cc:28-36): a lobe counts only if ALL its flags are inside `type`
 SPB_SHD int bsdfNumComponents(const Bsdf& b, int type) { return (b.flags != 0 && (b.flags & type) == b.flags) ? 1 : 0; }
@@ -468,6 +499,18 @@ SPB_SHD V3 lobeF(const Bsdf& b, V3 wo, V3 wi) {
         }
         return v3(0.f);
     }
+    case SPB_MAT_PLASTIC: {                                                       // bsdfs/plastic.cc:32-46
+        const float Fo = frDielectric(wo.z, 1.f, b.ior);
+        if (plasticAlongNormal(wi)) return b.kr * (Fo / fabsf(wi.z));
+        return plasticDiffuse(b, Fo, wi.z);
+    }
+    case SPB_MAT_ROUGHPLASTIC: {                                                  // bsdfs/roughplastic.cc:35-47
+        if (wo.z == 0.f || wi.z == 0.f) return v3(0.f);
+        if (!(wo.z * wi.z > 0.f)) return v3(0.f);
+        const V3 wh = normalize(wi + wo);
+        const float F = frDielectric(dot(wo, wh), 1.f, b.ior);
+        return b.kr * (F * mfD(b.mf, wh) * mfG(b.mf, wo, wi, wh) / (4.f * wo.z * wi.z)) + b.kt * ((1.f - F) * kInvPi);
+    }
     default: return v3(0.f);
     }
 }
@@ -489,6 +532,17 @@ SPB_SHD float lobePdf(const Bsdf& b, V3 wo, V3 wi) {
             if (dot(wi, wt) > 1.f - kDeltaEps) return 1.f - F;
         }
         return 0.f;
+    }
+    case SPB_MAT_PLASTIC: {                                                       // bsdfs/plastic.cc:70-82
+        const float ps = plasticProbSpecular(b, frDielectric(wo.z, 1.f, b.ior));
+        if (plasticAlongNormal(wi)) return ps;
+        return (1.f - ps) * fabsf(wi.z) * kInvPi;
+    }
+    case SPB_MAT_ROUGHPLASTIC: {                                                  // bsdfs/roughplastic.cc:88-96
+        if (!(wo.z * wi.z > 0.f)) return 0.f;
+        const V3 wh = normalize(wi + wo);
+        const float F = frDielectric(dot(wo, wh), 1.f, b.ior);
+        return F * mfPdf(b.mf, wo, wh) / (4.f * absDot(wo, wh)) + (1.f - F) * fabsf(wi.z) * kInvPi;
     }
     default: return 0.f;
     }
@@ -552,6 +606,33 @@ SPB_SHD V3 lobeSample(const Bsdf& b, V3 wo, float u0, float u1, float u2, V3* wi
         const V3 whp = wh.z >= 0.f ? wh : -wh;
         *pdf = mfTransPdf(b, wo, *wi, whp);
         return mfTransF(b, wo, *wi, whp);
+    }
+    case SPB_MAT_PLASTIC: {                                                       // bsdfs/plastic.cc:48-68 (u2: its thread_local Random)
+        const float Fo = frDielectric(wo.z, 1.f, b.ior);
+        const float ps = plasticProbSpecular(b, Fo);
+        if (u2 < ps) {
+            *wi = v3(-wo.x, -wo.y, wo.z);
+            *pdf = ps;
+            return b.kr * (Fo / fabsf(wi->z));
+        }
+        *wi = cosineHemisphere(u0, u1);
+        *pdf = (1.f - ps) * fabsf(wi->z) * kInvPi;
+        return plasticDiffuse(b, Fo, wi->z);
+    }
+    case SPB_MAT_ROUGHPLASTIC: {                                                  // bsdfs/roughplastic.cc:49-86
+        if (wo.z == 0.f) return v3(0.f);
+        const V3 wh = mfSample(b.mf, wo, u0, u1);
+        const float Fo = frDielectric(dot(wo, wh), 1.f, b.ior);
+        const float ps = plasticProbSpecular(b, Fo);
+        if (u2 < ps) {
+            *wi = -wo + wh * (2.f * dot(wh, wo));
+            if (!(wo.z * wi->z > 0.f)) return v3(0.f);
+            *pdf = ps * mfPdf(b.mf, wo, wh) / (4.f * absDot(wo, wh));
+            return b.kr * (Fo * mfD(b.mf, wh) * mfG(b.mf, wo, *wi, wh) / (4.f * wo.z * wi->z));
+        }
+        *wi = cosineHemisphere(u0, u1);
+        *pdf = (1.f - ps) * fabsf(wi->z) * kInvPi;
+        return plasticDiffuse(b, Fo, wi->z);
     }
     default: return v3(0.f);
     }

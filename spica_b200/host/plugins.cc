@@ -207,6 +207,43 @@ private:
     Spectrum kr_, kt_; double au_, av_, ior_; int distr_;
 };
 
+class Plastic : public SurfaceMaterial {                  // bsdfs/plastic.cc:102-128
+public:
+    explicit Plastic(RenderParams& p) {
+        bool f1, f2;
+        kd_ = p.getTexture("diffuseReflectance", false, &f1);
+        ks_ = p.getTexture("specularReflectance", false, &f2);
+        SpicaAssert(f1 && f2, "plastic needs diffuseReflectance and specularReflectance (the reference dereferences null otherwise, plastic.cc:122-123)");
+        ior_ = p.getTexture("intIOR", Spectrum(1.5)).gray();
+        rejectBump(p, false);
+    }
+    void describe(spb_material* m) const override {
+        std::memset(m, 0, sizeof(*m)); m->type = SPB_MAT_PLASTIC; setv(m->kr, ks_); setv(m->kt, kd_);
+        m->eta[0] = m->eta[1] = m->eta[2] = (float)ior_;
+    }
+private:
+    Spectrum kd_, ks_; double ior_;
+};
+class RoughPlastic : public SurfaceMaterial {             // bsdfs/roughplastic.cc:118-165
+public:
+    explicit RoughPlastic(RenderParams& p) {
+        bool f1, f2;
+        kd_ = p.getTexture("diffuseReflectance", false, &f1);
+        ks_ = p.getTexture("specularReflectance", false, &f2);
+        SpicaAssert(f1 && f2, "roughplastic needs diffuseReflectance and specularReflectance");
+        ior_ = p.getTexture("intIOR", Spectrum(1.5)).gray();
+        alpha_ = p.getTexture("alpha", Spectrum(0.1)).gray();
+        distr_ = distributionId(p.getString("distribution", "beckmann", true));
+        rejectBump(p, false);
+    }
+    void describe(spb_material* m) const override {
+        std::memset(m, 0, sizeof(*m)); m->type = SPB_MAT_ROUGHPLASTIC; m->distribution = distr_; setv(m->kr, ks_); setv(m->kt, kd_);
+        m->eta[0] = m->eta[1] = m->eta[2] = (float)ior_; m->alpha_u = m->alpha_v = (float)alpha_;
+    }
+private:
+    Spectrum kd_, ks_; double ior_, alpha_; int distr_;
+};
+
 // ---- lights --------------------------------------------------------------------------------------------
 static CObject* makeArea(RenderParams& p) {                // lights/area.cc:20-24
     p.getObject("shape", true);
@@ -244,6 +281,8 @@ void registerBuiltinPlugins() {
     pm.registerPlugin("roughconductor", [](RenderParams& p) -> CObject* { return new RoughConductor(p); });
     pm.registerPlugin("conductor", [](RenderParams& p) -> CObject* { return new Conductor(p); });
     pm.registerPlugin("roughdielectric", [](RenderParams& p) -> CObject* { return new RoughDielectric(p); });
+    pm.registerPlugin("plastic", [](RenderParams& p) -> CObject* { return new Plastic(p); });
+    pm.registerPlugin("roughplastic", [](RenderParams& p) -> CObject* { return new RoughPlastic(p); });
     pm.registerPlugin("area", makeArea);
     pm.registerPlugin("envmap", makeEnvmap);
     registerGpuPlugins();

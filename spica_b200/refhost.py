@@ -1,4 +1,4 @@
-"""Drives the UNMODIFIED reference host (`spica -i scene.xml`, compiled by oracle/Makefile) with this
+"""Drives the UNMODIFIED reference host (`spica -i scene.xml`, any build of it) with this
 repo's plugins/path.so and plugins/bvh.so swapped in (spica_b200/refplugin).  The reference loads
 plugins from ./plugins relative to its working directory (core/cobject.cc:12-13), so a run
 directory is assembled whose plugins/ holds the reference's own film / sampler / camera / bsdf /

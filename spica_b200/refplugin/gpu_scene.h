@@ -80,8 +80,22 @@ inline void describeMaterial(const SurfaceMaterial* sm, spb_material* m) {
         noBump(d->bumpMap_);
         m->type = SPB_MAT_CONDUCTOR; m->kr[0] = m->kr[1] = m->kr[2] = 1.f;
         setv(m->eta, constantValue(d->eta_, "eta")); setv(m->k, constantValue(d->k_, "k"));
+    } else if (isType(sm, "N5spica7PlasticE")) {                            // bsdfs/plastic.cc:118-128
+        const auto* d = static_cast<const Plastic*>(sm);
+        noBump(d->bumpMap_);
+        m->type = SPB_MAT_PLASTIC;
+        setv(m->kr, constantValue(d->Ks_, "specularReflectance")); setv(m->kt, constantValue(d->Kd_, "diffuseReflectance"));
+        m->eta[0] = m->eta[1] = m->eta[2] = (float)constantValue(d->eta_, "intIOR").gray();
+    } else if (isType(sm, "N5spica12RoughPlasticE")) {                      // bsdfs/roughplastic.cc:130-165
+        const auto* d = static_cast<const RoughPlastic*>(sm);
+        noBump(d->bumpMap_);
+        if (d->remapRoughness_) FatalError("roughness remapping is outside the GPU path's scope");
+        m->type = SPB_MAT_ROUGHPLASTIC; m->distribution = distributionId(d->distribution_);
+        setv(m->kr, constantValue(d->Ks_, "specularReflectance")); setv(m->kt, constantValue(d->Kd_, "diffuseReflectance"));
+        m->eta[0] = m->eta[1] = m->eta[2] = (float)constantValue(d->index_, "intIOR").gray();
+        m->alpha_u = m->alpha_v = (float)constantValue(d->roughness_, "alpha").gray();
     } else {
-        FatalError("bsdf %s is outside the GPU path's scope (diffuse, dielectric, conductor, roughconductor, roughdielectric)", typeid(*sm).name());
+        FatalError("bsdf %s is outside the GPU path's scope (diffuse, dielectric, conductor, roughconductor, roughdielectric, plastic, roughplastic)", typeid(*sm).name());
     }
 }
 

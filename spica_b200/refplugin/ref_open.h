@@ -84,8 +84,10 @@
 #include "bsdfs/conductor.h"
 #include "bsdfs/dielectric.h"
 #include "bsdfs/diffuse.h"
+#include "bsdfs/plastic.h"
 #include "bsdfs/roughconductor.h"
 #include "bsdfs/roughdielectric.h"
+#include "bsdfs/roughplastic.h"
 #include "cameras/perspective.h"
 #include "filters/box.h"
 #include "filters/gaussian.h"

@@ -192,9 +192,11 @@ def cornell_parts(variant="diffuse"):
     variant "diffuse": BASELINE config 0 / 2 (all Lambertian + one emitter quad);
     variant "glossy" : config 3 (tall box rough conductor, short box dielectric);
     variant "zoo"    : specular conductor, Beckmann rough dielectric, GGX rough conductor back wall; its
-                       XML also uses a thin-lens camera and a Gaussian filter."""
+                       XML also uses a thin-lens camera and a Gaussian filter;
+    variant "plastic": SURVEY 8f rank 2 -- smooth plastic tall box, GGX rough plastic short box, Beckmann rough
+                       plastic floor."""
     parts = [
-        ("floor", "white", [_quad((-1, -1, -1), (-1, -1, 1), (1, -1, 1), (1, -1, -1))], None),
+        ("floor", "lacquer" if variant == "plastic" else "white", [_quad((-1, -1, -1), (-1, -1, 1), (1, -1, 1), (1, -1, -1))], None),
         ("ceiling", "white", [_quad((-1, 1, -1), (1, 1, -1), (1, 1, 1), (-1, 1, 1))], None),
         ("back", "brushed" if variant == "zoo" else "white", [_quad((-1, -1, -1), (1, -1, -1), (1, 1, -1), (-1, 1, -1))], None),
         ("left", "red", [_quad((-1, -1, -1), (-1, 1, -1), (-1, 1, 1), (-1, -1, 1))], None),
@@ -202,8 +204,8 @@ def cornell_parts(variant="diffuse"):
         # emitter: faces down (e1 x e2 = -y), just below the ceiling
         ("light", "black", [_quad((-0.25, 0.995, -0.25), (0.25, 0.995, -0.25), (0.25, 0.995, 0.25), (-0.25, 0.995, 0.25))],
          (17.0, 12.0, 4.0)),
-        ("tallbox", {"glossy": "metal", "zoo": "mirror"}.get(variant, "white"), _box_quads(-0.33, -0.3, 0.3, 1.2, 0.3, -1.0, 0.3), None),
-        ("shortbox", {"glossy": "glass", "zoo": "frosted"}.get(variant, "white"), _box_quads(0.35, 0.3, 0.3, 0.6, 0.3, -1.0, -0.3), None),
+        ("tallbox", {"glossy": "metal", "zoo": "mirror", "plastic": "plastic"}.get(variant, "white"), _box_quads(-0.33, -0.3, 0.3, 1.2, 0.3, -1.0, 0.3), None),
+        ("shortbox", {"glossy": "glass", "zoo": "frosted", "plastic": "satin"}.get(variant, "white"), _box_quads(0.35, 0.3, 0.3, 0.6, 0.3, -1.0, -0.3), None),
     ]
     return parts
 
@@ -220,6 +222,11 @@ CORNELL_BSDFS = {
     "frosted": ("roughdielectric", {"specularReflectance": (1.0, 1.0, 1.0), "specularTransmittance": (1.0, 1.0, 1.0),
                                     "alpha": 0.2, "intIOR": 1.5, "distribution": "beckmann"}),
     "brushed": ("roughconductor", {"eta": (0.2, 0.92, 1.1), "k": (3.9, 2.45, 2.14), "alpha": 0.3, "distribution": "ggx"}),
+    # variant "plastic"
+    "plastic": ("plastic", {"diffuseReflectance": (0.2, 0.3, 0.7), "specularReflectance": (1.0, 1.0, 1.0), "intIOR": 1.5}),
+    "satin": ("roughplastic", {"diffuseReflectance": (0.7, 0.3, 0.2), "specularReflectance": (0.9, 0.9, 0.9), "intIOR": 1.6,
+                               "alpha": 0.15, "distribution": "ggx"}),
+    "lacquer": ("roughplastic", {"diffuseReflectance": (0.6, 0.6, 0.6), "specularReflectance": (1.0, 1.0, 1.0), "alpha": 0.08}),
     "glass": ("dielectric", {"specularReflectance": (1.0, 1.0, 1.0), "specularTransmittance": (1.0, 1.0, 1.0), "intIOR": 1.5}),
 }
 ZOO_LENS = (0.04, 3.4)      # apertureRadius, focusDistance of the "zoo" variant

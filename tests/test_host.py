@@ -22,7 +22,7 @@ def test_host_library_exports():
     assert os.access(host.CLI_PATH, os.X_OK)
 
 
-@pytest.mark.parametrize("variant", ["diffuse", "glossy", "zoo"])
+@pytest.mark.parametrize("variant", ["diffuse", "glossy", "zoo", "plastic"])
 def test_parse_cornell_matches_the_flat_scene(variant):
     r = host.parse_scene(os.path.join(SCENES, "cornell_%s.xml" % variant))
     tris, mid, lid, mats, lights = scenes.cornell_arrays(variant)

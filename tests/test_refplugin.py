@@ -27,7 +27,7 @@ def _dump(tmp_path, xml, **kw):
     return refhost.read_dump(d)
 
 
-@pytest.mark.parametrize("variant", ["diffuse", "glossy", "zoo"])
+@pytest.mark.parametrize("variant", ["diffuse", "glossy", "zoo", "plastic"])
 @pytest.mark.parametrize("gpu_plugins", [("path", "bvh"), ("path",)])
 def test_reference_host_scene_resolves_to_the_flat_scene(tmp_path, variant, gpu_plugins):
     """The scene as the reference's parser built it == the flat arrays the C ABI tests use; also with the
@@ -90,7 +90,7 @@ def test_reference_host_has_no_cpu_fallback(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("variant", ["diffuse", "zoo"])
+@pytest.mark.parametrize("variant", ["diffuse", "zoo", "plastic"])
 def test_reference_host_renders_on_the_gpu(tmp_path, variant):
     """`spica -i scene.xml` of the unmodified reference, GPU plugins swapped in: the .hdr its hdrfilm
     wrote is within the reference's own seed-to-seed variance of the reference's renders."""
