@@ -97,6 +97,7 @@ struct RenderState {
     spb_material* d_mats = nullptr; spb_light* d_lights = nullptr;
     std::vector<spb_material> mats; std::vector<spb_light> lights;
     bool scene_dirty = true;
+    bool sort_materials = false;        // more than one BSDF type in the scene: shade in material order
     // envmap
     std::vector<float> env_rgb; int env_w = 0, env_h = 0; double env_l2w[16]; double env_scale = 1.0, env_center[3] = {0, 0, 0}, env_radius = 2.0;
     bool env_present = false, env_dirty = false;
@@ -206,15 +207,56 @@ __device__ __forceinline__ void writeRay(spb_ray_f32* q, uint32_t idx, V3 o, V3 
     p[1] = make_float4(d.y, d.z, __uint_as_float(slot), tmax);
 }
 
-__global__ void __launch_bounds__(128) shadeKernel(RenderParamsPOD rp, DeviceScene sc, PathSoA paths, Queues q, int cur) {
+template <bool SORT>
+__global__ void __launch_bounds__(128, SORT ? 4 : 3) shadeKernel(RenderParamsPOD rp, DeviceScene sc, PathSoA paths, Queues q, int cur) {
     const uint32_t n = q.count[cur];
     const spb_ray_f32* rays = q.ray[cur];
     spb_ray_f32* nextQ = q.ray[cur ^ 1];
     uint32_t* nextCount = q.count + (cur ^ 1);
-    const uint32_t stridex = gridDim.x * blockDim.x;
-    // whole warps iterate together so that the warp-aggregated pushes see converged lanes
-    const uint32_t nRound = (n + 31u) & ~31u;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nRound; i += stridex) {
+    // Material-sorted shading: the block takes a tile of kTile queue entries, buckets them by the BSDF type of
+    // the surface that was hit (counting sort in shared memory, one warp-aggregated atomic per key and warp)
+    // and shades them in bucket order, so a warp runs ONE material's code instead of the sum of all of them
+    // (the microfacet lobes cost ~10x the Lambertian one).  SORT = false (every material has the same BSDF
+    // type) shades in queue order.  Whole warps iterate together so that the warp-aggregated queue pushes see
+    // converged lanes.
+    constexpr uint32_t kTile = SORT ? 512 : 128, kPer = kTile / 128;
+    __shared__ uint32_t s_cnt[16], s_start[16];
+    __shared__ uint16_t s_order[kTile];
+    const uint32_t nTiles = (n + kTile - 1) / kTile;
+    for (uint32_t tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
+      const uint32_t tileBase = tile * kTile;
+      if (SORT) {
+      if (threadIdx.x < 16) s_cnt[threadIdx.x] = 0u;
+      __syncthreads();
+      uint32_t keys[kPer], ranks[kPer];
+#pragma unroll
+      for (uint32_t k = 0; k < kPer; k++) {
+          const uint32_t e = tileBase + k * 128u + threadIdx.x;
+          uint32_t key = 15u;                                        // past the end of the queue: sorted last, skipped
+          if (e < n) {
+              const int prim = __float_as_int(((const float*)(q.hit + e))[1]);
+              key = 0u;                                              // escaped rays
+              if (prim >= 0) {
+                  const int mat = __ldg((const int*)(sc.tris + prim) + 19);       // ShadeTri::material
+                  key = (mat >= 0 && mat < sc.n_mats) ? (uint32_t)(sc.mats[mat].type + 2) & 15u : 1u;
+              }
+          }
+          const unsigned peers = __match_any_sync(0xffffffffu, key);
+          const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+          uint32_t r = 0u;
+          if (lane == leader) r = atomicAdd(&s_cnt[key], (uint32_t)__popc(peers));
+          r = __shfl_sync(0xffffffffu, r, leader);
+          keys[k] = key; ranks[k] = r + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) { uint32_t run = 0u; for (int j = 0; j < 16; j++) { s_start[j] = run; run += s_cnt[j]; } }
+      __syncthreads();
+#pragma unroll
+      for (uint32_t k = 0; k < kPer; k++) s_order[s_start[keys[k]] + ranks[k]] = (uint16_t)(k * 128u + threadIdx.x);
+      __syncthreads();
+      }
+      for (uint32_t k = 0; k < kPer; k++) {
+        const uint32_t i = tileBase + (SORT ? (uint32_t)s_order[k * 128u + threadIdx.x] : k * 128u + threadIdx.x);
         const bool valid = i < n;
         bool pushNext = false, pushShadow = false, pushMis = false;
         V3 nO = v3(0.f), nD = v3(0.f), sO = v3(0.f), sD = v3(0.f), mO = v3(0.f), mD = v3(0.f);
@@ -396,6 +438,8 @@ __global__ void __launch_bounds__(128) shadeKernel(RenderParamsPOD rp, DeviceSce
         const uint32_t im = queuePush(q.count + 3, pushMis);
         if (pushMis) { writeRay(q.mis, im, mO, mD, slot, kRayInf); q.misC[im] = make_float4(mC.x, mC.y, mC.z, __uint_as_float((uint32_t)mExpect)); }
         __syncwarp();
+      }
+      if (SORT) __syncthreads();      // s_order / s_cnt are rewritten by the next tile
     }
 }
 
@@ -548,6 +592,8 @@ static int uploadScene(spb_ctx* ctx, RenderState* R) {
     if (!R->lights.empty()) SPB_CUDA(ctx, cudaMemcpy(R->d_lights, R->lights.data(), R->lights.size() * sizeof(spb_light), cudaMemcpyHostToDevice));
     R->ds.tris = R->d_tris; R->ds.vnormals = R->d_vnormals; R->ds.mats = R->d_mats; R->ds.lights = R->d_lights;
     R->ds.n_mats = (int)R->mats.size(); R->ds.n_lights = (int)R->lights.size();
+    R->sort_materials = false;
+    for (const spb_material& m : R->mats) if (m.type != R->mats[0].type) R->sort_materials = true;
     R->scene_dirty = false;
     return SPB_OK;
 }
@@ -791,7 +837,8 @@ int spb_render_samples(spb_ctx* ctx, int32_t first, int32_t count, int32_t strid
         for (int bounce = 0; bounce <= R->rp.max_depth; bounce++) {
             // extend
             if ((rc = launchTrace<false>(ctx, R->q.ray[cur], n, R->q.count + cur, HitOut{R->q.hit}, R->d_cursor, st))) return rc;
-            shadeKernel<<<shadeGrid, 128, 0, st>>>(R->rp, R->ds, R->paths, R->q, cur);
+            if (R->sort_materials) shadeKernel<true><<<shadeGrid, 128, 0, st>>>(R->rp, R->ds, R->paths, R->q, cur);
+            else shadeKernel<false><<<shadeGrid, 128, 0, st>>>(R->rp, R->ds, R->paths, R->q, cur);
             // connect + MIS (skipped by their own zero counts when empty)
             if ((rc = launchTrace<true>(ctx, R->q.shadow, n, R->q.count + 2, SinkShadow{R->q.shadow, R->q.shadowC, R->paths}, R->d_cursor + 4, st))) return rc;
             if ((rc = launchTrace<false>(ctx, R->q.mis, n, R->q.count + 3, SinkMis{R->q.mis, R->q.misC, R->paths}, R->d_cursor + 8, st))) return rc;

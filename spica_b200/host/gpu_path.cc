@@ -57,7 +57,9 @@ void uploadGeometry(spb_ctx* ctx, const FlatScene& f) {
     const int64_t n = (int64_t)f.material_id.size();
     check(ctx, spb_scene_set_triangles(ctx, f.verts.data(), f.anyNormals ? f.normals.data() : nullptr, f.anyUV ? f.uvs.data() : nullptr,
                                        f.material_id.data(), f.light_id.data(), n), "spb_scene_set_triangles");
-    check(ctx, spb_bvh_build(ctx, nullptr), "spb_bvh_build");
+    spb_build_opts opts; std::memset(&opts, 0, sizeof(opts));
+    if (const char* b = getenv("SPICA_BVH_BUILDER")) opts.builder = atoi(b);    // 0 host binned SAH (default), 1 GPU LBVH
+    check(ctx, spb_bvh_build(ctx, &opts), "spb_bvh_build");
 }
 }  // namespace
 

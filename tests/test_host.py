@@ -91,7 +91,9 @@ def test_host_render_matches_reference(tmp_path):
     r = host.run_cli(os.path.join(SCENES, "cornell_diffuse.xml"), str(tmp_path / "cli_out"), seed=3)
     assert r.returncode == 0, r.stderr
     cli = scenes.read_hdr(str(tmp_path / "cli_out.hdr"))
-    assert np.allclose(cli, hdr)                                              # same seed -> same image
+    # same seed -> same samples; the film's float atomics may add in a different order, which can move an
+    # RGBE mantissa by one step
+    assert (np.abs(cli - hdr) <= hdr.max(-1, keepdims=True) / 128 + 1e-6).all()
     assert "Finish!!" in r.stdout
 
 
