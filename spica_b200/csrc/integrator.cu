@@ -962,6 +962,18 @@ int spb_comm_init(spb_ctx* ctx, const char id[SPB_COMM_ID_BYTES], int32_t n_rank
         ncclGetErrorString_t es = (ncclGetErrorString_t)dlsym(lib, "ncclGetErrorString");
         return fail(ctx, SPB_ERR_CUDA, std::string("ncclCommInitRank: ") + (es ? es(rc) : "error"));
     }
+    // NCCL connects its channels lazily inside the first collective (tens of ms over 8 GPUs): do that here, as
+    // part of communicator set-up, so that the one all-reduce of a frame costs what the transfer costs
+    ncclAllReduce_t ar = (ncclAllReduce_t)dlsym(lib, "ncclAllReduce");
+    if (ar) {
+        float* d_warm = nullptr;
+        SPB_CUDA(ctx, cudaMalloc(&d_warm, 1024 * sizeof(float)));
+        SPB_CUDA(ctx, cudaMemsetAsync(d_warm, 0, 1024 * sizeof(float), ctx->stream));
+        const int wrc = ar(d_warm, d_warm, 1024, 7, 0, R->comm, ctx->stream);
+        SPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(d_warm);
+        if (wrc != 0) return fail(ctx, SPB_ERR_CUDA, "ncclAllReduce (communicator warm-up) failed");
+    }
     return SPB_OK;
 }
 

@@ -202,12 +202,22 @@ public:
             }
         } else {
             // GPU g renders sample indices g, g+G, ... ; then ONE all-reduce of the RGBW film
+            std::vector<double> tRender(G, 0.0), tReduce(G, 0.0);
             forEachGpu([&](int g) {
                 const int count = (numSamples - g + G - 1) / G;
+                const auto a = std::chrono::steady_clock::now();
                 check(ctxs[g], spb_render_samples(ctxs[g], g, std::max(count, 0), G), "spb_render_samples");
+                const auto b = std::chrono::steady_clock::now();
                 if (G > 1) check(ctxs[g], spb_film_allreduce(ctxs[g]), "spb_film_allreduce");
+                tRender[g] = std::chrono::duration<double>(b - a).count();
+                tReduce[g] = std::chrono::duration<double>(std::chrono::steady_clock::now() - b).count();   // includes waiting for the slowest GPU
             });
             const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            if (G > 1) {
+                double rmax = 0, rmin = 1e30, amin = 1e30;
+                for (int g = 0; g < G; g++) { rmax = std::max(rmax, tRender[g]); rmin = std::min(rmin, tRender[g]); amin = std::min(amin, tReduce[g]); }
+                MsgInfo("per-GPU render %.3f .. %.3f s, film all-reduce %.4f s", rmin, rmax, amin);
+            }
             spb_render_stats st;
             check(ctxs[0], spb_render_get_stats(ctxs[0], &st), "spb_render_get_stats");
             MsgInfo("rendered %d spp at %dx%d on %d GPU(s) in %.3f s: %.2f Msamples/s; GPU0: %.1f Mrays/s", numSamples, width, height, G, sec,
