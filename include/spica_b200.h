@@ -127,6 +127,10 @@ int spb_scene_set_envmap(spb_ctx* ctx, const float* rgb, int32_t w, int32_t h, c
 /* ---- the path-tracing integrator ------------------------------------------------------------------ */
 
 enum { SPB_FILTER_BOX = 0, SPB_FILTER_TENT = 1, SPB_FILTER_GAUSSIAN = 2 };
+enum {
+    SPB_INTEGRATOR_PATH = 0,    /* integrators/path/path.cc:42-125 (the hot path)                                */
+    SPB_INTEGRATOR_DIRECT = 1   /* integrators/directlighting/directlighting.cc:21-57: same kernels, no indirect light */
+};
 
 /* Everything SamplerIntegrator::render (core/integrator.cc:46-110) + PathIntegrator::Li
  * (integrators/path/path.cc:42-125) read from the camera / film / sampler / params objects,
@@ -142,7 +146,7 @@ typedef struct spb_render_desc {
     double  lens_radius, focal_distance;
     uint64_t seed;                  /* counter-based sampler key (replaces time(0) seeding, core/integrator.cc:51,71) */
     int32_t rr_start_bounce;        /* Russian roulette applies when bounces > this; reference: 3 (path.cc:117) */
-    int32_t reserved_;
+    int32_t integrator;             /* SPB_INTEGRATOR_* (0 = path)                                       */
 } spb_render_desc;
 
 /* Allocates (or re-uses) and clears the device film and the wavefront queues. */

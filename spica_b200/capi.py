@@ -52,7 +52,7 @@ class RenderDesc(C.Structure):
                 ("filter_radius", C.c_double * 2), ("filter_sigma", C.c_double),
                 ("camera_to_world", C.c_double * 16), ("raster_to_camera", C.c_double * 16),
                 ("lens_radius", C.c_double), ("focal_distance", C.c_double), ("seed", C.c_uint64),
-                ("rr_start_bounce", C.c_int32), ("reserved_", C.c_int32)]
+                ("rr_start_bounce", C.c_int32), ("integrator", C.c_int32)]
 
 
 class RenderStats(C.Structure):
@@ -63,6 +63,7 @@ class RenderStats(C.Structure):
 MAT_TYPES = {"none": -1, "diffuse": 0, "dielectric": 1, "roughconductor": 2, "roughdielectric": 3, "conductor": 4,
              "plastic": 5, "roughplastic": 6}
 FILTERS = {"box": 0, "tent": 1, "gaussian": 2}
+INTEGRATORS = {"path": 0, "directlighting": 1}
 assert C.sizeof(Material) == 64 and C.sizeof(Light) == 24
 
 
@@ -298,7 +299,8 @@ class Context:
         self._check(self.L.spb_scene_set_envmap(self.h, _ptr(rgb), w, h, _ptr(m), float(scale), _ptr(c), float(radius)))
 
     def render_begin(self, width, height, camera_to_world, raster_to_camera, max_depth=16, seed=0, filter="box",
-                     filter_radius=(1.0, 1.0), filter_sigma=0.5, lens_radius=0.0, focal_distance=50.0, rr_start=3):
+                     filter_radius=(1.0, 1.0), filter_sigma=0.5, lens_radius=0.0, focal_distance=50.0, rr_start=3,
+                     integrator="path"):
         d = RenderDesc()
         d.width, d.height, d.max_depth, d.filter = width, height, max_depth, FILTERS[filter]
         d.filter_radius[0], d.filter_radius[1], d.filter_sigma = filter_radius[0], filter_radius[1], filter_sigma
@@ -307,6 +309,7 @@ class Context:
         for i in range(16):
             d.camera_to_world[i] = c2w[i]; d.raster_to_camera[i] = r2c[i]
         d.lens_radius, d.focal_distance, d.seed, d.rr_start_bounce = lens_radius, focal_distance, seed, rr_start
+        d.integrator = INTEGRATORS[integrator]
         self._film_shape = (height, width)
         self._check(self.L.spb_render_begin(self.h, C.byref(d)))
 
@@ -349,7 +352,8 @@ def comm_unique_id():
     return buf.raw
 
 
-def cornell_render(ctx, width, height, spp, max_depth=8, variant="diffuse", seed=1, first=0, stride=1, begin=True):
+def cornell_render(ctx, width, height, spp, max_depth=8, variant="diffuse", seed=1, first=0, stride=1, begin=True,
+                   integrator="path"):
     """Sets up the Cornell scene of spica_b200.scenes on `ctx` and renders `spp` samples per pixel."""
     from . import scenes
     if begin:
@@ -361,6 +365,6 @@ def cornell_render(ctx, width, height, spp, max_depth=8, variant="diffuse", seed
         cam = scenes.CORNELL_CAMERA
         c2w, r2c = scenes.perspective_camera(scenes.look_at(cam["origin"], cam["target"], cam["up"]), cam["fov"], width, height)
         kw = dict(filter="gaussian", lens_radius=scenes.ZOO_LENS[0], focal_distance=scenes.ZOO_LENS[1]) if variant == "zoo" else {}
-        ctx.render_begin(width, height, c2w, r2c, max_depth=max_depth, seed=seed, **kw)
+        ctx.render_begin(width, height, c2w, r2c, max_depth=max_depth, seed=seed, integrator=integrator, **kw)
     ctx.render_samples(first, spp, stride)
     return ctx.film_resolve()

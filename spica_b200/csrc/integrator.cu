@@ -64,6 +64,7 @@ struct CameraPOD {
 
 struct RenderParamsPOD {
     int width, height, max_depth, filter, rr_start;
+    int integrator;                          // SPB_INTEGRATOR_*
     float frx, fry, fbeta, fexpx, fexpy;     // filter parameters
     uint64_t seed;
 };
@@ -279,9 +280,14 @@ __global__ void __launch_bounds__(128, SORT ? 4 : 3) shadeKernel(RenderParamsPOD
             const uint32_t key = paths.key[slot];
             const uint32_t dim = kDimBounce0 + vertex * kDimsPerBounce;
 
+            // directlighting (integrators/directlighting/directlighting.cc:21-57): emitted light only at depth 0, one
+            // light sample at every vertex, continuation only through a specular REFLECTION lobe
+            // (SamplerIntegrator::specularReflect, core/integrator.cc:112-130; specularTransmit never finds a
+            // matching lobe among the in-scope materials), depth growing by 2 per reflection (:53-54 + :125).
+            const bool direct = rp.integrator == SPB_INTEGRATOR_DIRECT;
             if (prim < 0) {
-                // escaped: path.cc:62-65 (only environment lights answer Le(ray))
-                if ((bounces == 0 || specularBounce) && sc.env.present) {
+                // escaped: path.cc:62-65 / directlighting.cc:30-35 (only environment lights answer Le(ray))
+                if ((direct || bounces == 0 || specularBounce) && sc.env.present) {
                     int nEnv = 0;
                     for (int l = 0; l < sc.n_lights; l++) nEnv += (sc.lights[l].type == SPB_LIGHT_ENVMAP);
                     Ladd = beta * envLe(sc.env, d) * (float)nEnv;
@@ -289,11 +295,13 @@ __global__ void __launch_bounds__(128, SORT ? 4 : 3) shadeKernel(RenderParamsPOD
             } else {
                 const TriGeom tri = loadTri(sc.tris, prim);
                 // path.cc:58-61 + SurfaceInteraction::Le -> AreaLight::L (interaction.cc:160-163, area.cc:29-31)
-                if ((bounces == 0 || specularBounce) && tri.light >= 0) {
+                const bool emitHere = direct ? (bounces == 0 && tri.material >= 0 && tri.material < sc.n_mats)   // after the bsdf check (:38-46)
+                                             : (bounces == 0 || specularBounce);
+                if (emitHere && tri.light >= 0) {
                     const spb_light lt = sc.lights[tri.light];
                     if (dot(tri.ng, -d) > 0.f) Ladd = beta * v3(lt.radiance[0], lt.radiance[1], lt.radiance[2]);
                 }
-                if (bounces < rp.max_depth) {                       // path.cc:68
+                if (direct || bounces < rp.max_depth) {             // path.cc:68
                     // ---- surface point (core/triangle.cc:119-156)
                     SurfacePoint sp;
                     const float u = hv.z, v = hv.w;
@@ -402,11 +410,24 @@ __global__ void __launch_bounds__(128, SORT ? 4 : 3) shadeKernel(RenderParamsPOD
                                 }
                             }
                         }
-                        // ---- next segment (path.cc:82-94)
-                        V3 wi; float pdf; int sampled;
-                        const V3 f = bsdfSample(bsdf, sp, wo, sample1D(key, dim + kDBsdf), sample1D(key, dim + kDBsdf + 1),
-                                                sample1D(key, dim + kDLobePath), kBxAll, &wi, &pdf, &sampled);
-                        if (!isBlack(f) && pdf != 0.f) {
+                        // ---- next segment (path.cc:82-94; directlighting.cc:52-55)
+                        V3 wi; float pdf = 0.f; int sampled = 0;
+                        V3 f = v3(0.f);
+                        if (!direct) {
+                            f = bsdfSample(bsdf, sp, wo, sample1D(key, dim + kDBsdf), sample1D(key, dim + kDBsdf + 1),
+                                           sample1D(key, dim + kDLobePath), kBxAll, &wi, &pdf, &sampled);
+                        } else if (2 * bounces + 1 < rp.max_depth) {
+                            f = bsdfSample(bsdf, sp, wo, sample1D(key, dim + kDBsdf), sample1D(key, dim + kDBsdf + 1),
+                                           sample1D(key, dim + kDLobePath), kBxReflection | kBxSpecular, &wi, &pdf, &sampled);
+                            if (absDot(wi, sp.ns) == 0.f) pdf = 0.f;
+                        }
+                        if (direct) {
+                            if (!isBlack(f) && pdf > 0.f) {
+                                beta = beta * f * (absDot(wi, sp.ns) / pdf);
+                                nO = offsetRayOrigin(sp.p, sp.ng, wi); nD = wi; pushNext = true;
+                                flags = (uint32_t)(bounces + 1) | 0x100u | ((vertex + 1u) << 16);
+                            }
+                        } else if (!isBlack(f) && pdf != 0.f) {
                             beta = beta * f * (absDot(wi, sp.ns) / pdf);
                             bool alive = true;
                             if (bounces > rp.rr_start) {                       // path.cc:117-121
@@ -768,6 +789,7 @@ int spb_scene_set_envmap(spb_ctx* ctx, const float* rgb, int32_t w, int32_t h, c
 int spb_render_begin(spb_ctx* ctx, const spb_render_desc* desc) {
     if (!ctx || !desc) return fail(ctx, SPB_ERR_INVALID, "spb_render_begin: NULL argument");
     if (desc->width <= 0 || desc->height <= 0 || desc->max_depth < 0) return fail(ctx, SPB_ERR_INVALID, "spb_render_begin: bad film size or depth");
+    if (desc->integrator != SPB_INTEGRATOR_PATH && desc->integrator != SPB_INTEGRATOR_DIRECT) return fail(ctx, SPB_ERR_INVALID, "spb_render_begin: unknown integrator");
     if (!ctx->bvh_ready) return fail(ctx, SPB_ERR_INVALID, "spb_render_begin: no acceleration structure (call spb_bvh_build first)");
     cudaSetDevice(ctx->device);
     RenderState* R = rs(ctx);
@@ -787,6 +809,7 @@ int spb_render_begin(spb_ctx* ctx, const spb_render_desc* desc) {
     RenderParamsPOD& rp = R->rp;
     rp.width = desc->width; rp.height = desc->height; rp.max_depth = desc->max_depth; rp.filter = desc->filter;
     rp.rr_start = desc->rr_start_bounce;
+    rp.integrator = desc->integrator;
     rp.frx = (float)desc->filter_radius[0]; rp.fry = (float)desc->filter_radius[1];
     const double sigma = desc->filter_sigma != 0.0 ? desc->filter_sigma : 0.5;
     rp.fbeta = (float)(1.0 / sigma);

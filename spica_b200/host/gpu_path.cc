@@ -110,7 +110,8 @@ private:
 
 class PathIntegrator : public Integrator {
 public:
-    explicit PathIntegrator(RenderParams& params) : sampler_(std::static_pointer_cast<Sampler>(params.getObject("sampler"))) {}   // path.cc:34-36
+    // path.cc:34-36; directlighting.cc:17-19 (which consumes the sampler, remove = true)
+    PathIntegrator(RenderParams& params, int mode) : sampler_(std::static_pointer_cast<Sampler>(params.getObject("sampler", mode == SPB_INTEGRATOR_DIRECT))), mode_(mode) {}
 
     void render(const std::shared_ptr<const Camera>& camera, const Scene& scene, RenderParams& params) override {
         auto* accel = dynamic_cast<BVHAccel*>(scene.accelerator().get());
@@ -149,6 +150,7 @@ public:
         desc.lens_radius = camera->lensRadius; desc.focal_distance = camera->focalLength;
         desc.seed = opt.seed ? opt.seed : (uint64_t)time(nullptr);         // the reference seeds from time(0) (integrator.cc:51)
         desc.rr_start_bounce = 3;                                          // path.cc:117
+        desc.integrator = mode_;
 
         const int G = std::max(1, opt.gpus);
         std::vector<spb_ctx*> ctxs(G, nullptr);
@@ -231,12 +233,15 @@ public:
     }
 private:
     std::shared_ptr<Sampler> sampler_;
+    int mode_;
 };
 
 void registerGpuPlugins() {
     PluginManager& pm = PluginManager::getInstance();
     pm.registerAccelerator("bvh", [](const std::vector<std::shared_ptr<Primitive>>& prims, RenderParams& p) -> Accelerator* { return new BVHAccel(prims, p); });
-    pm.registerPlugin("path", [](RenderParams& p) -> CObject* { return new PathIntegrator(p); });
+    pm.registerPlugin("path", [](RenderParams& p) -> CObject* { return new PathIntegrator(p, SPB_INTEGRATOR_PATH); });
+    // integrators/directlighting: the same kernels without indirect light
+    pm.registerPlugin("directlighting", [](RenderParams& p) -> CObject* { return new PathIntegrator(p, SPB_INTEGRATOR_DIRECT); });
 }
 
 }  // namespace spica

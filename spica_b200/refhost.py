@@ -13,7 +13,7 @@ from . import capi
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SHIM_DIR = os.path.join(HERE, "lib", "refplugins")
-SHIM_PLUGINS = ("path", "bvh")
+SHIM_PLUGINS = ("path", "bvh", "directlighting")
 
 
 def available(ref_root):
@@ -32,6 +32,10 @@ def make_run_dir(run_dir, ref_root, gpu_plugins=SHIM_PLUGINS):
             os.remove(dst)
         name = f[:-3]
         os.symlink(os.path.join(SHIM_DIR, f) if name in gpu_plugins else os.path.join(src, f), dst)
+    for name in gpu_plugins:            # GPU plugins the reference build does not have
+        dst = os.path.join(pdir, name + ".so")
+        if not os.path.lexists(dst):
+            os.symlink(os.path.join(SHIM_DIR, name + ".so"), dst)
     return run_dir
 
 

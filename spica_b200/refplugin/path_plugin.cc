@@ -11,6 +11,12 @@
 // SPICA_SAVE_PASSES=1 (save after every pass like core/integrator.cc:98).
 #include "gpu_scene.h"
 
+// the same source builds plugins/path.so (default) and plugins/directlighting.so (-DSPB_REFPLUGIN_INTEGRATOR=1,
+// replaces integrators/directlighting/directlighting.cc)
+#ifndef SPB_REFPLUGIN_INTEGRATOR
+#define SPB_REFPLUGIN_INTEGRATOR SPB_INTEGRATOR_PATH
+#endif
+
 namespace spica {
 namespace b200 {
 
@@ -22,8 +28,8 @@ static void rowMajor(const Transform& t, double out[16]) {
 
 class GpuPathIntegrator : public Integrator {
 public:
-    explicit GpuPathIntegrator(RenderParams& params)
-        : sampler_(std::static_pointer_cast<Sampler>(params.getObject("sampler"))) {}                   // path.cc:35-37
+    explicit GpuPathIntegrator(RenderParams& params)                                                    // path.cc:35-37, directlighting.cc:17-19
+        : sampler_(std::static_pointer_cast<Sampler>(params.getObject("sampler", SPB_REFPLUGIN_INTEGRATOR == SPB_INTEGRATOR_DIRECT))) {}
 
     void render(const std::shared_ptr<const Camera>& camera, const Scene& scene, RenderParams& params) override {
         // the tree: shared with the GPU `bvh` accelerator when the scene uses it, else built here from the same primitives
@@ -86,6 +92,7 @@ public:
         desc.lens_radius = camera->lensRadius_; desc.focal_distance = camera->focalLength_;
         desc.seed = (uint64_t)envInt("SPICA_SEED", (long)time(nullptr));                               // core/integrator.cc:51
         desc.rr_start_bounce = 3;                                                                       // path.cc:117
+        desc.integrator = SPB_REFPLUGIN_INTEGRATOR;
 
         // environment map: level 0 of the reference's pyramid is the scaled image (lights/envmap.cc:27-33);
         // Light keeps the transposed XML matrix (envmap.cc:19), the C ABI takes the XML one
@@ -203,5 +210,8 @@ private:
 
 extern "C" {
 spica::CObject* createInstance(spica::RenderParams& params) { return (spica::CObject*)(new spica::b200::GpuPathIntegrator(params)); }
-const char* getDescription() { return "B200 wavefront path tracer (unidirectional, next-event estimation + MIS)"; }
+const char* getDescription() {
+    return SPB_REFPLUGIN_INTEGRATOR == SPB_INTEGRATOR_DIRECT ? "B200 wavefront direct-lighting integrator"
+                                                             : "B200 wavefront path tracer (unidirectional, next-event estimation + MIS)";
+}
 }

@@ -241,7 +241,7 @@ def _quads_to_tris(quads):
     return out
 
 
-def write_cornell(dirpath, width=512, height=512, spp=64, max_depth=8, variant="diffuse", name="cornell"):
+def write_cornell(dirpath, width=512, height=512, spp=64, max_depth=8, variant="diffuse", name="cornell", integrator="path"):
     """Writes <dirpath>/<name>.xml + one OBJ per part; returns the XML path."""
     os.makedirs(dirpath, exist_ok=True)
     parts = cornell_parts(variant)
@@ -259,7 +259,7 @@ def write_cornell(dirpath, width=512, height=512, spp=64, max_depth=8, variant="
             used.append(bsdf)
     cam = CORNELL_CAMERA
     x = ['<?xml version="1.0" encoding="utf-8"?>', '<scene version="0.5.0">',
-         '  <integrator type="path">', '    <integer name="maxDepth" value="%d"/>' % max_depth, '  </integrator>',
+         '  <integrator type="%s">' % integrator, '    <integer name="maxDepth" value="%d"/>' % max_depth, '  </integrator>',
          '  <sensor type="perspective">', '    <float name="fov" value="%g"/>' % cam["fov"],
          '    <transform name="toWorld">',
          '      <lookAt origin="%g, %g, %g" target="%g, %g, %g" up="%g, %g, %g"/>' % (cam["origin"] + cam["target"] + cam["up"]),

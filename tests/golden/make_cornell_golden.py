@@ -37,6 +37,8 @@ def main():
         d = os.path.join(ROOT, "tests", "golden", "scenes")
         if variant == "envtorus":
             xml = scenes.write_envscene(d, W, H, SPP, DEPTH, name="envtorus")
+        elif variant == "direct":       # the "zoo" scene (it has a mirror) under the directlighting integrator
+            xml = scenes.write_cornell(d, W, H, SPP, DEPTH, variant="zoo", name="cornell_direct", integrator="directlighting")
         else:
             xml = scenes.write_cornell(d, W, H, SPP, DEPTH, variant=variant, name="cornell_" + variant)
         runs = []

@@ -111,6 +111,19 @@ def test_reference_host_renders_on_the_gpu(tmp_path, variant):
 
 
 @pytest.mark.gpu
+def test_reference_host_directlighting_plugin(tmp_path):
+    """plugins/directlighting.so: `<integrator type="directlighting">` of the unmodified reference host on the GPU."""
+    g = np.load(os.path.join(GOLDEN, "cornell_direct_ref.npz"))
+    runs = g["runs"].astype(np.float64)
+    mean = runs.mean(0)
+    out = str(tmp_path / "out")
+    r = refhost.run(os.path.join(SCENES, "cornell_direct.xml"), out, str(tmp_path / "run"), REF, env={"SPICA_SEED": 7})
+    assert r.returncode == 0, r.stderr
+    img = scenes.read_hdr(out + ".hdr")
+    assert max(scenes.rel_mse(img, run, mean) for run in runs) <= 1.5 * float(g["pair_relmse"][0])
+
+
+@pytest.mark.gpu
 def test_reference_host_envmap_scene_and_reference_accelerator(tmp_path):
     """Environment lighting through the shim, once with the GPU `bvh` plugin and once with the
     reference's own accelerator left in place: same seed, same image."""

@@ -46,6 +46,28 @@ def test_cornell_relmse_against_reference(gpu_ctx, variant):
         np.save(os.path.join(out, "cornell_%s_gpu.npy" % variant), hi.astype(np.float32))
 
 
+def test_directlighting_integrator_against_reference(gpu_ctx):
+    """integrators/directlighting on the "zoo" scene (it has a mirror): emitted light at depth 0
+    only, one light sample per vertex, continuation through specular reflection only.  The reference's own
+    directlighting renders are the bar; their seed-to-seed variance is ~15x lower than the path tracer's."""
+    g = np.load(os.path.join(GOLDEN, "cornell_direct_ref.npz"))
+    runs = g["runs"].astype(np.float64)
+    K = len(runs)
+    mean = runs.mean(0)
+    pair_max = float(g["pair_relmse"][0])
+    spp, w, h, depth = int(g["spp"]), int(g["width"]), int(g["height"]), int(g["max_depth"])
+    img = capi.cornell_render(gpu_ctx, w, h, spp, max_depth=depth, variant="zoo", seed=31, integrator="directlighting")
+    r_equal = max(scenes.rel_mse(img, runs[k], mean) for k in range(K))
+    assert r_equal <= 1.5 * pair_max, (r_equal, pair_max)
+    hi = capi.cornell_render(gpu_ctx, w, h, 64 * spp, max_depth=depth, variant="zoo", seed=32, integrator="directlighting")
+    r_hi = scenes.rel_mse(hi, mean, mean)
+    assert r_hi <= 1.5 * pair_max / (2 * K) * (1.0 + K / 64.0), (r_hi, pair_max / (2 * K))
+    assert abs(hi.mean() / mean.mean() - 1.0) < 0.01, (hi.mean(), mean.mean())
+    # and it is not the path tracer: no indirect light
+    pt = capi.cornell_render(gpu_ctx, w, h, spp, max_depth=depth, variant="zoo", seed=31)
+    assert pt.mean() > 1.3 * img.mean()
+
+
 def test_sample_partition_is_deterministic(gpu_ctx):
     """Counter-based sampler: rendering samples {0..7} in one call == two interleaved halves
     (what two GPUs do) up to float32 summation order."""
