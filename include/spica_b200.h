@@ -106,6 +106,27 @@ typedef struct spb_material {
 } spb_material;             /* 64 B */
 int spb_scene_set_materials(spb_ctx* ctx, const spb_material* mats, int32_t n);
 
+/* Textures (textures/bitmap.cc:16-26, textures/checkerboard.cc:23-40): the reflectance-type parameters of a
+ * material (kr, kt) may come from a texture evaluated at the hit point's interpolated uv
+ * (core/triangle.cc:120) instead of the constant in spb_material.
+ *   bitmap       : MipMap::lookup(st, 0) = bilinear on level 0 with Repeat wrap (core/mipmap.cc:67-93), st = (u, 1 - v)
+ *                  (UVMapping2D's default invertHorizontal, core/texture.cc:24-31);
+ *   checkerboard : color0 when int((u*uscale+uoffset)*2) + int((v*vscale+voffset)*2) is odd, else color1. */
+enum { SPB_TEX_BITMAP = 0, SPB_TEX_CHECKERBOARD = 1 };
+typedef struct spb_texture {
+    int32_t type;               /* SPB_TEX_*                                                        */
+    int32_t width, height;      /* bitmap                                                           */
+    int32_t reserved_;
+    int64_t texel_offset;       /* bitmap: index of its first texel in the texel array (rgb triples) */
+    float   color0[3], color1[3];
+    float   uoffset, voffset, uscale, vscale;
+} spb_texture;                  /* 64 B */
+/* texels_rgb: 3 floats per texel, row-major per bitmap; copied. */
+int spb_scene_set_textures(spb_ctx* ctx, const spb_texture* texs, int32_t n, const float* texels_rgb, int64_t n_texels);
+/* tex_ids: 2 ints per material {texture for kr, texture for kt}, -1 = use the constant.  NULL clears all bindings.
+ * Call after spb_scene_set_materials (which resets the bindings). */
+int spb_scene_set_material_textures(spb_ctx* ctx, const int32_t* tex_ids, int32_t n_mats);
+
 enum { SPB_LIGHT_AREA = 0, SPB_LIGHT_ENVMAP = 1 };
 /* One entry per light in Scene::lights() order (spica/sceneparser.cc:168-179: ONE AreaLight per
  * emitter triangle; lights/area.cc).  The list order only matters for the uniform light pick

@@ -47,6 +47,12 @@ class Light(C.Structure):
     _fields_ = [("type", C.c_int32), ("prim", C.c_int32), ("radiance", C.c_float * 3), ("pad_", C.c_float)]
 
 
+class Texture(C.Structure):
+    _fields_ = [("type", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("reserved_", C.c_int32),
+                ("texel_offset", C.c_int64), ("color0", C.c_float * 3), ("color1", C.c_float * 3),
+                ("uoffset", C.c_float), ("voffset", C.c_float), ("uscale", C.c_float), ("vscale", C.c_float)]
+
+
 class RenderDesc(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("max_depth", C.c_int32), ("filter", C.c_int32),
                 ("filter_radius", C.c_double * 2), ("filter_sigma", C.c_double),
@@ -64,7 +70,7 @@ MAT_TYPES = {"none": -1, "diffuse": 0, "dielectric": 1, "roughconductor": 2, "ro
              "plastic": 5, "roughplastic": 6}
 FILTERS = {"box": 0, "tent": 1, "gaussian": 2}
 INTEGRATORS = {"path": 0, "directlighting": 1}
-assert C.sizeof(Material) == 64 and C.sizeof(Light) == 24
+assert C.sizeof(Material) == 64 and C.sizeof(Light) == 24 and C.sizeof(Texture) == 64
 
 
 class SpbError(RuntimeError):
@@ -82,6 +88,7 @@ SYMBOLS = [
     "spb_dev_alloc", "spb_dev_free", "spb_dev_upload", "spb_dev_download", "spb_dev_sync",
     "spb_ctx_stream",
     "spb_scene_set_triangle_attributes", "spb_scene_set_materials", "spb_scene_set_lights", "spb_scene_set_envmap",
+    "spb_scene_set_textures", "spb_scene_set_material_textures",
     "spb_render_begin", "spb_render_samples", "spb_film_read", "spb_film_resolve", "spb_film_add",
     "spb_render_get_stats", "spb_comm_get_unique_id", "spb_comm_init", "spb_film_allreduce", "spb_comm_destroy",
 ]
@@ -118,6 +125,8 @@ def load():
     L.spb_scene_set_triangle_attributes.argtypes = [vp, vp, vp, i64]
     L.spb_scene_set_materials.argtypes = [vp, C.POINTER(Material), i32]
     L.spb_scene_set_lights.argtypes = [vp, C.POINTER(Light), i32]
+    L.spb_scene_set_textures.argtypes = [vp, C.POINTER(Texture), i32, vp, i64]
+    L.spb_scene_set_material_textures.argtypes = [vp, vp, i32]
     L.spb_scene_set_envmap.argtypes = [vp, vp, i32, i32, vp, C.c_double, vp, C.c_double]
     L.spb_render_begin.argtypes = [vp, C.POINTER(RenderDesc)]
     L.spb_render_samples.argtypes = [vp, i32, i32, i32]
@@ -261,7 +270,28 @@ class Context:
         """mats: list of dicts {type, reflectance | specularReflectance/specularTransmittance/intIOR |
         eta/k/alpha/distribution} using the reference's XML parameter names."""
         arr = (Material * max(len(mats), 1))()
+        texs, texels, bind = [], [], np.full((max(len(mats), 1), 2), -1, dtype=np.int32)
         for i, m in enumerate(mats):
+            m = dict(m)
+            # texture-valued reflectances ({"texture": "bitmap", "image": array} / {"texture": "checkerboard", ...})
+            for slot, keys in ((0, ("reflectance", "specularReflectance")), (1, ("specularTransmittance", "diffuseReflectance"))):
+                for k in keys:
+                    if isinstance(m.get(k), dict):
+                        d = m[k]
+                        t = Texture()
+                        if d["texture"] == "bitmap":
+                            img = np.ascontiguousarray(d["image"], dtype=np.float32)
+                            t.type, t.height, t.width = 0, img.shape[0], img.shape[1]
+                            t.texel_offset = sum(len(x) for x in texels) // 3
+                            texels.append(img.reshape(-1))
+                        else:
+                            t.type = 1
+                            for j in range(3):
+                                t.color0[j] = d["color0"][j]; t.color1[j] = d["color1"][j]
+                            t.uoffset, t.voffset, t.uscale, t.vscale = d["uoffset"], d["voffset"], d["uscale"], d["vscale"]
+                        bind[i, slot] = len(texs)
+                        texs.append(t)
+                        m[k] = (0.0, 0.0, 0.0)
             a = arr[i]
             a.type = MAT_TYPES[m["type"]]
             a.distribution = 1 if m.get("distribution", "beckmann") == "ggx" else 0
@@ -274,6 +304,11 @@ class Context:
                 a.kr[j] = kr[j]; a.kt[j] = kt[j]; a.eta[j] = eta[j]; a.k[j] = k[j]
             a.alpha_u = a.alpha_v = m.get("alpha", 0.1)
         self._check(self.L.spb_scene_set_materials(self.h, arr, len(mats)))
+        if texs:
+            tarr = (Texture * len(texs))(*texs)
+            flat = np.concatenate(texels) if texels else np.zeros(0, dtype=np.float32)
+            self._check(self.L.spb_scene_set_textures(self.h, tarr, len(texs), _ptr(flat) if len(flat) else None, len(flat) // 3))
+            self._check(self.L.spb_scene_set_material_textures(self.h, _ptr(bind), len(mats)))
 
     def set_lights(self, lights, envmap_at=None):
         """lights: list of (prim, (r, g, b)) area lights; envmap_at: list position of an envmap light."""
@@ -358,7 +393,11 @@ def cornell_render(ctx, width, height, spp, max_depth=8, variant="diffuse", seed
     from . import scenes
     if begin:
         tris, mid, lid, mats, lights = scenes.cornell_arrays(variant)
-        ctx.set_triangles(tris, material_id=mid, light_id=lid)
+        ctx.set_triangles(tris, normals=scenes.cornell_normals(variant), material_id=mid, light_id=lid, uvs=scenes.cornell_uvs(variant))
+        for m in mats:                                   # bitmap textures: the image the XML's .hdr file holds
+            for v in m.values():
+                if isinstance(v, dict) and v["texture"] == "bitmap":
+                    v["image"] = scenes.texture_image()
         ctx.set_materials(mats)
         ctx.set_lights(lights)
         ctx.build()

@@ -54,6 +54,11 @@ struct DeviceScene {
     const spb_material* mats;
     const spb_light* lights;
     int n_mats, n_lights;
+    // textures: NULL mat_tex = no material is textured (the common case costs one uniform branch)
+    const int2*        mat_tex;   // per material {kr texture, kt texture} or -1
+    const spb_texture* texs;
+    const float4*      texels;    // all bitmaps, rgb_
+    const float*       uvs;       // 6 per triangle
     EnvMap env;
 };
 
@@ -97,6 +102,8 @@ struct RenderState {
     ShadeTri* d_tris = nullptr; float* d_vnormals = nullptr; int64_t n_tris = 0;
     spb_material* d_mats = nullptr; spb_light* d_lights = nullptr;
     std::vector<spb_material> mats; std::vector<spb_light> lights;
+    std::vector<spb_texture> texs; std::vector<float> texels; std::vector<int32_t> mat_tex;   // textures + per-material bindings
+    int2* d_mat_tex = nullptr; spb_texture* d_texs = nullptr; float4* d_texels = nullptr; float* d_uvs = nullptr;
     bool scene_dirty = true;
     bool sort_materials = false;        // more than one BSDF type in the scene: shade in material order
     // envmap
@@ -206,6 +213,25 @@ __device__ __forceinline__ void writeRay(spb_ray_f32* q, uint32_t idx, V3 o, V3 
     float4* p = (float4*)(q + idx);
     p[0] = make_float4(o.x, o.y, o.z, d.x);
     p[1] = make_float4(d.y, d.z, __uint_as_float(slot), tmax);
+}
+
+// Texture<Spectrum>::evaluate for the two texture plugins (textures/bitmap.cc:22-26, checkerboard.cc:31-40)
+__device__ __forceinline__ V3 texTexel(const float4* texels, const spb_texture& t, int s, int tt) {
+    s = (s % t.width + t.width) % t.width; tt = (tt % t.height + t.height) % t.height;            // ImageWrap::Repeat (mipmap.cc:101-104)
+    const float4 v = __ldg(texels + t.texel_offset + (size_t)tt * t.width + s);
+    return v3(v.x, v.y, v.z);
+}
+__device__ __forceinline__ V3 evalTexture(const DeviceScene& sc, int id, float u, float v) {
+    const spb_texture t = sc.texs[id];
+    if (t.type == SPB_TEX_CHECKERBOARD) {
+        const int iu = (int)((u * t.uscale + t.uoffset) * 2.f), iv = (int)((v * t.vscale + t.voffset) * 2.f);
+        return ((iu + iv) % 2 != 0) ? v3(t.color0[0], t.color0[1], t.color0[2]) : v3(t.color1[0], t.color1[1], t.color1[2]);
+    }
+    const float s = u * t.width - 0.5f, tt = (1.f - v) * t.height - 0.5f;                           // MipMap::lookup -> bilinear(0, st)
+    const int si = (int)s, ti = (int)tt;
+    const float ds = s - si, dt = tt - ti;
+    return (1.f - ds) * (1.f - dt) * texTexel(sc.texels, t, si, ti) + ds * (1.f - dt) * texTexel(sc.texels, t, si + 1, ti) +
+           (1.f - ds) * dt * texTexel(sc.texels, t, si, ti + 1) + ds * dt * texTexel(sc.texels, t, si + 1, ti + 1);
 }
 
 template <bool SORT>
@@ -320,7 +346,18 @@ __global__ void __launch_bounds__(128, SORT ? 4 : 3) shadeKernel(RenderParamsPOD
                     }
                     const V3 wo = -d;
                     const bool hasMat = tri.material >= 0 && tri.material < sc.n_mats;
-                    const Bsdf bsdf = makeBsdf(sc.mats[hasMat ? tri.material : 0]);
+                    spb_material mat = sc.mats[hasMat ? tri.material : 0];
+                    if (sc.mat_tex && hasMat) {
+                        const int2 tx = sc.mat_tex[tri.material];
+                        if ((tx.x & tx.y) != -1) {
+                            const float* t = sc.uvs + (size_t)prim * 6;
+                            const float w0 = 1.f - u - v;                                               // core/triangle.cc:120
+                            const float tu = w0 * t[0] + u * t[2] + v * t[4], tv = w0 * t[1] + u * t[3] + v * t[5];
+                            if (tx.x >= 0) { const V3 c = evalTexture(sc, tx.x, tu, tv); mat.kr[0] = c.x; mat.kr[1] = c.y; mat.kr[2] = c.z; }
+                            if (tx.y >= 0) { const V3 c = evalTexture(sc, tx.y, tu, tv); mat.kt[0] = c.x; mat.kt[1] = c.y; mat.kt[2] = c.z; }
+                        }
+                    }
+                    const Bsdf bsdf = makeBsdf(mat);
                     if (!hasMat || bsdf.type == SPB_MAT_NONE && false) {
                         // no material: pass through without counting a bounce (path.cc:71-75)
                         nO = offsetRayOrigin(sp.p, sp.ng, d); nD = d; pushNext = true;
@@ -508,7 +545,12 @@ static void freeScene(RenderState* R) {
     if (R->d_vnormals) cudaFree(R->d_vnormals);
     if (R->d_mats) cudaFree(R->d_mats);
     if (R->d_lights) cudaFree(R->d_lights);
+    if (R->d_mat_tex) cudaFree(R->d_mat_tex);
+    if (R->d_texs) cudaFree(R->d_texs);
+    if (R->d_texels) cudaFree(R->d_texels);
+    if (R->d_uvs) cudaFree(R->d_uvs);
     R->d_tris = nullptr; R->d_vnormals = nullptr; R->d_mats = nullptr; R->d_lights = nullptr;
+    R->d_mat_tex = nullptr; R->d_texs = nullptr; R->d_texels = nullptr; R->d_uvs = nullptr;
 }
 static void freeEnv(RenderState* R) {
     if (R->d_env_texels) cudaFree(R->d_env_texels);
@@ -613,6 +655,30 @@ static int uploadScene(spb_ctx* ctx, RenderState* R) {
     if (!R->lights.empty()) SPB_CUDA(ctx, cudaMemcpy(R->d_lights, R->lights.data(), R->lights.size() * sizeof(spb_light), cudaMemcpyHostToDevice));
     R->ds.tris = R->d_tris; R->ds.vnormals = R->d_vnormals; R->ds.mats = R->d_mats; R->ds.lights = R->d_lights;
     R->ds.n_mats = (int)R->mats.size(); R->ds.n_lights = (int)R->lights.size();
+    R->ds.mat_tex = nullptr; R->ds.texs = nullptr; R->ds.texels = nullptr; R->ds.uvs = nullptr;
+    bool anyTex = false;
+    for (int32_t t : R->mat_tex) anyTex |= (t >= 0);
+    if (anyTex && n > 0) {
+        if (R->mat_tex.size() != R->mats.size() * 2) return fail(ctx, SPB_ERR_INVALID, "texture bindings do not match the material list");
+        for (int32_t t : R->mat_tex) if (t >= (int32_t)R->texs.size()) return fail(ctx, SPB_ERR_INVALID, "a material refers to a texture that was not set");
+        for (const spb_texture& t : R->texs)
+            if (t.type == SPB_TEX_BITMAP && (t.width <= 0 || t.height <= 0 || t.texel_offset < 0 ||
+                                             (size_t)(t.texel_offset + (int64_t)t.width * t.height) * 3 > R->texels.size()))
+                return fail(ctx, SPB_ERR_INVALID, "bitmap texture outside the texel array");
+        std::vector<float> uv((size_t)n * 6, 0.f);
+        if (!ctx->uvs.empty()) uv = ctx->uvs;
+        std::vector<float4> tx(std::max<size_t>(R->texels.size() / 3, 1));
+        for (size_t i = 0; i < R->texels.size() / 3; i++) tx[i] = make_float4(R->texels[i * 3], R->texels[i * 3 + 1], R->texels[i * 3 + 2], 0.f);
+        SPB_CUDA(ctx, cudaMalloc(&R->d_mat_tex, R->mat_tex.size() * sizeof(int32_t)));
+        SPB_CUDA(ctx, cudaMalloc(&R->d_texs, R->texs.size() * sizeof(spb_texture)));
+        SPB_CUDA(ctx, cudaMalloc(&R->d_texels, tx.size() * sizeof(float4)));
+        SPB_CUDA(ctx, cudaMalloc(&R->d_uvs, uv.size() * sizeof(float)));
+        SPB_CUDA(ctx, cudaMemcpy(R->d_mat_tex, R->mat_tex.data(), R->mat_tex.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        SPB_CUDA(ctx, cudaMemcpy(R->d_texs, R->texs.data(), R->texs.size() * sizeof(spb_texture), cudaMemcpyHostToDevice));
+        SPB_CUDA(ctx, cudaMemcpy(R->d_texels, tx.data(), tx.size() * sizeof(float4), cudaMemcpyHostToDevice));
+        SPB_CUDA(ctx, cudaMemcpy(R->d_uvs, uv.data(), uv.size() * sizeof(float), cudaMemcpyHostToDevice));
+        R->ds.mat_tex = R->d_mat_tex; R->ds.texs = R->d_texs; R->ds.texels = R->d_texels; R->ds.uvs = R->d_uvs;
+    }
     R->sort_materials = false;
     for (const spb_material& m : R->mats) if (m.type != R->mats[0].type) R->sort_materials = true;
     R->scene_dirty = false;
@@ -759,6 +825,29 @@ int spb_scene_set_materials(spb_ctx* ctx, const spb_material* mats, int32_t n) {
     if (n < 0 || (n > 0 && !mats)) return fail(ctx, SPB_ERR_INVALID, "spb_scene_set_materials: bad arguments");
     RenderState* R = rs(ctx);
     R->mats.assign(mats, mats + n);
+    R->mat_tex.clear();
+    R->scene_dirty = true;
+    return SPB_OK;
+}
+
+int spb_scene_set_textures(spb_ctx* ctx, const spb_texture* texs, int32_t n, const float* texels_rgb, int64_t n_texels) {
+    if (!ctx) return fail(nullptr, SPB_ERR_INVALID, "ctx is NULL");
+    if (n < 0 || (n > 0 && !texs) || n_texels < 0 || (n_texels > 0 && !texels_rgb)) return fail(ctx, SPB_ERR_INVALID, "spb_scene_set_textures: bad arguments");
+    for (int32_t i = 0; i < n; i++)
+        if (texs[i].type != SPB_TEX_BITMAP && texs[i].type != SPB_TEX_CHECKERBOARD) return fail(ctx, SPB_ERR_INVALID, "spb_scene_set_textures: unknown texture type");
+    RenderState* R = rs(ctx);
+    R->texs.assign(texs, texs + n);
+    R->texels.assign(texels_rgb, texels_rgb + n_texels * 3);
+    R->scene_dirty = true;
+    return SPB_OK;
+}
+
+int spb_scene_set_material_textures(spb_ctx* ctx, const int32_t* tex_ids, int32_t n_mats) {
+    if (!ctx) return fail(nullptr, SPB_ERR_INVALID, "ctx is NULL");
+    RenderState* R = rs(ctx);
+    if (!tex_ids) { R->mat_tex.clear(); R->scene_dirty = true; return SPB_OK; }
+    if (n_mats != (int32_t)R->mats.size()) return fail(ctx, SPB_ERR_INVALID, "spb_scene_set_material_textures: call spb_scene_set_materials first (counts differ)");
+    R->mat_tex.assign(tex_ids, tex_ids + (size_t)n_mats * 2);
     R->scene_dirty = true;
     return SPB_OK;
 }

@@ -162,9 +162,16 @@ std::shared_ptr<CObject> RenderParams::getObject(const std::string& n, bool remo
 std::shared_ptr<CObject> RenderParams::getObject(const std::string& n, std::nullptr_t, bool remove) {
     return takeOr(objects_, n, std::shared_ptr<CObject>(), remove);
 }
+std::shared_ptr<CObject> RenderParams::getTextureObject(const std::string& n, bool remove) {
+    auto it = objects_.find(n);
+    if (it == objects_.end()) return nullptr;
+    auto v = it->second;
+    if (remove) objects_.erase(it);
+    return v;
+}
 Spectrum RenderParams::getTexture(const std::string& n, bool remove, bool* found) {
     *found = true;
-    if (objects_.count(n)) FatalError("texture objects (bitmap / checkerboard) are outside this host's scope: %s", n.c_str());
+    if (objects_.count(n)) FatalError("a texture object on parameter \"%s\" is outside this host's scope (textures bind to reflectance-type parameters only)", n.c_str());
     auto s = spectrums_.find(n);
     if (s != spectrums_.end()) { Spectrum v = s->second; if (remove) spectrums_.erase(s); return v; }
     auto d = doubles_.find(n);

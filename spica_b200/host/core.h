@@ -119,6 +119,8 @@ public:
     // getTexture (renderparams.cc:374-440): object, else spectrum, else double -> a constant; here
     // only constants are in scope, returned as a Spectrum. `found` tells whether anything was there.
     Spectrum getTexture(const std::string& n, bool remove, bool* found);
+    // the texture OBJECT stored under `n` (a nested <texture type="bitmap|checkerboard" name=n>), or nullptr
+    std::shared_ptr<CObject> getTextureObject(const std::string& n, bool remove);
     Spectrum getTexture(const std::string& n, const Spectrum& def, bool remove = false);
     bool hasObject(const std::string& n) const { return objects_.count(n) != 0; }
 private:
@@ -190,9 +192,16 @@ public:
     std::shared_ptr<Film> film;
 };
 
+class Texture : public CObject {    // core/texture.h:64-69, as far as the device needs it: the POD + (bitmap) its texels
+public:
+    virtual void describe(spb_texture* out, std::vector<float>* texels) const = 0;
+};
+
 class SurfaceMaterial : public CObject {
 public:
     virtual void describe(spb_material* out) const = 0;   // the POD the device shades with
+    // textures bound to the reflectance-type parameters (spb_material::kr / kt), nullptr = the constant
+    virtual void textures(const Texture** kr, const Texture** kt) const { *kr = nullptr; *kt = nullptr; }
 };
 
 struct Triangle {                   // core/triangle.h: world-space points, optional normals / uvs

@@ -26,6 +26,9 @@ struct FlatScene {              // the primitives as the C ABI takes them
     std::vector<float> normals, uvs;
     std::vector<int32_t> material_id, light_id;
     std::vector<spb_material> materials;
+    std::vector<spb_texture> textures;      // + the bitmaps' texels and {kr, kt} bindings per material
+    std::vector<float> texels;
+    std::vector<int32_t> matTex;
     bool anyNormals = false, anyUV = false;
 };
 
@@ -34,6 +37,17 @@ void flatten(const std::vector<std::shared_ptr<Primitive>>& prims, FlatScene* f)
     f->verts.resize(n * 9); f->normals.assign(n * 9, 0.f); f->uvs.assign(n * 6, 0.f);
     f->material_id.resize(n); f->light_id.assign(n, -1);
     std::map<const SurfaceMaterial*, int> matIndex;
+    std::map<const Texture*, int> texIndex;
+    auto bindTexture = [&](const Texture* t) -> int32_t {
+        if (!t) return -1;
+        auto it = texIndex.find(t);
+        if (it == texIndex.end()) {
+            spb_texture d; t->describe(&d, &f->texels);
+            it = texIndex.emplace(t, (int)f->textures.size()).first;
+            f->textures.push_back(d);
+        }
+        return it->second;
+    };
     for (size_t i = 0; i < n; i++) {
         const Primitive& p = *prims[i];
         for (int k = 0; k < 3; k++) { f->verts[i * 9 + k * 3] = p.tri.p[k].x; f->verts[i * 9 + k * 3 + 1] = p.tri.p[k].y; f->verts[i * 9 + k * 3 + 2] = p.tri.p[k].z; }
@@ -46,8 +60,10 @@ void flatten(const std::vector<std::shared_ptr<Primitive>>& prims, FlatScene* f)
         auto it = matIndex.find(p.material.get());
         if (it == matIndex.end()) {
             spb_material m; p.material->describe(&m);
+            const Texture *tkr, *tkt; p.material->textures(&tkr, &tkt);
             it = matIndex.emplace(p.material.get(), (int)f->materials.size()).first;
             f->materials.push_back(m);
+            f->matTex.push_back(bindTexture(tkr)); f->matTex.push_back(bindTexture(tkt));
         }
         f->material_id[i] = it->second;
     }
@@ -167,6 +183,10 @@ public:
             }
             check(ctx, spb_scene_set_triangle_attributes(ctx, flat.material_id.data(), flat.light_id.data(), (int64_t)flat.material_id.size()), "spb_scene_set_triangle_attributes");
             check(ctx, spb_scene_set_materials(ctx, flat.materials.data(), (int32_t)flat.materials.size()), "spb_scene_set_materials");
+            if (!flat.textures.empty()) {
+                check(ctx, spb_scene_set_textures(ctx, flat.textures.data(), (int32_t)flat.textures.size(), flat.texels.data(), (int64_t)(flat.texels.size() / 3)), "spb_scene_set_textures");
+                check(ctx, spb_scene_set_material_textures(ctx, flat.matTex.data(), (int32_t)flat.materials.size()), "spb_scene_set_material_textures");
+            }
             check(ctx, spb_scene_set_lights(ctx, lights.data(), (int32_t)lights.size()), "spb_scene_set_lights");
             if (env) {
                 std::vector<float> rgb(env->image.rgb.begin(), env->image.rgb.end());

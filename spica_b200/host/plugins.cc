@@ -128,16 +128,60 @@ static void rejectBump(RenderParams& p, bool remove) {
     if (found) FatalError("bumpMap is outside this host's scope");
 }
 
+// ---- textures (textures/bitmap.cc:16-26, textures/checkerboard.cc:14-40) -------------------------------
+class BitmapTexture : public Texture {
+public:
+    explicit BitmapTexture(RenderParams& p) : image_(Image::fromFile(p.getString("filename", true))) {}
+    void describe(spb_texture* t, std::vector<float>* texels) const override {
+        std::memset(t, 0, sizeof(*t));
+        t->type = SPB_TEX_BITMAP; t->width = image_.width; t->height = image_.height;
+        t->texel_offset = (int64_t)(texels->size() / 3);
+        texels->insert(texels->end(), image_.rgb.begin(), image_.rgb.end());
+    }
+private:
+    Image image_;
+};
+class Checkerboard : public Texture {
+public:
+    explicit Checkerboard(RenderParams& p)
+        : c0_(p.getSpectrum("color0")), c1_(p.getSpectrum("color1")), uo_(p.getDouble("uoffset")), vo_(p.getDouble("voffset")),
+          us_(p.getDouble("uscale")), vs_(p.getDouble("vscale")) {}
+    void describe(spb_texture* t, std::vector<float>* texels) const override;
+private:
+    Spectrum c0_, c1_; double uo_, vo_, us_, vs_;
+};
+
+void Checkerboard::describe(spb_texture* t, std::vector<float>*) const {
+    std::memset(t, 0, sizeof(*t));
+    t->type = SPB_TEX_CHECKERBOARD; setv(t->color0, c0_); setv(t->color1, c1_);
+    t->uoffset = (float)uo_; t->voffset = (float)vo_; t->uscale = (float)us_; t->vscale = (float)vs_;
+}
+
+// a reflectance-type parameter: a nested texture object, else the constant getTexture returns
+struct TexParam { Spectrum value; std::shared_ptr<Texture> tex; };
+static TexParam takeTexParam(RenderParams& p, const char* name, bool remove, bool* found) {
+    TexParam t;
+    if (auto obj = p.getTextureObject(name, remove)) {
+        t.tex = std::dynamic_pointer_cast<Texture>(obj);
+        if (!t.tex) FatalError("parameter \"%s\" is not a texture", name);
+        *found = true;
+        return t;
+    }
+    t.value = p.getTexture(name, remove, found);
+    return t;
+}
+
 class Diffuse : public SurfaceMaterial {                  // bsdfs/diffuse.cc:18-32
 public:
     explicit Diffuse(RenderParams& p) {
-        bool found; kd_ = p.getTexture("reflectance", true, &found);
+        bool found; kd_ = takeTexParam(p, "reflectance", true, &found);
         SpicaAssert(found, "Object not found: name = reflectance");
         rejectBump(p, true);
     }
-    void describe(spb_material* m) const override { std::memset(m, 0, sizeof(*m)); m->type = SPB_MAT_DIFFUSE; setv(m->kr, kd_); }
+    void describe(spb_material* m) const override { std::memset(m, 0, sizeof(*m)); m->type = SPB_MAT_DIFFUSE; setv(m->kr, kd_.value); }
+    void textures(const Texture** kr, const Texture** kt) const override { *kr = kd_.tex.get(); *kt = nullptr; }
 private:
-    Spectrum kd_;
+    TexParam kd_;
 };
 class Dielectric : public SurfaceMaterial {               // bsdfs/dielectric.cc:23-42
 public:
@@ -211,25 +255,26 @@ class Plastic : public SurfaceMaterial {                  // bsdfs/plastic.cc:10
 public:
     explicit Plastic(RenderParams& p) {
         bool f1, f2;
-        kd_ = p.getTexture("diffuseReflectance", false, &f1);
-        ks_ = p.getTexture("specularReflectance", false, &f2);
+        kd_ = takeTexParam(p, "diffuseReflectance", false, &f1);
+        ks_ = takeTexParam(p, "specularReflectance", false, &f2);
         SpicaAssert(f1 && f2, "plastic needs diffuseReflectance and specularReflectance (the reference dereferences null otherwise, plastic.cc:122-123)");
         ior_ = p.getTexture("intIOR", Spectrum(1.5)).gray();
         rejectBump(p, false);
     }
     void describe(spb_material* m) const override {
-        std::memset(m, 0, sizeof(*m)); m->type = SPB_MAT_PLASTIC; setv(m->kr, ks_); setv(m->kt, kd_);
+        std::memset(m, 0, sizeof(*m)); m->type = SPB_MAT_PLASTIC; setv(m->kr, ks_.value); setv(m->kt, kd_.value);
         m->eta[0] = m->eta[1] = m->eta[2] = (float)ior_;
     }
+    void textures(const Texture** kr, const Texture** kt) const override { *kr = ks_.tex.get(); *kt = kd_.tex.get(); }
 private:
-    Spectrum kd_, ks_; double ior_;
+    TexParam kd_, ks_; double ior_;
 };
 class RoughPlastic : public SurfaceMaterial {             // bsdfs/roughplastic.cc:118-165
 public:
     explicit RoughPlastic(RenderParams& p) {
         bool f1, f2;
-        kd_ = p.getTexture("diffuseReflectance", false, &f1);
-        ks_ = p.getTexture("specularReflectance", false, &f2);
+        kd_ = takeTexParam(p, "diffuseReflectance", false, &f1);
+        ks_ = takeTexParam(p, "specularReflectance", false, &f2);
         SpicaAssert(f1 && f2, "roughplastic needs diffuseReflectance and specularReflectance");
         ior_ = p.getTexture("intIOR", Spectrum(1.5)).gray();
         alpha_ = p.getTexture("alpha", Spectrum(0.1)).gray();
@@ -237,11 +282,12 @@ public:
         rejectBump(p, false);
     }
     void describe(spb_material* m) const override {
-        std::memset(m, 0, sizeof(*m)); m->type = SPB_MAT_ROUGHPLASTIC; m->distribution = distr_; setv(m->kr, ks_); setv(m->kt, kd_);
+        std::memset(m, 0, sizeof(*m)); m->type = SPB_MAT_ROUGHPLASTIC; m->distribution = distr_; setv(m->kr, ks_.value); setv(m->kt, kd_.value);
         m->eta[0] = m->eta[1] = m->eta[2] = (float)ior_; m->alpha_u = m->alpha_v = (float)alpha_;
     }
+    void textures(const Texture** kr, const Texture** kt) const override { *kr = ks_.tex.get(); *kt = kd_.tex.get(); }
 private:
-    Spectrum kd_, ks_; double ior_, alpha_; int distr_;
+    TexParam kd_, ks_; double ior_, alpha_; int distr_;
 };
 
 // ---- lights --------------------------------------------------------------------------------------------
@@ -281,6 +327,8 @@ void registerBuiltinPlugins() {
     pm.registerPlugin("roughconductor", [](RenderParams& p) -> CObject* { return new RoughConductor(p); });
     pm.registerPlugin("conductor", [](RenderParams& p) -> CObject* { return new Conductor(p); });
     pm.registerPlugin("roughdielectric", [](RenderParams& p) -> CObject* { return new RoughDielectric(p); });
+    pm.registerPlugin("bitmap", [](RenderParams& p) -> CObject* { return new BitmapTexture(p); });
+    pm.registerPlugin("checkerboard", [](RenderParams& p) -> CObject* { return new Checkerboard(p); });
     pm.registerPlugin("plastic", [](RenderParams& p) -> CObject* { return new Plastic(p); });
     pm.registerPlugin("roughplastic", [](RenderParams& p) -> CObject* { return new RoughPlastic(p); });
     pm.registerPlugin("area", makeArea);

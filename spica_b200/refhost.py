@@ -78,5 +78,12 @@ def read_dump(path):
         tail = take(np.float64, 4)
         out["env_center"], out["env_radius"] = tail[:3], float(tail[3])
         out["env_rgb"] = take(np.float32, ew * eh * 3).reshape(eh, ew, 3)
+    nt, ntex = (int(x) for x in take(np.int64, 2))
+    texs = (capi.Texture * max(nt, 1)).from_buffer_copy(raw[off:off + C.sizeof(capi.Texture) * max(nt, 1)].ljust(C.sizeof(capi.Texture) * max(nt, 1), b"\0"))
+    off += C.sizeof(capi.Texture) * nt
+    out["textures"] = [dict(type=t.type, width=t.width, height=t.height, texel_offset=t.texel_offset, color0=list(t.color0), color1=list(t.color1),
+                            uoffset=t.uoffset, voffset=t.voffset, uscale=t.uscale, vscale=t.vscale) for t in texs[:nt]]
+    out["material_textures"] = take(np.int32, 2 * nm).reshape(nm, 2)
+    out["texels"] = take(np.float32, ntex * 3).reshape(ntex, 3)
     assert off == len(raw), (off, len(raw))
     return out

@@ -27,12 +27,50 @@ struct FlatScene {              // the primitives as spb_scene_set_triangles tak
     std::vector<float> normals, uvs;
     std::vector<int32_t> material_id, light_id;
     std::vector<spb_material> materials;
+    std::vector<spb_texture> textures;      // + the bitmaps' texels and {kr, kt} bindings per material
+    std::vector<float> texels;
+    std::vector<int32_t> matTex;
+    std::map<const void*, int> texIndex;
     bool anyNormals = false, anyUV = false;
 };
 
 inline void setv(float dst[3], const Spectrum& s) { dst[0] = (float)s.red(); dst[1] = (float)s.green(); dst[2] = (float)s.blue(); }
 
-// Only constant textures are inside the path's scope (SURVEY.md 8f rank 2 lists bitmap / checkerboard as next).
+// A reflectance-type parameter: constant, or a bitmap / checkerboard texture bound to the material slot
+// (textures/bitmap.cc:16-26, textures/checkerboard.cc:23-40).  Returns the texture index or -1 (constant in *value).
+inline int32_t reflectanceParam(FlatScene* f, const std::shared_ptr<Texture<Spectrum>>& tex, const char* what, float value[3]) {
+    value[0] = value[1] = value[2] = 0.f;
+    if (!tex) FatalError("%s is missing", what);
+    if (isType(tex.get(), "N5spica15ConstantTextureINS_11RGBSpectrumEEE")) { setv(value, tex->evaluate(SurfaceInteraction())); return -1; }
+    auto it = f->texIndex.find(tex.get());
+    if (it != f->texIndex.end()) return it->second;
+    spb_texture t; std::memset(&t, 0, sizeof(t));
+    if (isType(tex.get(), "N5spica13BitmapTextureE")) {
+        const auto* b = static_cast<const BitmapTexture*>(tex.get());
+        if (!isType(b->texmap_.get(), "N5spica11UVMapping2DE")) FatalError("%s: only UV-mapped bitmaps are inside the GPU path's scope", what);
+        const auto* m = static_cast<const UVMapping2D*>(b->texmap_.get());
+        if (m->su_ != 1.0 || m->sv_ != 1.0 || m->du_ != 0.0 || m->dv_ != 0.0 || !m->invertHorizontal_) FatalError("%s: non-default UV mapping is outside the GPU path's scope", what);
+        if (b->mipmap_->imageWrap_ != ImageWrap::Repeat) FatalError("%s: only the Repeat wrap mode is inside the GPU path's scope", what);
+        const Image& im = b->mipmap_->pyramid_[0];
+        t.type = SPB_TEX_BITMAP; t.width = im.width(); t.height = im.height(); t.texel_offset = (int64_t)(f->texels.size() / 3);
+        for (int y = 0; y < im.height(); y++) for (int x = 0; x < im.width(); x++) {
+            const RGBSpectrum& c = im(x, y);
+            f->texels.push_back((float)c.red()); f->texels.push_back((float)c.green()); f->texels.push_back((float)c.blue());
+        }
+    } else if (isType(tex.get(), "N5spica12CheckerboardE")) {
+        const auto* c = static_cast<const Checkerboard*>(tex.get());
+        t.type = SPB_TEX_CHECKERBOARD; setv(t.color0, c->color0_); setv(t.color1, c->color1_);
+        t.uoffset = (float)c->uOffset_; t.voffset = (float)c->vOffset_; t.uscale = (float)c->uScale_; t.vscale = (float)c->vScale_;
+    } else {
+        FatalError("%s: texture type %s is outside the GPU path's scope (constant, bitmap, checkerboard)", what, typeid(*tex).name());
+    }
+    const int32_t id = (int32_t)f->textures.size();
+    f->textures.push_back(t);
+    f->texIndex.emplace(tex.get(), id);
+    return id;
+}
+
+// every other parameter must be constant
 inline Spectrum constantValue(const std::shared_ptr<Texture<Spectrum>>& tex, const char* what) {
     if (!tex) FatalError("%s is missing", what);
     if (!isType(tex.get(), "N5spica15ConstantTextureINS_11RGBSpectrumEEE"))
@@ -46,13 +84,14 @@ inline int distributionId(const std::string& name) {          // bsdfs/roughcond
     return 0;
 }
 
-inline void describeMaterial(const SurfaceMaterial* sm, spb_material* m) {
+inline void describeMaterial(FlatScene* f, const SurfaceMaterial* sm, spb_material* m, int32_t tex[2]) {
     std::memset(m, 0, sizeof(*m));
+    tex[0] = tex[1] = -1;
     auto noBump = [](const std::shared_ptr<Texture<Spectrum>>& b) { if (b) FatalError("bump maps are outside the GPU path's scope"); };
     if (isType(sm, "N5spica7DiffuseE")) {                                   // bsdfs/diffuse.cc:23-32
         const auto* d = static_cast<const Diffuse*>(sm);
         noBump(d->bumpMap_);
-        m->type = SPB_MAT_DIFFUSE; setv(m->kr, constantValue(d->Kd_, "diffuse reflectance"));
+        m->type = SPB_MAT_DIFFUSE; tex[0] = reflectanceParam(f, d->Kd_, "diffuse reflectance", m->kr);
     } else if (isType(sm, "N5spica10DielectricE")) {                        // bsdfs/dielectric.cc:30-42
         const auto* d = static_cast<const Dielectric*>(sm);
         noBump(d->bumpMap_);
@@ -84,14 +123,14 @@ inline void describeMaterial(const SurfaceMaterial* sm, spb_material* m) {
         const auto* d = static_cast<const Plastic*>(sm);
         noBump(d->bumpMap_);
         m->type = SPB_MAT_PLASTIC;
-        setv(m->kr, constantValue(d->Ks_, "specularReflectance")); setv(m->kt, constantValue(d->Kd_, "diffuseReflectance"));
+        tex[0] = reflectanceParam(f, d->Ks_, "specularReflectance", m->kr); tex[1] = reflectanceParam(f, d->Kd_, "diffuseReflectance", m->kt);
         m->eta[0] = m->eta[1] = m->eta[2] = (float)constantValue(d->eta_, "intIOR").gray();
     } else if (isType(sm, "N5spica12RoughPlasticE")) {                      // bsdfs/roughplastic.cc:130-165
         const auto* d = static_cast<const RoughPlastic*>(sm);
         noBump(d->bumpMap_);
         if (d->remapRoughness_) FatalError("roughness remapping is outside the GPU path's scope");
         m->type = SPB_MAT_ROUGHPLASTIC; m->distribution = distributionId(d->distribution_);
-        setv(m->kr, constantValue(d->Ks_, "specularReflectance")); setv(m->kt, constantValue(d->Kd_, "diffuseReflectance"));
+        tex[0] = reflectanceParam(f, d->Ks_, "specularReflectance", m->kr); tex[1] = reflectanceParam(f, d->Kd_, "diffuseReflectance", m->kt);
         m->eta[0] = m->eta[1] = m->eta[2] = (float)constantValue(d->index_, "intIOR").gray();
         m->alpha_u = m->alpha_v = (float)constantValue(d->roughness_, "alpha").gray();
     } else {
@@ -132,9 +171,11 @@ inline void flatten(const std::vector<std::shared_ptr<Primitive>>& prims, FlatSc
         const SurfaceMaterial* sm = mat->bsdf_.get();
         auto it = matIndex.find(sm);
         if (it == matIndex.end()) {
-            spb_material m; describeMaterial(sm, &m);
+            spb_material m; int32_t tex[2];
+            describeMaterial(f, sm, &m, tex);
             it = matIndex.emplace(sm, (int)f->materials.size()).first;
             f->materials.push_back(m);
+            f->matTex.push_back(tex[0]); f->matTex.push_back(tex[1]);
         }
         f->material_id[i] = it->second;
     }

@@ -129,6 +129,11 @@ public:
                 fwrite(envL2W, sizeof(double), 16, fp); fwrite(tail, sizeof(double), 4, fp);
                 fwrite(envRgb.data(), sizeof(float), envRgb.size(), fp);
             }
+            const int64_t thdr[2] = {(int64_t)flat.textures.size(), (int64_t)(flat.texels.size() / 3)};     // trailer: textures
+            fwrite(thdr, sizeof(thdr), 1, fp);
+            fwrite(flat.textures.data(), sizeof(spb_texture), flat.textures.size(), fp);
+            fwrite(flat.matTex.data(), sizeof(int32_t), flat.matTex.size(), fp);
+            fwrite(flat.texels.data(), sizeof(float), flat.texels.size(), fp);
             fclose(fp);
             MsgInfo("scene PODs written to %s; not rendering", path);
             return;
@@ -149,6 +154,10 @@ public:
             }
             check(ctx, spb_scene_set_triangle_attributes(ctx, flat.material_id.data(), flat.light_id.data(), (int64_t)flat.material_id.size()), "spb_scene_set_triangle_attributes");
             check(ctx, spb_scene_set_materials(ctx, flat.materials.data(), (int32_t)flat.materials.size()), "spb_scene_set_materials");
+            if (!flat.textures.empty()) {
+                check(ctx, spb_scene_set_textures(ctx, flat.textures.data(), (int32_t)flat.textures.size(), flat.texels.data(), (int64_t)(flat.texels.size() / 3)), "spb_scene_set_textures");
+                check(ctx, spb_scene_set_material_textures(ctx, flat.matTex.data(), (int32_t)flat.materials.size()), "spb_scene_set_material_textures");
+            }
             check(ctx, spb_scene_set_lights(ctx, lights.data(), (int32_t)lights.size()), "spb_scene_set_lights");
             if (env) check(ctx, spb_scene_set_envmap(ctx, envRgb.data(), envW, envH, envL2W, 1.0, envCenter, env->worldRadius_), "spb_scene_set_envmap");
             if (G > 1) check(ctx, spb_comm_init(ctx, commId, G, g), "spb_comm_init");

@@ -94,6 +94,8 @@
 #include "filters/tent.h"
 #include "lights/area.h"
 #include "lights/envmap.h"
+#include "textures/bitmap.h"
+#include "textures/checkerboard.h"
 #undef private
 #undef protected
 

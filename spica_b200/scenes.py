@@ -193,18 +193,21 @@ def cornell_parts(variant="diffuse"):
     variant "glossy" : config 3 (tall box rough conductor, short box dielectric);
     variant "zoo"    : specular conductor, Beckmann rough dielectric, GGX rough conductor back wall; its
                        XML also uses a thin-lens camera and a Gaussian filter;
+    variant "textured": checkerboard floor, bitmap back wall, plastic tall box with a bitmap diffuse layer
+                       (textures/checkerboard.cc, textures/bitmap.cc); its OBJ files carry vn + vt, which the
+                       reference needs both of to keep the texcoords (core/meshio.cc:193-233);
     variant "plastic": SURVEY 8f rank 2 -- smooth plastic tall box, GGX rough plastic short box, Beckmann rough
                        plastic floor."""
     parts = [
-        ("floor", "lacquer" if variant == "plastic" else "white", [_quad((-1, -1, -1), (-1, -1, 1), (1, -1, 1), (1, -1, -1))], None),
+        ("floor", {"plastic": "lacquer", "textured": "checker"}.get(variant, "white"), [_quad((-1, -1, -1), (-1, -1, 1), (1, -1, 1), (1, -1, -1))], None),
         ("ceiling", "white", [_quad((-1, 1, -1), (1, 1, -1), (1, 1, 1), (-1, 1, 1))], None),
-        ("back", "brushed" if variant == "zoo" else "white", [_quad((-1, -1, -1), (1, -1, -1), (1, 1, -1), (-1, 1, -1))], None),
+        ("back", {"zoo": "brushed", "textured": "poster"}.get(variant, "white"), [_quad((-1, -1, -1), (1, -1, -1), (1, 1, -1), (-1, 1, -1))], None),
         ("left", "red", [_quad((-1, -1, -1), (-1, 1, -1), (-1, 1, 1), (-1, -1, 1))], None),
         ("right", "green", [_quad((1, -1, -1), (1, -1, 1), (1, 1, 1), (1, 1, -1))], None),
         # emitter: faces down (e1 x e2 = -y), just below the ceiling
         ("light", "black", [_quad((-0.25, 0.995, -0.25), (0.25, 0.995, -0.25), (0.25, 0.995, 0.25), (-0.25, 0.995, 0.25))],
          (17.0, 12.0, 4.0)),
-        ("tallbox", {"glossy": "metal", "zoo": "mirror", "plastic": "plastic"}.get(variant, "white"), _box_quads(-0.33, -0.3, 0.3, 1.2, 0.3, -1.0, 0.3), None),
+        ("tallbox", {"glossy": "metal", "zoo": "mirror", "plastic": "plastic", "textured": "decal"}.get(variant, "white"), _box_quads(-0.33, -0.3, 0.3, 1.2, 0.3, -1.0, 0.3), None),
         ("shortbox", {"glossy": "glass", "zoo": "frosted", "plastic": "satin"}.get(variant, "white"), _box_quads(0.35, 0.3, 0.3, 0.6, 0.3, -1.0, -0.3), None),
     ]
     return parts
@@ -227,10 +230,56 @@ CORNELL_BSDFS = {
     "satin": ("roughplastic", {"diffuseReflectance": (0.7, 0.3, 0.2), "specularReflectance": (0.9, 0.9, 0.9), "intIOR": 1.6,
                                "alpha": 0.15, "distribution": "ggx"}),
     "lacquer": ("roughplastic", {"diffuseReflectance": (0.6, 0.6, 0.6), "specularReflectance": (1.0, 1.0, 1.0), "alpha": 0.08}),
+    # variant "textured": a texture-valued parameter is a dict {"texture": plugin type, ...plugin parameters}
+    "checker": ("diffuse", {"reflectance": {"texture": "checkerboard", "color0": (0.8, 0.8, 0.8), "color1": (0.15, 0.2, 0.55),
+                                            "uoffset": 0.0, "voffset": 0.25, "uscale": 3.0, "vscale": 2.0}}),
+    "poster": ("diffuse", {"reflectance": {"texture": "bitmap"}}),
+    "decal": ("plastic", {"diffuseReflectance": {"texture": "bitmap"}, "specularReflectance": (1.0, 1.0, 1.0), "intIOR": 1.5}),
     "glass": ("dielectric", {"specularReflectance": (1.0, 1.0, 1.0), "specularTransmittance": (1.0, 1.0, 1.0), "intIOR": 1.5}),
 }
 ZOO_LENS = (0.04, 3.4)      # apertureRadius, focusDistance of the "zoo" variant
 CORNELL_CAMERA = {"origin": (0.0, 0.0, 3.9), "target": (0.0, 0.0, 0.0), "up": (0.0, 1.0, 0.0), "fov": 39.3}
+
+
+QUAD_UVS = ((0.0, 0.0), (1.0, 0.0), (1.0, 1.0), (0.0, 1.0))     # texcoords of a quad's corners (variant "textured")
+
+
+def texture_image(w=16, h=8):
+    """The bitmap of the "textured" variant. Every texel is a multiple of 1/256 with its largest channel in
+    [0.5, 1), so the RGBE file holds it exactly and the reference's decode (m / 256 * 2^e, core/image.cc:380-382)
+    returns the same floats this function does."""
+    y, x = np.mgrid[0:h, 0:w]
+    r = 128 + ((x * 37 + y * 11) % 120)
+    g = 40 + ((x * 13 + y * 29) % 160)
+    b = 30 + (((x // 2 + y // 2) % 2) * 150)
+    img = np.stack([r, g, b], -1).astype(np.float32) / 256.0
+    assert (img.max(-1) >= 0.5).all() and (img.max(-1) < 1.0).all()
+    return img
+
+
+def cornell_uvs(variant):
+    """[n_triangles, 6] float32 texcoords in cornell_arrays order, or None when the variant has none."""
+    if variant != "textured":
+        return None
+    out = []
+    for _, _, quads, _ in cornell_parts(variant):
+        for _ in quads:
+            out.append([c for k in (0, 1, 2) for c in QUAD_UVS[k]])
+            out.append([c for k in (0, 2, 3) for c in QUAD_UVS[k]])
+    return np.asarray(out, dtype=np.float32)
+
+
+def cornell_normals(variant):
+    """[n_triangles, 9] float32 vertex normals (= the quad's face normal, as written to the OBJ) or None."""
+    if variant != "textured":
+        return None
+    out = []
+    for _, _, quads, _ in cornell_parts(variant):
+        for a, b, c, d in quads:
+            n = np.cross(b - a, c - a)
+            n = (n / np.linalg.norm(n)).astype(np.float32)
+            out.append(np.tile(n, 3)); out.append(np.tile(n, 3))
+    return np.asarray(out, dtype=np.float32)
 
 
 def _quads_to_tris(quads):
@@ -250,10 +299,20 @@ def write_cornell(dirpath, width=512, height=512, spp=64, max_depth=8, variant="
         with open(os.path.join(dirpath, "%s_%s.obj" % (name, pname)), "w") as f:
             f.write("# %s\no %s\n" % (pname, pname))
             nv = 0
-            for q in quads:
+            for qi, q in enumerate(quads):
                 for p in q:
                     f.write("v %.9g %.9g %.9g\n" % (np.float32(p[0]), np.float32(p[1]), np.float32(p[2])))
-                f.write("f %d %d %d\nf %d %d %d\n" % (nv + 1, nv + 2, nv + 3, nv + 1, nv + 3, nv + 4))
+                if variant == "textured":
+                    n = np.cross(q[1] - q[0], q[2] - q[0])
+                    n = (n / np.linalg.norm(n)).astype(np.float32)
+                    f.write("vn %.9g %.9g %.9g\n" % (n[0], n[1], n[2]))
+                    for uv in QUAD_UVS:
+                        f.write("vt %g %g\n" % uv)
+                    ix = [(nv + k, nv + k, qi + 1) for k in (1, 2, 3, 4)]
+                    for tri in ((0, 1, 2), (0, 2, 3)):
+                        f.write("f " + " ".join("%d/%d/%d" % ix[k] for k in tri) + "\n")
+                else:
+                    f.write("f %d %d %d\nf %d %d %d\n" % (nv + 1, nv + 2, nv + 3, nv + 1, nv + 3, nv + 4))
                 nv += 4
         if bsdf not in used:
             used.append(bsdf)
@@ -275,7 +334,20 @@ def write_cornell(dirpath, width=512, height=512, spp=64, max_depth=8, variant="
         typ, prm = CORNELL_BSDFS[b]
         x.append('  <bsdf type="%s" id="%s">' % (typ, b))
         for k, v in prm.items():
-            if isinstance(v, tuple):
+            if isinstance(v, dict):                      # nested texture plugin (spica/sceneparser.cc:303-327)
+                x.append('    <texture type="%s" name="%s">' % (v["texture"], k))
+                if v["texture"] == "bitmap":
+                    write_hdr(os.path.join(dirpath, name + "_tex.hdr"), texture_image())
+                    x.append('      <string name="filename" value="%s_tex.hdr"/>' % name)
+                for tk, tv in v.items():
+                    if tk == "texture":
+                        continue
+                    if isinstance(tv, tuple):
+                        x.append('      <rgb name="%s" value="%g, %g, %g"/>' % ((tk,) + tv))
+                    else:
+                        x.append('      <float name="%s" value="%g"/>' % (tk, tv))
+                x.append('    </texture>')
+            elif isinstance(v, tuple):
                 x.append('    <rgb name="%s" value="%g, %g, %g"/>' % ((k,) + v))
             elif isinstance(v, str):
                 x.append('    <string name="%s" value="%s"/>' % (k, v))

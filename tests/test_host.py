@@ -98,6 +98,21 @@ def test_host_render_matches_reference(tmp_path):
 
 
 @pytest.mark.gpu
+def test_textured_scene_through_the_host_matches_the_direct_call(tmp_path):
+    """bitmap / checkerboard textures + OBJ vn/vt through the XML loader == the same scene set up through the C ABI."""
+    from spica_b200 import capi
+    xml = os.path.join(SCENES, "cornell_textured.xml")
+    img = host.render_scene(xml, str(tmp_path / "tex"), seed=5)
+    ctx = capi.Context(0)
+    direct = capi.cornell_render(ctx, 128, 128, 64, max_depth=8, variant="textured", seed=5)
+    ctx.close()
+    assert np.allclose(img, direct, rtol=1e-4, atol=1e-5)
+    g = np.load(os.path.join(GOLDEN, "cornell_textured_ref.npz"))
+    runs = g["runs"].astype(np.float64)
+    assert max(scenes.rel_mse(img, r, runs.mean(0)) for r in runs) <= 1.5 * float(g["pair_relmse"][0])
+
+
+@pytest.mark.gpu
 def test_envmap_roughdielectric_ply_scene_matches_reference(tmp_path):
     """Environment lighting (lights/envmap.cc), a PLY mesh with a GGX rough dielectric
     (bsdfs/roughdielectric.cc), a tent filter and a rotated envmap, loaded from the committed XML

@@ -59,7 +59,35 @@ def test_reference_host_scene_resolves_to_the_flat_scene(tmp_path, variant, gpu_
     assert np.allclose(d["raster_to_camera"].reshape(4, 4), r2c, atol=1e-15)
 
 
-def test_reference_host_matches_own_host_on_the_envmap_scene(tmp_path):
+def test_reference_host_textured_scene_resolves(tmp_path):
+    """bitmap + checkerboard textures on reflectance-type parameters, OBJ files with vn + vt: texture PODs, bindings,
+    texels and per-triangle texcoords as the reference's parser built them."""
+    s = _dump(tmp_path, os.path.join(SCENES, "cornell_textured.xml"))
+    tris, mid, lid, mats, lights = scenes.cornell_arrays("textured")
+    assert np.array_equal(s["verts"], tris) and np.array_equal(s["material_id"], mid)
+    assert s["any_uv"] and np.array_equal(s["uvs"], scenes.cornell_uvs("textured"))
+    assert np.allclose(s["normals"], scenes.cornell_normals("textured"), atol=1e-7)
+    assert len(s["materials"]) == len(mats)
+    kinds = {0: "bitmap", 1: "checkerboard"}
+    for got, want, bind in zip(s["materials"], mats, s["material_textures"]):
+        assert got["type"] == capi.MAT_TYPES[want["type"]]
+        for slot, keys in ((0, ("reflectance", "specularReflectance")), (1, ("specularTransmittance", "diffuseReflectance"))):
+            wanted = [want[k] for k in keys if k in want]
+            if wanted and isinstance(wanted[0], dict):
+                t = s["textures"][bind[slot]]
+                assert kinds[t["type"]] == wanted[0]["texture"]
+                if t["type"] == 1:
+                    assert np.allclose(t["color0"], wanted[0]["color0"]) and np.allclose(t["color1"], wanted[0]["color1"])
+                    assert (t["uoffset"], t["voffset"], t["uscale"], t["vscale"]) == (0.0, 0.25, 3.0, 2.0)
+                else:
+                    img = scenes.texture_image()
+                    assert (t["height"], t["width"]) == img.shape[:2]
+                    tex = s["texels"][t["texel_offset"]:t["texel_offset"] + img.shape[0] * img.shape[1]].reshape(img.shape)
+                    assert np.array_equal(tex, img)                  # the RGBE file holds these texels exactly
+            else:
+                assert bind[slot] == -1
+    assert len(s["textures"]) == 3                                   # one object per <texture> element: checker, poster, decal
+
     """PLY mesh with vertex normals, rough dielectric, tent filter, rotated environment map: the shim's
     PODs equal what this repo's own C++ host resolves from the same file."""
     xml = os.path.join(SCENES, "envtorus.xml")
@@ -90,7 +118,7 @@ def test_reference_host_has_no_cpu_fallback(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("variant", ["diffuse", "zoo", "plastic"])
+@pytest.mark.parametrize("variant", ["diffuse", "zoo", "plastic", "textured"])
 def test_reference_host_renders_on_the_gpu(tmp_path, variant):
     """`spica -i scene.xml` of the unmodified reference, GPU plugins swapped in: the .hdr its hdrfilm
     wrote is within the reference's own seed-to-seed variance of the reference's renders."""

@@ -22,7 +22,7 @@ def _golden(variant):
     return runs, int(g["spp"]), int(g["width"]), int(g["height"]), int(g["max_depth"]), float(g["pair_relmse"][0])
 
 
-@pytest.mark.parametrize("variant", ["diffuse", "glossy", "zoo", "plastic"])
+@pytest.mark.parametrize("variant", ["diffuse", "glossy", "zoo", "plastic", "textured"])
 def test_cornell_relmse_against_reference(gpu_ctx, variant):
     if not os.path.exists(os.path.join(GOLDEN, "cornell_%s_ref.npz" % variant)):
         pytest.skip("no fixture for " + variant)
