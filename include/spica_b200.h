@@ -182,6 +182,14 @@ int spb_render_samples(spb_ctx* ctx, int32_t first, int32_t count, int32_t strid
 int spb_film_read(spb_ctx* ctx, float* rgbw);
 /* Film::save's normalisation (core/film.cc:23-29): rgb = sum / (wsum + 1e-12); height x width x 3. */
 int spb_film_resolve(spb_ctx* ctx, float* rgb);
+/* The film's output stage on the device: normalise as spb_film_resolve does, then encode
+ * the pixel the way the reference's film plugins do before writing the file, so only the encoded bytes cross PCIe.
+ *   rgbe : HDRFilm -> Image::saveHdr's HDRPixel (core/image.cc:60-88): m = frexp(max(r,g,b)), bytes = c * m*256/max,
+ *          exponent + 128; height x width x 4 bytes.
+ *   ldr  : LDRFilm -> GammaTmo (core/tmo.cc:53-71: clamp(pow(c, 1/gamma), 0, 1)) then Image::toByte
+ *          (core/image.cc:484-487: uint8(255 * c)); height x width x 3 bytes. */
+int spb_film_resolve_rgbe(spb_ctx* ctx, uint8_t* rgbe);
+int spb_film_resolve_ldr(spb_ctx* ctx, double gamma, uint8_t* rgb8);
 /* Adds raw accumulators (same layout as spb_film_read) into the device film: resume / merge. */
 int spb_film_add(spb_ctx* ctx, const float* rgbw);
 

@@ -89,7 +89,8 @@ SYMBOLS = [
     "spb_ctx_stream",
     "spb_scene_set_triangle_attributes", "spb_scene_set_materials", "spb_scene_set_lights", "spb_scene_set_envmap",
     "spb_scene_set_textures", "spb_scene_set_material_textures",
-    "spb_render_begin", "spb_render_samples", "spb_film_read", "spb_film_resolve", "spb_film_add",
+    "spb_render_begin", "spb_render_samples", "spb_film_read", "spb_film_resolve", "spb_film_resolve_rgbe", "spb_film_resolve_ldr",
+    "spb_film_add",
     "spb_render_get_stats", "spb_comm_get_unique_id", "spb_comm_init", "spb_film_allreduce", "spb_comm_destroy",
 ]
 
@@ -133,6 +134,8 @@ def load():
     L.spb_film_read.argtypes = [vp, vp]
     L.spb_film_resolve.argtypes = [vp, vp]
     L.spb_film_add.argtypes = [vp, vp]
+    L.spb_film_resolve_rgbe.argtypes = [vp, vp]
+    L.spb_film_resolve_ldr.argtypes = [vp, C.c_double, vp]
     L.spb_render_get_stats.argtypes = [vp, C.POINTER(RenderStats)]
     L.spb_comm_get_unique_id.argtypes = [C.c_char_p]
     L.spb_comm_init.argtypes = [vp, C.c_char_p, i32, i32]
@@ -354,6 +357,16 @@ class Context:
     def film_read(self):
         out = np.empty(self._film_shape + (4,), dtype=np.float32)
         self._check(self.L.spb_film_read(self.h, _ptr(out)))
+        return out
+
+    def film_resolve_rgbe(self):
+        out = np.empty(self._film_shape + (4,), dtype=np.uint8)
+        self._check(self.L.spb_film_resolve_rgbe(self.h, _ptr(out)))
+        return out
+
+    def film_resolve_ldr(self, gamma=2.2):
+        out = np.empty(self._film_shape + (3,), dtype=np.uint8)
+        self._check(self.L.spb_film_resolve_ldr(self.h, float(gamma), _ptr(out)))
         return out
 
     def film_resolve(self):

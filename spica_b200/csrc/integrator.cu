@@ -532,6 +532,32 @@ __global__ void resolveKernel(const float4* film, float* rgb, int64_t n) {
     const float inv = 1.0f / (v.w + 1.0e-12f);                               // core/film.cc:27
     rgb[i * 3 + 0] = v.x * inv; rgb[i * 3 + 1] = v.y * inv; rgb[i * 3 + 2] = v.z * inv;
 }
+// the film plugins' pixel encodings (core/image.cc:60-88, core/tmo.cc:53-71 + core/image.cc:484-487), on the resolved float pixel
+__global__ void encodeRgbeKernel(const float4* film, uchar4* out, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 v = film[i];
+    const float inv = 1.0f / (v.w + 1.0e-12f);
+    const double r = (double)(v.x * inv), g = (double)(v.y * inv), b = (double)(v.z * inv);
+    double d = fmax(r, fmax(g, b));
+    if (!(d > 1.0e-32)) { out[i] = make_uchar4(0, 0, 0, 0); return; }
+    int ie;
+    const double m = frexp(d, &ie);
+    d = m * 256.0 / d;
+    out[i] = make_uchar4((unsigned char)(r * d), (unsigned char)(g * d), (unsigned char)(b * d), (unsigned char)(ie + 128));
+}
+__global__ void encodeLdrKernel(const float4* film, unsigned char* out, double invGamma, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 v = film[i];
+    const float inv = 1.0f / (v.w + 1.0e-12f);
+    const double c[3] = {(double)(v.x * inv), (double)(v.y * inv), (double)(v.z * inv)};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const double t = fmin(1.0, fmax(0.0, pow(c[k], invGamma)));
+        out[i * 3 + k] = (unsigned char)(255.0 * t);
+    }
+}
 __global__ void filmAddKernel(float4* film, const float4* add, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -995,6 +1021,29 @@ int spb_film_resolve(spb_ctx* ctx, float* rgb) {
     cudaFree(d);
     SPB_CUDA(ctx, e);
     return SPB_OK;
+}
+
+static int filmEncode(spb_ctx* ctx, void* host, size_t bytesPerPixel, double invGamma, const char* what) {
+    if (!ctx || !host) return fail(ctx, SPB_ERR_INVALID, std::string(what) + ": NULL argument");
+    RenderState* R = ctx->render;
+    if (!R || !R->begun) return fail(ctx, SPB_ERR_INVALID, std::string(what) + ": no film (call spb_render_begin)");
+    cudaSetDevice(ctx->device);
+    unsigned char* d = nullptr;
+    SPB_CUDA(ctx, cudaMalloc(&d, (size_t)R->film_pixels * bytesPerPixel));
+    const unsigned grid = (unsigned)((R->film_pixels + 255) / 256);
+    if (bytesPerPixel == 4) encodeRgbeKernel<<<grid, 256, 0, ctx->stream>>>(R->d_film, (uchar4*)d, R->film_pixels);
+    else encodeLdrKernel<<<grid, 256, 0, ctx->stream>>>(R->d_film, d, invGamma, R->film_pixels);
+    R->launches++;
+    cudaError_t e = cudaMemcpyAsync(host, d, (size_t)R->film_pixels * bytesPerPixel, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    SPB_CUDA(ctx, e);
+    return SPB_OK;
+}
+int spb_film_resolve_rgbe(spb_ctx* ctx, uint8_t* rgbe) { return filmEncode(ctx, rgbe, 4, 0.0, "spb_film_resolve_rgbe"); }
+int spb_film_resolve_ldr(spb_ctx* ctx, double gamma, uint8_t* rgb8) {
+    if (!(gamma >= 1.0e-12)) return fail(ctx, SPB_ERR_INVALID, "spb_film_resolve_ldr: too small gamma (core/tmo.cc:54)");
+    return filmEncode(ctx, rgb8, 3, 1.0 / gamma, "spb_film_resolve_ldr");
 }
 
 int spb_film_add(spb_ctx* ctx, const float* rgbw) {

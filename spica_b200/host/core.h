@@ -151,6 +151,8 @@ struct Image {              // row-major RGB doubles
     const double* pixel(int x, int y) const { return &rgb[((size_t)y * width + x) * 3]; }
     void saveHdr(const std::string& file) const;  // core/image.cc:390-435 (RGBE, literal runs)
     void savePng(const std::string& file) const;  // 8-bit, values clamped to [0,1]
+    static void writeHdrRgbe(const std::string& file, int width, int height, const unsigned char* rgbe);   // already-encoded pixels
+    static void writePngRgb8(const std::string& file, int width, int height, const unsigned char* rgb);
     static Image loadHdr(const std::string& file);
     static Image fromFile(const std::string& file);
 };
@@ -167,6 +169,11 @@ public:
     void save(int id) const;                                                    // film.cc:23-40
     void setSaveCallback(std::function<void(const Image&)> cb) { callback_ = std::move(cb); }
     virtual void saveImage(const std::string& filename, const Image& img) const = 0;
+    // Output stage on the device: fetch the ENCODED pixels of `ctx`'s film (spb_film_resolve_rgbe / _ldr) and write
+    // the same file save() would.  false = this film cannot (or a save callback wants the float image).
+    virtual bool saveFromDevice(spb_ctx* ctx, int id) const { (void)ctx; (void)id; return false; }
+    std::string fileNameFor(int id) const;                                      // film.cc:31-33: sprintf(filename_, id)
+    bool hasCallback() const { return (bool)callback_; }
 protected:
     int width_, height_;
     std::shared_ptr<Filter> filter_;

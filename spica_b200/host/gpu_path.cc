@@ -206,6 +206,8 @@ public:
 
         std::vector<float> rgb((size_t)width * height * 3);
         auto publish = [&](int id) {
+            // output stage on the device when nobody needs the float image: only the encoded pixels cross PCIe
+            if (!opt.onImage && !getenv("SPICA_HOST_ENCODE") && film.saveFromDevice(ctxs[0], id)) return;
             check(ctxs[0], spb_film_resolve(ctxs[0], rgb.data()), "spb_film_resolve");
             Image img(width, height);
             for (size_t i = 0; i < rgb.size(); i++) img.rgb[i] = rgb[i];

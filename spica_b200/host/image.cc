@@ -9,18 +9,12 @@
 namespace spica {
 
 void Image::saveHdr(const std::string& file) const {
-    std::ofstream ofs(file, std::ios::out | std::ios::binary);
-    if (!ofs.is_open()) FatalError("Failed to open file: %s", file.c_str());
-    char buf[256];
-    // header text as the reference writes it (core/image.cc:396-407)
-    snprintf(buf, sizeof(buf), "#?RADIANCE\n# Made with 100%% pure HDR Shop\nFORMAT=32-bit_rle_rgbe\nEXPOSURE=1.0000000000000\n\n-Y %d +X %d\n", height, width);
-    ofs.write(buf, strlen(buf));
-    std::vector<unsigned char> out;
-    std::vector<unsigned char> line((size_t)width * 4);
+    // HDRPixel (core/image.cc:60-88)
+    std::vector<unsigned char> rgbe((size_t)width * height * 4);
     for (int y = 0; y < height; y++) {
         for (int x = 0; x < width; x++) {
             const double* c = pixel(x, y);
-            unsigned char* q = &line[(size_t)x * 4];
+            unsigned char* q = &rgbe[((size_t)y * width + x) * 4];
             double d = std::max(c[0], std::max(c[1], c[2]));
             if (!(d > 1.0e-32)) { q[0] = q[1] = q[2] = q[3] = 0; continue; }      // image.cc:72-76
             int ie;
@@ -29,6 +23,20 @@ void Image::saveHdr(const std::string& file) const {
             q[0] = (unsigned char)(c[0] * d); q[1] = (unsigned char)(c[1] * d); q[2] = (unsigned char)(c[2] * d);
             q[3] = (unsigned char)(ie + 128);
         }
+    }
+    writeHdrRgbe(file, width, height, rgbe.data());
+}
+
+void Image::writeHdrRgbe(const std::string& file, int width, int height, const unsigned char* rgbe) {
+    std::ofstream ofs(file, std::ios::out | std::ios::binary);
+    if (!ofs.is_open()) FatalError("Failed to open file: %s", file.c_str());
+    char buf[256];
+    // header text as the reference writes it (core/image.cc:396-407)
+    snprintf(buf, sizeof(buf), "#?RADIANCE\n# Made with 100%% pure HDR Shop\nFORMAT=32-bit_rle_rgbe\nEXPOSURE=1.0000000000000\n\n-Y %d +X %d\n", height, width);
+    ofs.write(buf, strlen(buf));
+    std::vector<unsigned char> out;
+    for (int y = 0; y < height; y++) {
+        const unsigned char* line = rgbe + (size_t)y * width * 4;
         out.push_back(0x02); out.push_back(0x02); out.push_back((width >> 8) & 0xff); out.push_back(width & 0xff);
         for (int c = 0; c < 4; c++) {
             for (int cur = 0; cur < width;) {
@@ -114,6 +122,15 @@ void chunk(std::ofstream& ofs, const char* type, const std::vector<unsigned char
 }  // namespace
 
 void Image::savePng(const std::string& file) const {
+    std::vector<unsigned char> rgb((size_t)width * height * 3);
+    for (int y = 0; y < height; y++) for (int x = 0; x < width; x++) for (int c = 0; c < 3; c++) {
+        const double v = std::min(1.0, std::max(0.0, pixel(x, y)[c]));                                 // Image::toByte (core/image.cc:484-487)
+        rgb[((size_t)y * width + x) * 3 + c] = (unsigned char)(v * 255.0);
+    }
+    writePngRgb8(file, width, height, rgb.data());
+}
+
+void Image::writePngRgb8(const std::string& file, int width, int height, const unsigned char* rgb) {
     std::ofstream ofs(file, std::ios::out | std::ios::binary);
     if (!ofs.is_open()) FatalError("Failed to open file: %s", file.c_str());
     const unsigned char sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
@@ -126,10 +143,7 @@ void Image::savePng(const std::string& file) const {
     raw.reserve((size_t)height * (width * 3 + 1));
     for (int y = 0; y < height; y++) {
         raw.push_back(0);
-        for (int x = 0; x < width; x++) for (int c = 0; c < 3; c++) {
-            const double v = std::min(1.0, std::max(0.0, pixel(x, y)[c]));
-            raw.push_back((unsigned char)(v * 255.0));
-        }
+        raw.insert(raw.end(), rgb + (size_t)y * width * 3, rgb + (size_t)(y + 1) * width * 3);
     }
     std::vector<unsigned char> z = {0x78, 0x01};
     uint32_t a = 1, b = 0;

@@ -51,10 +51,13 @@ void Film::save(int id) const {
         double* q = res.pixel(x, y);
         q[0] *= inv; q[1] *= inv; q[2] *= inv;
     }
+    saveImage(fileNameFor(id), res);
+    if (callback_) callback_(res);
+}
+std::string Film::fileNameFor(int id) const {
     char savefile[1024];
     snprintf(savefile, sizeof(savefile), filename_.c_str(), id);
-    saveImage(savefile, res);
-    if (callback_) callback_(res);
+    return savefile;
 }
 class HDRFilm : public Film {
 public:
@@ -64,6 +67,15 @@ public:
         const std::string out = filename + ".hdr";
         img.saveHdr(out);
         MsgInfo("Save: %s", out.c_str());
+    }
+    bool saveFromDevice(spb_ctx* ctx, int id) const override {       // the same file, pixels encoded by the GPU
+        if (hasCallback()) return false;
+        std::vector<unsigned char> rgbe((size_t)width_ * height_ * 4);
+        if (spb_film_resolve_rgbe(ctx, rgbe.data()) != SPB_OK) FatalError("spb_film_resolve_rgbe failed: %s", spb_last_error(ctx));
+        const std::string out = fileNameFor(id) + ".hdr";
+        Image::writeHdrRgbe(out, width_, height_, rgbe.data());
+        MsgInfo("Save: %s", out.c_str());
+        return true;
     }
 };
 class LDRFilm : public Film {
@@ -79,6 +91,15 @@ public:
         const std::string out = filename + ".png";
         t.savePng(out);
         MsgInfo("Save: %s", out.c_str());
+    }
+    bool saveFromDevice(spb_ctx* ctx, int id) const override {
+        if (hasCallback()) return false;
+        std::vector<unsigned char> rgb((size_t)width_ * height_ * 3);
+        if (spb_film_resolve_ldr(ctx, gamma_, rgb.data()) != SPB_OK) FatalError("spb_film_resolve_ldr failed: %s", spb_last_error(ctx));
+        const std::string out = fileNameFor(id) + ".png";
+        Image::writePngRgb8(out, width_, height_, rgb.data());
+        MsgInfo("Save: %s", out.c_str());
+        return true;
     }
 private:
     double gamma_;

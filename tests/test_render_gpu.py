@@ -68,6 +68,38 @@ def test_directlighting_integrator_against_reference(gpu_ctx):
     assert pt.mean() > 1.3 * img.mean()
 
 
+def test_film_output_stage_on_the_device(gpu_ctx, tmp_path):
+    """spb_film_resolve_rgbe / _ldr == the reference's pixel encodings (core/image.cc:60-88; core/tmo.cc:53-71 +
+    core/image.cc:484-487) applied on the host to the floats spb_film_resolve returns for the same film."""
+    capi.cornell_render(gpu_ctx, 96, 64, 8, max_depth=6, variant="glossy", seed=4)
+    rgb = gpu_ctx.film_resolve().astype(np.float64)
+    d = rgb.max(-1)
+    m, e = np.frexp(d)
+    lit = d > 1e-32
+    scale = np.where(lit, m * 256.0 / np.where(lit, d, 1.0), 0.0)
+    want = np.zeros(rgb.shape[:2] + (4,), dtype=np.uint8)
+    want[..., :3] = (rgb * scale[..., None]).astype(np.uint8)
+    want[..., 3] = np.where(lit, e + 128, 0).astype(np.uint8)
+    got = gpu_ctx.film_resolve_rgbe()
+    assert np.array_equal(got, want)
+    for gamma in (2.2, 1.0):
+        ldr = gpu_ctx.film_resolve_ldr(gamma)
+        ref = (255.0 * np.clip(np.power(rgb, 1.0 / gamma), 0.0, 1.0)).astype(np.uint8)
+        diff = np.abs(ldr.astype(np.int32) - ref.astype(np.int32))
+        assert diff.max() <= 1 and (diff != 0).mean() < 1e-3        # CUDA's pow is not correctly rounded: a value on a step boundary may move
+    # the films of the C++ host write their files from these bytes: same file as encoding on the host
+    import subprocess
+    from spica_b200 import host
+    xml = os.path.join(os.path.dirname(GOLDEN), "golden", "scenes", "cornell_diffuse.xml")
+    a = host.run_cli(xml, str(tmp_path / "dev"), seed=9)
+    env = dict(os.environ, SPICA_HOST_ENCODE="1")
+    b = subprocess.run([host.CLI_PATH, "-i", xml, "-o", str(tmp_path / "hostenc"), "--seed", "9"], capture_output=True, text=True,
+                       cwd=os.path.dirname(host.CLI_PATH), env=env)
+    assert a.returncode == 0 and b.returncode == 0, (a.stderr, b.stderr)
+    ia, ib = scenes.read_hdr(str(tmp_path / "dev.hdr")), scenes.read_hdr(str(tmp_path / "hostenc.hdr"))
+    assert (np.abs(ia - ib) <= ib.max(-1, keepdims=True) / 128 + 1e-6).all()      # same seed; float atomics may reorder
+
+
 def test_sample_partition_is_deterministic(gpu_ctx):
     """Counter-based sampler: rendering samples {0..7} in one call == two interleaved halves
     (what two GPUs do) up to float32 summation order."""
