@@ -75,6 +75,7 @@ void uploadGeometry(spb_ctx* ctx, const FlatScene& f) {
                                        f.material_id.data(), f.light_id.data(), n), "spb_scene_set_triangles");
     spb_build_opts opts; std::memset(&opts, 0, sizeof(opts));
     if (const char* b = getenv("SPICA_BVH_BUILDER")) opts.builder = atoi(b);    // 0 host binned SAH (default), 1 GPU LBVH
+    if (const char* b = getenv("SPICA_BVH_MAX_LEAF")) opts.max_leaf_tris = atoi(b);   // 1..3 triangles per leaf (default 1)
     check(ctx, spb_bvh_build(ctx, &opts), "spb_bvh_build");
 }
 }  // namespace
@@ -194,6 +195,7 @@ public:
                 check(ctx, spb_scene_set_envmap(ctx, rgb.data(), env->image.width, env->image.height, &env->toWorld.getMat().m[0][0], env->scale, c, env->worldRadius), "spb_scene_set_envmap");
             }
             if (G > 1) check(ctx, spb_comm_init(ctx, commId, G, g), "spb_comm_init");
+            if (const char* ws = getenv("SPICA_WAVE_SLOTS")) check(ctx, spb_set_option(ctx, "wave_slots", atoll(ws)), "spb_set_option(wave_slots)");
             check(ctx, spb_render_begin(ctx, &desc), "spb_render_begin");
         };
         auto forEachGpu = [&](const std::function<void(int)>& fn) {

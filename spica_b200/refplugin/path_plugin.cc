@@ -161,6 +161,7 @@ public:
             check(ctx, spb_scene_set_lights(ctx, lights.data(), (int32_t)lights.size()), "spb_scene_set_lights");
             if (env) check(ctx, spb_scene_set_envmap(ctx, envRgb.data(), envW, envH, envL2W, 1.0, envCenter, env->worldRadius_), "spb_scene_set_envmap");
             if (G > 1) check(ctx, spb_comm_init(ctx, commId, G, g), "spb_comm_init");
+            if (const char* ws = getenv("SPICA_WAVE_SLOTS")) check(ctx, spb_set_option(ctx, "wave_slots", atoll(ws)), "spb_set_option(wave_slots)");
             check(ctx, spb_render_begin(ctx, &desc), "spb_render_begin");
         };
         auto forEachGpu = [&](const std::function<void(int)>& fn) {
