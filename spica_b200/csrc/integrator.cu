@@ -947,6 +947,28 @@ int spb_render_begin(spb_ctx* ctx, const spb_render_desc* desc) {
     SPB_CUDA(ctx, cudaMemsetAsync(R->d_stats, 0, 8 * sizeof(unsigned long long), ctx->stream));
     SPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     R->launches = 0; R->render_ms = 0.0; R->paths_total = 0;
+    // Set-up that would otherwise land in the first spb_render_samples: the wavefront pool (capacity for 64 spp
+    // or one full wave, whichever is smaller) and the lazy loading of the loop's kernels -- with several
+    // contexts driven from one process the driver serialises those loads across the GPUs.
+    if ((rc = allocWave(ctx, R, std::min<int64_t>(ctx->opt_wave_slots, npix * 64)))) return rc;
+    {
+        cudaFuncAttributes fa;
+        cudaFuncGetAttributes(&fa, generateKernel);
+        cudaFuncGetAttributes(&fa, shadeKernel<true>);
+        cudaFuncGetAttributes(&fa, shadeKernel<false>);
+        cudaFuncGetAttributes(&fa, bounceEndKernel);
+        cudaFuncGetAttributes(&fa, filmKernel);
+        if (ctx->sp.tri_format == 0) {
+            cudaFuncGetAttributes(&fa, traceCoopKernel<0, false, false, spb_ray_f32, HitOut, 8>);
+            cudaFuncGetAttributes(&fa, traceCoopKernel<0, true, false, spb_ray_f32, SinkShadow, 8>);
+            cudaFuncGetAttributes(&fa, traceCoopKernel<0, false, false, spb_ray_f32, SinkMis, 8>);
+        } else {
+            cudaFuncGetAttributes(&fa, traceCoopKernel<1, false, false, spb_ray_f32, HitOut, 8>);
+            cudaFuncGetAttributes(&fa, traceCoopKernel<1, true, false, spb_ray_f32, SinkShadow, 8>);
+            cudaFuncGetAttributes(&fa, traceCoopKernel<1, false, false, spb_ray_f32, SinkMis, 8>);
+        }
+        cudaGetLastError();
+    }
     R->begun = true;
     return SPB_OK;
 }

@@ -3,8 +3,8 @@
 mkdir -p gpurun_out /tmp/rc
 python - <<'PY'
 from spica_b200 import scenes
-scenes.write_cornell("/tmp/rc", 1920, 1080, 4, 16, variant="diffuse", name="c3")
-scenes.write_cornell("/tmp/rc", 1920, 1080, 4, 16, variant="glossy", name="c4")
+scenes.write_cornell("/tmp/rc", 1920, 1080, 8, 16, variant="diffuse", name="c3")
+scenes.write_cornell("/tmp/rc", 1920, 1080, 8, 16, variant="glossy", name="c4")
 PY
 for c in c3 c4; do
   (cd spica_b200/bin && timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file ../../gpurun_out/launches_render_$c.csv \
