@@ -44,6 +44,7 @@ static int uploadBvh(spb_ctx* ctx) {
     sp.empty = (b.n_tris == 0 || b.nodes.empty()) ? 1 : 0;
     sp.n_tris = (int32_t)b.n_tris;
     sp.tri_format = b.tri_format;
+    sp.max_depth = b.max_depth;
     sp.inflate = (float)b.inflate;
     for (int k = 0; k < 3; k++) {
         sp.wlo[k] = b.wlo[k] - 2.0 * b.inflate;

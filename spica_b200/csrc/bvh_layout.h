@@ -47,6 +47,7 @@ struct SceneParams {                    // small POD passed to kernels by value
     int32_t tri_format;                 // 0 = TriF32, 1 = TriF64
     int32_t n_tris;
     int32_t empty;                      // 1: no geometry
+    int32_t max_depth;                  // depth of the wide tree = the most stack entries a ray can hold
 };
 
 }  // namespace spb

@@ -10,6 +10,7 @@
 // kept as the measurement baseline.
 #include <algorithm>
 
+#define SPB_EXPERIMENTAL_VARIANTS 1
 #include "context.h"
 #include "trace_kernels.cuh"
 

@@ -210,6 +210,56 @@ SPB_HD bool triPretestMayHit(const CullRay& r, float maxCoord, const U4& a, cons
     return true;
 }
 
+// The same pre-test with a third answer (kernel variant 6): 0 = certainly rejected, 1 = undecided
+// (the exact test decides), 2 = CERTAIN hit: every inequality of the exact test holds with the
+// error bound on the other side, so the exact test accepts this triangle at some distance in
+// [*tlo, *thi] along the culling ray (before its t <= maxDist comparison, which the caller makes
+// certain separately).  A certain hit lets the ray shrink its culling interval at once and postpone
+// the double-precision test until the lane has nothing else to do.
+#if defined(__CUDA_ARCH__)
+SPB_HD float fdivApprox(float a, float b) { return __fdividef(a, b); }   // <= 2 ulp for |b| < 2^126
+#else
+SPB_HD float fdivApprox(float a, float b) { return a / b; }
+#endif
+
+SPB_HD int triPretestClassify(const CullRay& r, float maxCoord, const U4& a, const U4& b, const U4& c, float* tlo,
+                              float* thi) {
+    const float p0x = asFloat(a.x), p0y = asFloat(a.y), p0z = asFloat(a.z);
+    const float e1x = asFloat(b.x) - p0x, e1y = asFloat(b.y) - p0y, e1z = asFloat(b.z) - p0z;
+    const float e2x = asFloat(c.x) - p0x, e2y = asFloat(c.y) - p0y, e2z = asFloat(c.z) - p0z;
+    const float px = r.fdy * e2z - r.fdz * e2y, py = r.fdz * e2x - r.fdx * e2z, pz = r.fdx * e2y - r.fdy * e2x;
+    const float det = e1x * px + e1y * py + e1z * pz;
+    const float tx = r.cox - p0x, ty = r.coy - p0y, tz = r.coz - p0z;
+    const float U = tx * px + ty * py + tz * pz;
+    const float qx = ty * e1z - tz * e1y, qy = tz * e1x - tx * e1z, qz = tx * e1y - ty * e1x;
+    const float V = r.fdx * qx + r.fdy * qy + r.fdz * qz;
+    const float T = e2x * qx + e2y * qy + e2z * qz;
+    const float E1 = fmaxf(fmaxf(fabsf(e1x), fabsf(e1y)), fabsf(e1z));
+    const float E2 = fmaxf(fmaxf(fabsf(e2x), fabsf(e2y)), fabsf(e2z));
+    const float TV = fmaxf(fmaxf(fabsf(tx), fabsf(ty)), fabsf(tz));
+    const float k = 7.62939453125e-06f;              // 2^-17
+    const float mt = k * (maxCoord + TV);
+    const float eDet = k * E1 * E2, eU = mt * E2, eV = mt * E1, eT = mt * E1 * E2;
+    const float D = fabsf(det);
+    if (!(D > eDet)) return 1;
+    const float sgn = det < 0.f ? -1.f : 1.f;
+    const float Us = sgn * U, Vs = sgn * V, Ts = sgn * T, Dhi = D + eDet, Dlo = D - eDet;
+    if (Us + eU < 0.f) return 0;
+    if (Us - eU > Dhi) return 0;
+    if (Vs + eV < 0.f) return 0;
+    if ((Us + Vs) - (eU + eV) > Dhi) return 0;
+    if (Ts + eT < 0.f) return 0;
+    if (Ts - eT > r.ctmax * Dhi) return 0;
+    // certain? (every comparison is false for NaN, which leaves the triangle undecided)
+    const float Tlo = Ts - eT, Thi = Ts + eT;
+    if (!(Dlo > 1e-10f && Us - eU > 0.f && Us + eU < Dlo && Vs - eV > 0.f && (Us + Vs) + (eU + eV) < Dlo && Tlo > 0.f))
+        return 1;
+    const float lo = fdivApprox(Tlo, Dhi) * 0.999999f, hi = fdivApprox(Thi, Dlo) * 1.000001f;
+    if (!(lo > 1e-9f && hi < 1e30f)) return 1;
+    *tlo = lo; *thi = hi;
+    return 2;
+}
+
 SPB_HD bool triPretestMayHit(const RayState& r, float maxCoord, const U4& a, const U4& b, const U4& c) {
     const CullRay cr = {r.cox, r.coy, r.coz, r.fdx, r.fdy, r.fdz, r.ctmax};
     return triPretestMayHit(cr, maxCoord, a, b, c);
@@ -366,6 +416,144 @@ struct Traverser {
         triPhase<true>(sp, r, tgroup, ctr);
         popPhase();
     }
+
+    // ---- early-select order (kernel variants 3, 4) -------------------------------------------------
+    // The same walk with the phases reordered: visit -> select the NEXT node -> triangles.  The
+    // loop-carried state is one node index (`cur`), known before the triangle phase starts, so the
+    // kernel can start fetching that node while the warp is busy with the triangle tests.  A closer
+    // hit found in the triangle phase cannot un-select the node; it is visited with the smaller
+    // ctmax and culls its children (conservative, never changes the result).
+    uint32_t cur;
+
+    SPB_HD void begin2(bool valid) { sp_ = 0; cur = 0u; finished = !valid; }
+
+    SPB_HD U2 visitLoaded(const U4& n0, const U4& n1, const U4& n2, const U4& n3, const U4& n4, const RayState& r,
+                          U2* cgroup, TraceCounters* ctr) {
+        const uint32_t hm = nodeHitMask(n0, n1, n2, n3, n4, r);
+        if (ctr) ctr->nodes++;
+        cgroup->x = n1.x;
+        cgroup->y = (hm & 0xff000000u) | (n0.w >> 24);
+        U2 tgroup;
+        tgroup.x = n1.y;
+        tgroup.y = hm & 0x00ffffffu;
+        return tgroup;
+    }
+
+    SPB_HD U2 visitPhase(const SceneParams& sp, const RayState& r, U2* cgroup, TraceCounters* ctr) {
+        const char* np = (const char*)(sp.nodes + cur);
+        const U4 n0 = ldg4(np), n1 = ldg4(np + 16), n2 = ldg4(np + 32), n3 = ldg4(np + 48), n4 = ldg4(np + 64);
+        return visitLoaded(n0, n1, n2, n3, n4, r, cgroup, ctr);
+    }
+
+    // g: the child group of the node just visited.  Takes the nearest pending inner child of g, or of
+    // the group on top of the stack when g has none; the rest of that group goes (back) on the stack.
+    SPB_HD void selectPhase(const RayState& r, U2 g) { selectPhaseOn(r, g, LocalStack{stack}); }
+
+    // The same with the stack held elsewhere (kernel variant 4: shared memory, entry i of a thread
+    // at s[i * stride], which no two lanes of a warp ever share a bank for).
+    struct LocalStack {
+        U2* s;
+        SPB_HD U2 get(int i) const { return s[i]; }
+        SPB_HD void set(int i, U2 v) const { s[i] = v; }
+    };
+    template <class Stack>
+    SPB_HD void selectPhaseOn(const RayState& r, U2 g, const Stack& st) {
+        if (!(g.y & 0xff000000u)) {
+            if (sp_ == 0) { finished = true; return; }
+            g = st.get(--sp_);
+        }
+        const uint32_t hits = g.y;
+        const int bit = 31 - clz32(hits);
+        g.y &= ~(1u << bit);
+        if (g.y & 0xff000000u) st.set(sp_++, g);
+        const uint32_t slot = (uint32_t)(bit - 24) ^ r.oct_inv;
+        cur = g.x + (uint32_t)popc32(hits & ~(0xffffffffu << slot) & 0xffu);
+    }
+
+    // ---- deferred exact test (kernel variant 6, float32-exact triangles) ----------------------------
+    // `pend` is a triangle record known to be a certain hit closer than r.best_t (see
+    // triPretestClassify) whose exact test has not been run yet; r.ctmax has already been shrunk to
+    // its upper bound.  It may be replaced by a certain hit that is certainly nearer, and it is
+    // resolved by the ordinary exact test when the ray has finished its walk - in the kernel all
+    // lanes waiting for new rays do that together instead of one or two lanes after each node.
+    // The answer is the reference's: every dropped candidate is certainly farther than a certain
+    // hit, and whatever is not certain goes through the exact test at once, as in triPhase.
+    uint32_t pend;
+    float pend_lo;
+
+    SPB_HD void acceptExact(const SceneParams& sp, RayState& r, uint32_t index, TraceCounters* ctr) {
+        double t, u, v; int32_t id, rank;
+        if (triTestRecord<TRI_FMT, false>(sp, r, index, &t, &u, &v, &id, &rank, ctr)) {
+            if (ANY_HIT) { r.best_prim = id; r.best_t = t; finished = true; return; }
+            if (t < r.best_t || r.best_prim < 0 || rank < r.best_rank) {
+                r.best_t = t; r.best_prim = id; r.best_rank = rank;
+                r.best_u = (float)u; r.best_v = (float)v;
+                r.ctmax = fminf(r.ctmax, cullTmax(r, t));
+            }
+        }
+    }
+
+    SPB_HD void resolvePending(const SceneParams& sp, RayState& r, TraceCounters* ctr) {
+        if (pend != 0xffffffffu) { const uint32_t p = pend; pend = 0xffffffffu; acceptExact(sp, r, p, ctr); }
+    }
+
+    // One node's candidates after the pre-test: `maybe` = undecided triangles, `cert` = certain hits
+    // that are not certainly farther than the nearest certain one, whose distance bounds are [tlo, thi]
+    // (tlo is only meaningful when `cert` has a single bit).
+    SPB_HD void mergePhase(const SceneParams& sp, RayState& r, uint32_t base, uint32_t maybe, uint32_t cert, float tlo,
+                           float thi, TraceCounters* ctr) {
+        uint32_t now = maybe;
+        if (cert) {
+            const bool single = !(cert & (cert - 1u));
+            // certainly inside the reference's t <= maxDist (the exact best so far, or the caller's tmax)
+            const bool closer = (double)thi * 1.000002 + r.t_shift < r.best_t;
+            if (single && closer && (pend == 0xffffffffu || thi < pend_lo)) {
+                const uint32_t index = base + (uint32_t)ctz32(cert);
+                if (ANY_HIT) {
+                    const TriF32* tp = (const TriF32*)sp.tris + index;
+                    r.best_prim = (int32_t)ldg4(&tp->v0[0]).w; finished = true; return;
+                }
+                pend = index; pend_lo = tlo;
+                r.ctmax = fminf(r.ctmax, thi * 1.000002f + 1e-30f);
+            } else {
+                now |= cert;
+            }
+        }
+        while (now) {
+            const int i = ctz32(now);
+            now &= now - 1u;
+            acceptExact(sp, r, base + (uint32_t)i, ctr);
+            if (ANY_HIT && r.best_prim >= 0) return;    // (`finished` may already be set by selectPhase)
+        }
+    }
+
+    // scalar statement of the kernel's pooled protocol for one lane (unit-test emulation)
+    SPB_HD void deferredTriPhase(const SceneParams& sp, RayState& r, U2 tgroup, TraceCounters* ctr) {
+        uint32_t maybe = 0u, certAll = 0u, cert = 0u;
+        float lo[24], hi[24], cmin = 3.0e38f, clo = 0.f;
+        const CullRay cr = {r.cox, r.coy, r.coz, r.fdx, r.fdy, r.fdz, r.ctmax};
+        for (uint32_t m = tgroup.y; m; m &= m - 1u) {
+            const int i = ctz32(m);
+            if (ctr) ctr->tris++;
+            const TriF32* tp = (const TriF32*)sp.tris + (tgroup.x + (uint32_t)i);
+            const U4 a = ldg4(&tp->v0[0]), b = ldg4(&tp->v1[0]), c = ldg4(&tp->v2[0]);
+            const int cls = triPretestClassify(cr, sp.max_coord, a, b, c, &lo[i], &hi[i]);
+            if (cls == 1) maybe |= 1u << i;
+            if (cls == 2) { certAll |= 1u << i; if (hi[i] < cmin) cmin = hi[i]; }
+        }
+        for (uint32_t m = certAll; m; m &= m - 1u) {
+            const int i = ctz32(m);
+            if (lo[i] <= cmin) { cert |= 1u << i; if (hi[i] == cmin) clo = lo[i]; }
+        }
+        if (maybe | cert) mergePhase(sp, r, tgroup.x, maybe, cert, clo, cmin, ctr);
+    }
+
+    SPB_HD void step2(const SceneParams& sp, RayState& r, TraceCounters* ctr) {
+        U2 g;
+        const U2 tgroup = visitPhase(sp, r, &g, ctr);
+        selectPhase(r, g);
+        triPhase<true>(sp, r, tgroup, ctr);
+    }
 };
 
 
@@ -375,6 +563,40 @@ SPB_HD void traceRay(const SceneParams& sp, RayState& r, bool valid, TraceCounte
     Traverser<TRI_FMT, ANY_HIT> tr;
     tr.begin(valid);
     while (!tr.finished) tr.step(sp, r, ctr);
+}
+
+// early-select order + deferred exact test (kernel variant 6); the result is identical to traceRay's
+template <bool ANY_HIT>
+SPB_HD void traceRayDeferred(const SceneParams& sp, RayState& r, bool valid, TraceCounters* ctr) {
+    Traverser<0, ANY_HIT> tr;
+    tr.begin2(valid);
+    tr.pend = 0xffffffffu; tr.pend_lo = 0.f;
+    if (tr.finished) return;
+    for (;;) {
+        U2 g;
+        const U2 tgroup = tr.visitPhase(sp, r, &g, ctr);
+        tr.selectPhase(r, g);
+        const bool last = tr.finished;
+        if (tgroup.y) tr.deferredTriPhase(sp, r, tgroup, ctr);
+        if (last || tr.finished) break;
+    }
+    if (!ANY_HIT || r.best_prim < 0) tr.resolvePending(sp, r, ctr);
+}
+
+// early-select order (Traverser::step2); the result is identical to traceRay's
+template <int TRI_FMT, bool ANY_HIT>
+SPB_HD void traceRayEarlySelect(const SceneParams& sp, RayState& r, bool valid, TraceCounters* ctr) {
+    Traverser<TRI_FMT, ANY_HIT> tr;
+    tr.begin2(valid);
+    if (tr.finished) return;
+    for (;;) {
+        U2 g;
+        const U2 tgroup = tr.visitPhase(sp, r, &g, ctr);
+        tr.selectPhase(r, g);
+        const bool last = tr.finished;          // nothing left after this node's triangles
+        tr.template triPhase<true>(sp, r, tgroup, ctr);
+        if (last || tr.finished) break;
+    }
 }
 
 }  // namespace spb

@@ -251,6 +251,192 @@ __global__ void __launch_bounds__(128, 7) traceCoopKernel(SceneParams sp, const 
 }
 
 
+// ---- variants 3, 4, 5: variant 2 in early-select order, with the next node fetched ahead ---------
+// Traverser::selectPhase picks the next node BEFORE the triangle phase, so its 80 bytes can be on
+// their way while the warp runs the pooled pre-test and the exact tests (ncu on variant 2: 31 % of
+// the stall samples sit on the node load and on the stack pop that feeds its address).
+//   PF 0: early-select order only (measurement control)
+//   PF 1: prefetch.global.L1 of the node's three 32-byte sectors
+//   PF 2: cp.async of the node into a per-thread shared-memory slot (5 x 16 B, [piece][thread]
+//         layout: conflict-free), consumed with cp.async.wait_all + LDS.128 at the next visit
+__device__ __forceinline__ void prefetchL1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void cpAsync16(uint32_t smem, const void* g) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cpAsyncWaitAll() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int PF>
+__device__ __forceinline__ void fetchNodeAhead(const SceneParams& sp, uint32_t node, uint32_t smemSlot) {
+    const char* np = (const char*)(sp.nodes + node);
+    if (PF == 1) { prefetchL1(np); prefetchL1(np + 32); prefetchL1(np + 64); }
+    if (PF == 2) {
+#pragma unroll
+        for (int k = 0; k < 5; k++) cpAsync16(smemSlot + (uint32_t)k * 128u * 16u, np + 16 * k);
+    }
+}
+
+// SS > 0: the traversal stack lives in shared memory (SS entries per thread, [entry][thread] layout)
+struct SharedStack {
+    uint2* s;
+    __device__ __forceinline__ U2 get(int i) const { const uint2 v = s[i * 128]; return U2{v.x, v.y}; }
+    __device__ __forceinline__ void set(int i, U2 v) const { s[i * 128] = make_uint2(v.x, v.y); }
+};
+
+template <int ANY_, bool COUNT, class RayT, class Out, int REFILL_MIN, int PF, bool DEFER, int MINB, int SS>
+__global__ void __launch_bounds__(128, MINB) traceCoopAheadKernel(SceneParams sp, const RayT* __restrict__ rays, int64_t n,
+                                                               const uint32_t* __restrict__ n_dev, Out out,
+                                                               unsigned long long* ctr) {
+    constexpr bool ANY = ANY_ != 0;
+    constexpr uint32_t NONE = 0xffffffffu;
+    __shared__ uint32_t s_filt[4][32];
+    __shared__ uint32_t s_cert[DEFER ? 4 : 1][32], s_cmin[DEFER ? 4 : 1][32];
+    __shared__ float s_clo[DEFER ? 4 : 1][32];
+    __shared__ uint4 s_node[PF == 2 ? 5 * 128 : 1];
+    __shared__ uint2 s_stack[SS > 0 ? SS * 128 : 1];
+    const SharedStack sstack = {s_stack + (SS > 0 ? threadIdx.x : 0)};
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int wid = threadIdx.x >> 5;
+    uint32_t* filt = s_filt[wid];
+    uint32_t* cert = s_cert[DEFER ? wid : 0];
+    uint32_t* cmin = s_cmin[DEFER ? wid : 0];
+    float* clo = s_clo[DEFER ? wid : 0];
+    const uint4* myNode = s_node + (PF == 2 ? threadIdx.x : 0);
+    const uint32_t smemSlot = (uint32_t)__cvta_generic_to_shared(myNode);
+    if (n_dev) n = (int64_t)__ldg(n_dev);
+    Traverser<0, ANY> tr;
+    tr.pend = NONE; tr.pend_lo = 0.f;
+    RayState r;
+    r.cox = r.coy = r.coz = r.fdx = r.fdy = r.fdz = r.ctmax = 0.f;
+    TraceCounters c = {0ull, 0ull, 0ull};
+    int64_t mine = -1;
+    bool active = false, exhausted = (n <= 0);
+
+    for (;;) {
+        const unsigned idle = __ballot_sync(full, !active);      // lanes waiting for a ray (with DEFER: some still hold a postponed exact test)
+        const int nIdle = __popc(idle);
+        const bool refill = !exhausted && (nIdle >= REFILL_MIN || nIdle == 32);
+        if (DEFER && !ANY && (refill || exhausted)) {
+            // the postponed exact tests of all waiting lanes, together
+            if (!active && tr.pend != NONE) {
+                tr.resolvePending(sp, r, COUNT ? &c : nullptr);
+                out.store(mine, r);
+            }
+        }
+        if (refill) {
+            const int leader = __ffs(idle) - 1;
+            unsigned long long base = 0;
+            if (lane == leader) base = atomicAdd(ctr, (unsigned long long)nIdle);
+            base = __shfl_sync(full, base, leader);
+            if ((int64_t)base + nIdle >= n) exhausted = true;
+            if (!active) {
+                const int64_t idx = (int64_t)base + __popc(idle & ((1u << lane) - 1u));
+                if (idx < n) {
+                    mine = idx;
+                    const bool valid = loadRay(sp, rays, idx, r);
+                    tr.begin2(valid);
+                    if (tr.finished) out.store(mine, r);   // trivial miss
+                    else {
+                        active = true;
+                        if (PF == 2 && ANY) cpAsyncWaitAll();   // an any-hit may have left a fetch in flight to this slot
+                        fetchNodeAhead<PF>(sp, 0u, smemSlot);
+                    }
+                }
+            }
+        }
+        if (!__any_sync(full, active)) {
+            if (exhausted) break;
+            continue;
+        }
+        U2 tg; tg.x = 0u; tg.y = 0u;
+        if (active) {
+            U2 g;
+            if (PF == 2) {
+                cpAsyncWaitAll();
+                const uint4 a0 = myNode[0], a1 = myNode[128], a2 = myNode[256], a3 = myNode[384], a4 = myNode[512];
+                tg = tr.visitLoaded(U4{a0.x, a0.y, a0.z, a0.w}, U4{a1.x, a1.y, a1.z, a1.w}, U4{a2.x, a2.y, a2.z, a2.w},
+                                    U4{a3.x, a3.y, a3.z, a3.w}, U4{a4.x, a4.y, a4.z, a4.w}, r, &g, COUNT ? &c : nullptr);
+            } else {
+                tg = tr.visitPhase(sp, r, &g, COUNT ? &c : nullptr);
+            }
+            if (SS > 0) tr.selectPhaseOn(r, g, sstack); else tr.selectPhase(r, g);
+            if (!tr.finished) fetchNodeAhead<PF>(sp, tr.cur, smemSlot);
+        }
+        if (__any_sync(full, tg.y != 0u)) {
+            const int cnt = __popc(tg.y);
+            if (COUNT) c.tris += (unsigned long long)cnt;
+            int incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(full, incl, d);
+                if (lane >= d) incl += v;
+            }
+            const int total = __shfl_sync(full, incl, 31);
+            filt[lane] = 0u;
+            if (DEFER) { cert[lane] = 0u; cmin[lane] = 0x7f800000u; }
+            __syncwarp();
+            for (int base = 0; base < total; base += 32) {
+                const int j = base + lane;
+                int L = 0;                      // the owner of pooled candidate j
+#pragma unroll
+                for (int s = 16; s >= 1; s >>= 1) {
+                    const int v = __shfl_sync(full, incl, L + s - 1);
+                    if (v <= j) L += s;
+                }
+                const int inclL = __shfl_sync(full, incl, L);
+                const uint32_t maskL = __shfl_sync(full, tg.y, L);
+                const uint32_t baseL = __shfl_sync(full, tg.x, L);
+                CullRay cr;
+                cr.cox = __shfl_sync(full, r.cox, L); cr.coy = __shfl_sync(full, r.coy, L); cr.coz = __shfl_sync(full, r.coz, L);
+                cr.fdx = __shfl_sync(full, r.fdx, L); cr.fdy = __shfl_sync(full, r.fdy, L); cr.fdz = __shfl_sync(full, r.fdz, L);
+                cr.ctmax = __shfl_sync(full, r.ctmax, L);
+                int cls = 0, bit = 0;
+                float tlo = 0.f, thi = 0.f;
+                if (j < total) {
+                    int k = j - (inclL - __popc(maskL));
+                    uint32_t m = maskL;
+                    for (; k > 0; k--) m &= m - 1u;
+                    bit = __ffs((int)m) - 1;
+                    const TriF32* tp = (const TriF32*)sp.tris + (baseL + (uint32_t)bit);
+                    const U4 a = ldg4(&tp->v0[0]), b = ldg4(&tp->v1[0]), cc = ldg4(&tp->v2[0]);
+                    if (DEFER) {
+                        cls = triPretestClassify(cr, sp.max_coord, a, b, cc, &tlo, &thi);
+                        if (cls == 1) atomicOr(&filt[L], 1u << bit);
+                        if (cls == 2) atomicMin(&cmin[L], __float_as_uint(thi));
+                    } else if (triPretestMayHit(cr, sp.max_coord, a, b, cc)) {
+                        atomicOr(&filt[L], 1u << bit);
+                    }
+                }
+                if (DEFER) {
+                    // second pass: a certain hit stays unless it is certainly farther than the nearest certain one
+                    __syncwarp();
+                    if (cls == 2) {
+                        const uint32_t mn = cmin[L];
+                        if (tlo <= __uint_as_float(mn)) {
+                            atomicOr(&cert[L], 1u << bit);
+                            if (__float_as_uint(thi) == mn) clo[L] = tlo;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (DEFER) {
+                const uint32_t maybe = filt[lane], ce = cert[lane];
+                if (maybe | ce) tr.mergePhase(sp, r, tg.x, maybe, ce, clo[lane], __uint_as_float(cmin[lane]), COUNT ? &c : nullptr);
+            } else {
+                tg.y = filt[lane];
+                if (tg.y) tr.template triPhase<false>(sp, r, tg, COUNT ? &c : nullptr);
+            }
+        }
+        if (active && tr.finished) {
+            active = false;
+            if (!DEFER || ANY || tr.pend == NONE) out.store(mine, r);     // else: waits, with its postponed test, for the next refill
+        }
+    }
+    if (COUNT) { atomicAdd(ctr + 1, c.nodes); atomicAdd(ctr + 2, c.tris); }
+}
+
+
 // ---- launch ------------------------------------------------------------------------------------
 // `cursor` points at 4 x u64: [0] the ray cursor (zeroed here), [1] node visits, [2] triangle tests.
 template <int FMT, bool ANY, bool COUNT, class RayT, class Out>
@@ -264,13 +450,35 @@ static int launchTraceTyped(spb_ctx* ctx, const RayT* d_rays, int64_t n, const u
         const int64_t grid = (n + block - 1) / block;
         traceSimpleKernel<FMT, ANY, COUNT, RayT, Out><<<(unsigned)grid, block, 0, st>>>(ctx->sp, d_rays, n, out, cursor);
     } else {
-        const int coop = ctx->opt_variant == 2 ? 1 : 0;
+        int coop = ctx->opt_variant >= 2 ? 1 : 0;
         void (*kern)(SceneParams, const RayT*, int64_t, const uint32_t*, Out, unsigned long long*) =
             coop ? traceCoopKernel<FMT, ANY, COUNT, RayT, Out, 8> : tracePersistentKernel<FMT, ANY, COUNT, RayT, Out, 8, 2>;
+        if constexpr (FMT == 0) {     // the early-select kernels exist for float32-exact triangles only
+            const int v = ctx->opt_variant;
+            if (v == 3) { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 8, 0, false, 7, 0>; coop = 2; }
+            // 4: the stack in shared memory, when the tree is shallow enough for its 16 entries
+            if (v == 4) {
+                if (ctx->sp.max_depth <= 14) { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 8, 0, false, 7, 16>; coop = 11; }
+                else { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 8, 0, false, 7, 0>; coop = 2; }
+            }
+#ifdef SPB_EXPERIMENTAL_VARIANTS      // measurement variants (trace.cu only; profiles/r01g_kernel_experiments.md)
+            if (v == 10) { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 8, 1, false, 7, 0>; coop = 3; }
+            if (v == 11) { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 8, 2, false, 7, 0>; coop = 4; }
+            if (v == 12) { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 8, 0, true, 7, 0>; coop = 5; }
+            if (v == 13) { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 8, 0, false, 8, 0>; coop = 6; }
+            if (v == 14) { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 8, 0, false, 6, 0>; coop = 7; }
+            if (v == 15) { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 4, 0, false, 7, 0>; coop = 8; }
+            if (v == 16) { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 12, 0, false, 7, 0>; coop = 9; }
+            if (v == 17) { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 16, 0, false, 7, 0>; coop = 10; }
+            if (v == 18 && ctx->sp.max_depth <= 10) { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 8, 0, false, 7, 12>; coop = 12; }
+            if (v == 19 && ctx->sp.max_depth <= 14) { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 8, 0, false, 8, 16>; coop = 13; }
+            if (v == 20 && ctx->sp.max_depth <= 14) { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 8, 0, false, 6, 16>; coop = 14; }
+#endif
+        }
         const int block = 128;
         int perSm = ctx->opt_ctas_per_sm;
         if (perSm <= 0) {
-            static int cached[2] = {0, 0};   // one per kernel instantiation; the query is slow enough to matter per chunk
+            static int cached[16] = {0};   // one per kernel instantiation; the query is slow enough to matter per chunk
             if (cached[coop] <= 0) {
                 SPB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cached[coop], kern, block, 0));
                 if (cached[coop] < 1) cached[coop] = 1;

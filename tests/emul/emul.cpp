@@ -43,6 +43,7 @@ Emul* emul_create(const double* verts, int64_t n, int max_leaf, int bins, const 
     sp.empty = (n == 0 || e->bvh.nodes.empty()) ? 1 : 0;
     sp.n_tris = (int32_t)n;
     sp.tri_format = e->bvh.tri_format;
+    sp.max_depth = e->bvh.max_depth;
     sp.inflate = (float)e->bvh.inflate;
     for (int k = 0; k < 3; k++) { sp.wlo[k] = e->bvh.wlo[k] - 2 * e->bvh.inflate; sp.whi[k] = e->bvh.whi[k] + 2 * e->bvh.inflate; }
     { double m = 0.0; for (int k = 0; k < 3; k++) m = std::max(m, std::max(std::abs(sp.wlo[k]), std::abs(sp.whi[k]))); sp.max_coord = (float)(m * 1.0000002); }
@@ -71,8 +72,12 @@ void emul_trace(Emul* e, const void* rays, int f64, int64_t n, int any, int32_t*
                 else { const float* p = (const float*)rays + i * 8; for (int k = 0; k < 3; k++) { o[k] = p[k]; d[k] = p[3 + k]; } tmax = p[7]; }
                 RayState r;
                 const bool valid = rayBegin(e->sp, o[0], o[1], o[2], d[0], d[1], d[2], tmax, r);
-                (void)mode;
-                if (e->sp.tri_format == 0) { if (any) traceRay<0, true>(e->sp, r, valid, &ctrs[th]); else traceRay<0, false>(e->sp, r, valid, &ctrs[th]); }
+                if (mode == 2 && e->sp.tri_format == 0) {   // early select + deferred exact test (kernel variant 6)
+                    if (any) traceRayDeferred<true>(e->sp, r, valid, &ctrs[th]); else traceRayDeferred<false>(e->sp, r, valid, &ctrs[th]);
+                } else if (mode == 1) {   // early-select phase order (kernel variants 3, 4)
+                    if (e->sp.tri_format == 0) { if (any) traceRayEarlySelect<0, true>(e->sp, r, valid, &ctrs[th]); else traceRayEarlySelect<0, false>(e->sp, r, valid, &ctrs[th]); }
+                    else { if (any) traceRayEarlySelect<1, true>(e->sp, r, valid, &ctrs[th]); else traceRayEarlySelect<1, false>(e->sp, r, valid, &ctrs[th]); }
+                } else if (e->sp.tri_format == 0) { if (any) traceRay<0, true>(e->sp, r, valid, &ctrs[th]); else traceRay<0, false>(e->sp, r, valid, &ctrs[th]); }
                 else { if (any) traceRay<1, true>(e->sp, r, valid, &ctrs[th]); else traceRay<1, false>(e->sp, r, valid, &ctrs[th]); }
                 prim[i] = r.best_prim;
                 t[i] = r.best_prim >= 0 ? r.best_t : 0.0;

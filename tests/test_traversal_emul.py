@@ -158,3 +158,74 @@ def test_float32_pretest_is_conservative_under_bad_conditioning():
         frac[(scale, shift)] = e.exact_tests / max(e.tri_tests, 1e-9)
     assert frac[(1.0, 0.0)] < 0.45          # well-conditioned: most candidates never reach the double test
     assert frac[(1e-2, 50.0)] > 0.9         # coordinates >> triangle size: the pre-test abstains, still exact
+
+
+@pytest.mark.parametrize("max_leaf", [1, 3])
+def test_early_select_phase_order_gives_identical_hits(max_leaf):
+    """Kernel variants 3-5 visit, select the next node, and only then test triangles
+    (Traverser::step2): same (prim, t, u, v) and any-hit flags as the default order, and the node
+    selected before a closer hit was found costs only a few extra visits."""
+    v, f = scenes.torus_mesh(200, 100)
+    tris = scenes.mesh_triangles(v, f)
+    rays = np.concatenate([scenes.incoherent_rays(30000, v.min(0), v.max(0), seed=5),
+                           scenes.primary_rays(64, 64)], 0)
+    short = rays.copy(); short[:, 7] = 0.7
+    e = Emul(tris, max_leaf=max_leaf)
+    for rr in (rays, short):
+        p0, t0, u0, v0 = e.trace(rr, mode=0)
+        n0 = e.node_visits
+        p1, t1, u1, v1 = e.trace(rr, mode=1)
+        assert np.array_equal(p0, p1) and np.array_equal(t0, t1) and np.array_equal(u0, u1) and np.array_equal(v0, v1)
+        assert e.node_visits <= 1.05 * n0
+        a0 = e.trace(rr, any_hit=True, mode=0)[0] >= 0
+        a1 = e.trace(rr, any_hit=True, mode=1)[0] >= 0
+        assert np.array_equal(a0, a1)
+
+
+@pytest.mark.parametrize("max_leaf", [1, 3])
+def test_deferred_exact_test_gives_identical_hits(max_leaf):
+    """Kernel variant 6: a triangle the float32 pre-test proves to be a hit shrinks the culling
+    interval at once and its double-precision test is postponed to the end of the walk
+    (Traverser::mergePhase).  Same (prim, t, u, v) and any-hit flags, fewer exact tests."""
+    v, f = scenes.torus_mesh(200, 100)
+    tris = scenes.mesh_triangles(v, f)
+    rays = np.concatenate([scenes.incoherent_rays(40000, v.min(0), v.max(0), seed=6),
+                           scenes.primary_rays(64, 64)], 0)
+    anyr = scenes.incoherent_rays(40000, v.min(0), v.max(0), seed=6, anyhit=True)
+    e = Emul(tris, max_leaf=max_leaf)
+    p0, t0, u0, v0 = e.trace(rays, mode=0)
+    x0 = e.exact_tests
+    p2, t2, u2, v2 = e.trace(rays, mode=2)
+    assert np.array_equal(p0, p2) and np.array_equal(t0, t2) and np.array_equal(u0, u2) and np.array_equal(v0, v2)
+    assert e.exact_tests < x0
+    for rr in (rays, anyr):
+        a0 = e.trace(rr, any_hit=True, mode=0)[0] >= 0
+        a2 = e.trace(rr, any_hit=True, mode=2)[0] >= 0
+        assert np.array_equal(a0, a2)
+    # hits exactly at the caller's tmax, and just short of it, are decided by the exact test
+    h = p0 >= 0
+    for scale in (1.0, 1.0 - 1e-7, 1.0 + 1e-7, 0.5):
+        lim = rays[h].copy(); lim[:, 7] = (t0[h] * scale).astype(np.float32)
+        q0 = e.trace(lim, mode=0); q2 = e.trace(lim, mode=2)
+        assert all(np.array_equal(a, b) for a, b in zip(q0, q2))
+        assert np.array_equal(e.trace(lim, any_hit=True, mode=0)[0] >= 0, e.trace(lim, any_hit=True, mode=2)[0] >= 0)
+
+
+def test_deferred_exact_test_on_duplicates_and_shared_edges():
+    # two copies of every triangle (exact ties in t) and rays aimed at shared vertices / edges
+    v, f = scenes.torus_mesh(24, 12)
+    tris = scenes.mesh_triangles(v, f)
+    dup = np.concatenate([tris, tris[::-1]], 0)
+    rng = np.random.default_rng(11)
+    n = 4000
+    tri = tris.reshape(-1, 3, 3)
+    tgt = np.concatenate([tri[rng.integers(0, len(tri), n // 2), rng.integers(0, 3, n // 2)],          # vertices
+                          tri[rng.integers(0, len(tri), n // 2)][:, :2].mean(1)], 0)                  # edge midpoints
+    org = rng.uniform(-2, 2, (n, 3))
+    rays = np.zeros((n, 8), np.float32)
+    rays[:, :3] = org; rays[:, 3:6] = tgt - org; rays[:, 7] = 1e32
+    for T in (tris, dup):
+        e = Emul(T, max_leaf=3)
+        q0 = e.trace(rays, mode=0); q2 = e.trace(rays, mode=2)
+        assert all(np.array_equal(a, b) for a, b in zip(q0, q2))
+        assert np.array_equal(e.trace(rays, any_hit=True, mode=0)[0] >= 0, e.trace(rays, any_hit=True, mode=2)[0] >= 0)
