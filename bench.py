@@ -337,7 +337,7 @@ def main():
     achieved = b_ray * n / (per_launch_ms * 1e-3) * 1e-9
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": None, "peak_source": peak_src, "bytes_per_ray": b_ray,
-            "V_int": vis["V_int"], "V_leaf": vis["V_leaf"], "kernel": "traceCoopAheadKernel (closest, trace_variant 4)",
+            "V_int": vis["V_int"], "V_leaf": vis["V_leaf"], "kernel": "traceCoopPairKernel (closest, trace_variant 5)",
             "kernel_ms": per_launch_ms}
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):

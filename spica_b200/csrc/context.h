@@ -49,7 +49,9 @@ struct spb_ctx {
     int opt_counters = 0;
     int opt_block = 128;
     int opt_ctas_per_sm = 0;             // 0 = occupancy query
-    int opt_variant = 4;                 // 0 = one thread per ray, 1 = persistent dynamic fetch, 2 = 1 + warp-cooperative pre-test, 3 = 2 in early-select order, 4 = 3 with the stack in shared memory (default; falls back to 3 on deep trees and to 2 on float64 triangles)
+    int opt_variant = 5;                 // 0 = one thread per ray, 1 = persistent dynamic fetch, 2 = 1 + warp-cooperative pre-test, 3 = 2 in early-select order,
+                                         // 4 = 3 with the stack in shared memory, 5 = 4 with two node visits per pooled triangle phase (default;
+                                         // falls back to 3 on trees deeper than the shared stack and to 2 on float64 triangles)
     int64_t opt_chunk = 1 << 20;         // rays per pipelined chunk on the host-buffer path
     int64_t opt_wave_slots = 1 << 24;    // paths in flight per wave of the integrator (228 B each: 3.8 GB of the 180 GB; the nearly empty late bounces of a wave amortise over 4x more paths than at 4 Mi: C3 +28 %)
 

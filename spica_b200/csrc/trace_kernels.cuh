@@ -437,6 +437,137 @@ __global__ void __launch_bounds__(128, MINB) traceCoopAheadKernel(SceneParams sp
 }
 
 
+// ---- variant 5: two node visits per pooled triangle phase -----------------------------------------
+// Variant 4 with each lane visiting TWO nodes (visit, select, visit, select) before the warp pools
+// its triangle candidates.  The pool is twice as full (about 28 candidates for 32 lanes instead of
+// 14), and the scan / owner search / survivor hand-back and the divergent exact-test phase run half
+// as often per node.  Testing a node's triangles one visit later costs 0.6 % more node visits and
+// 3.8 % more candidates on the C2 rays (tests/emul mode 3) and never changes a result: the later
+// node is only visited with a larger ctmax than it could have had.
+// What the pooled pre-test needs of a lane (its two candidate groups and its culling ray) is parked
+// in shared memory, where any lane can read it; the owner keeps neither in registers.
+template <int ANY_, bool COUNT, class RayT, class Out, int REFILL_MIN, int MINB, int SS>
+__global__ void __launch_bounds__(128, MINB) traceCoopPairKernel(SceneParams sp, const RayT* __restrict__ rays, int64_t n,
+                                                               const uint32_t* __restrict__ n_dev, Out out,
+                                                               unsigned long long* ctr) {
+    constexpr bool ANY = ANY_ != 0;
+    __shared__ uint32_t s_filt[2][4][32];
+    __shared__ uint2 s_tg[2][4][32];          // (first triangle record, candidate mask) of the two visits
+    __shared__ float4 s_cull[2][4][32];       // (cox, coy, coz, ctmax), (fdx, fdy, fdz, -)
+    __shared__ uint2 s_stack[SS * 128];
+    const SharedStack sstack = {s_stack + threadIdx.x};
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int wid = threadIdx.x >> 5;
+    uint32_t* filtA = s_filt[0][wid];
+    uint32_t* filtB = s_filt[1][wid];
+    uint2* tgsA = s_tg[0][wid];
+    uint2* tgsB = s_tg[1][wid];
+    float4* cullA = s_cull[0][wid];
+    float4* cullB = s_cull[1][wid];
+    if (n_dev) n = (int64_t)__ldg(n_dev);
+    Traverser<0, ANY> tr;
+    RayState r;
+    r.ctmax = 0.f;
+    TraceCounters c = {0ull, 0ull, 0ull};
+    int64_t mine = -1;
+    bool active = false, exhausted = (n <= 0);
+
+    for (;;) {
+        const unsigned idle = __ballot_sync(full, !active);
+        const int nIdle = __popc(idle);
+        if (!exhausted && (nIdle >= REFILL_MIN || nIdle == 32)) {
+            const int leader = __ffs(idle) - 1;
+            unsigned long long base = 0;
+            if (lane == leader) base = atomicAdd(ctr, (unsigned long long)nIdle);
+            base = __shfl_sync(full, base, leader);
+            if ((int64_t)base + nIdle >= n) exhausted = true;
+            if (!active) {
+                const int64_t idx = (int64_t)base + __popc(idle & ((1u << lane) - 1u));
+                if (idx < n) {
+                    mine = idx;
+                    const bool valid = loadRay(sp, rays, idx, r);
+                    tr.begin2(valid);
+                    if (tr.finished) out.store(mine, r);   // trivial miss
+                    else {
+                        active = true;
+                        cullA[lane] = make_float4(r.cox, r.coy, r.coz, r.ctmax);
+                        cullB[lane] = make_float4(r.fdx, r.fdy, r.fdz, 0.f);
+                    }
+                }
+            }
+        }
+        if (!__any_sync(full, active)) {
+            if (exhausted) break;
+            continue;
+        }
+        uint32_t mA = 0u, mB = 0u;
+        {
+            U2 tgA, tgB; tgA.x = tgA.y = tgB.x = tgB.y = 0u;
+            if (active) {
+                U2 g;
+                tgA = tr.visitPhase(sp, r, &g, COUNT ? &c : nullptr);
+                tr.selectPhaseOn(r, g, sstack);
+                if (!tr.finished) {
+                    tgB = tr.visitPhase(sp, r, &g, COUNT ? &c : nullptr);
+                    tr.selectPhaseOn(r, g, sstack);
+                }
+                reinterpret_cast<float*>(&cullA[lane])[3] = r.ctmax;
+            }
+            tgsA[lane] = make_uint2(tgA.x, tgA.y);
+            tgsB[lane] = make_uint2(tgB.x, tgB.y);
+            mA = tgA.y; mB = tgB.y;
+        }
+        if (__any_sync(full, (mA | mB) != 0u)) {
+            const int cnt = __popc(mA) + __popc(mB);
+            if (COUNT) c.tris += (unsigned long long)cnt;
+            int incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(full, incl, d);
+                if (lane >= d) incl += v;
+            }
+            const int total = __shfl_sync(full, incl, 31);
+            filtA[lane] = 0u; filtB[lane] = 0u;
+            __syncwarp();
+            for (int base = 0; base < total; base += 32) {
+                const int j = base + lane;
+                int L = 0;                      // the owner of pooled candidate j
+#pragma unroll
+                for (int s = 16; s >= 1; s >>= 1) {
+                    const int v = __shfl_sync(full, incl, L + s - 1);
+                    if (v <= j) L += s;
+                }
+                const int inclL = __shfl_sync(full, incl, L);
+                if (j < total) {
+                    const uint2 a = tgsA[L], b = tgsB[L];
+                    const int nA = __popc(a.y);
+                    int k = j - (inclL - nA - __popc(b.y));
+                    const bool second = k >= nA;
+                    if (second) k -= nA;
+                    uint32_t m = second ? b.y : a.y;
+                    for (; k > 0; k--) m &= m - 1u;
+                    const int bit = __ffs((int)m) - 1;
+                    const float4 c0 = cullA[L], c1 = cullB[L];
+                    const CullRay cr = {c0.x, c0.y, c0.z, c1.x, c1.y, c1.z, c0.w};
+                    const TriF32* tp = (const TriF32*)sp.tris + ((second ? b.x : a.x) + (uint32_t)bit);
+                    const U4 ta = ldg4(&tp->v0[0]), tb = ldg4(&tp->v1[0]), tc = ldg4(&tp->v2[0]);
+                    if (triPretestMayHit(cr, sp.max_coord, ta, tb, tc)) atomicOr(second ? &filtB[L] : &filtA[L], 1u << bit);
+                }
+            }
+            __syncwarp();
+            U2 tg;
+            tg.y = filtA[lane];
+            if (tg.y) { tg.x = tgsA[lane].x; tr.template triPhase<false>(sp, r, tg, COUNT ? &c : nullptr); }
+            tg.y = filtB[lane];
+            if (tg.y && !(ANY && r.best_prim >= 0)) { tg.x = tgsB[lane].x; tr.template triPhase<false>(sp, r, tg, COUNT ? &c : nullptr); }
+        }
+        if (active && tr.finished) { out.store(mine, r); active = false; }
+    }
+    if (COUNT) { atomicAdd(ctr + 1, c.nodes); atomicAdd(ctr + 2, c.tris); }
+}
+
+
 // ---- launch ------------------------------------------------------------------------------------
 // `cursor` points at 4 x u64: [0] the ray cursor (zeroed here), [1] node visits, [2] triangle tests.
 template <int FMT, bool ANY, bool COUNT, class RayT, class Out>
@@ -461,15 +592,24 @@ static int launchTraceTyped(spb_ctx* ctx, const RayT* d_rays, int64_t n, const u
                 if (ctx->sp.max_depth <= 14) { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 8, 0, false, 7, 16>; coop = 11; }
                 else { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 8, 0, false, 7, 0>; coop = 2; }
             }
+            // 5: two node visits per pooled triangle phase, 6 CTAs per SM (80 registers); same fallbacks as 4
+            if (v == 5) {
+                if (ctx->sp.max_depth <= 14) { kern = traceCoopPairKernel<ANY, COUNT, RayT, Out, 8, 6, 16>; coop = 15; }
+                else { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 8, 0, false, 7, 0>; coop = 2; }
+            }
 #ifdef SPB_EXPERIMENTAL_VARIANTS      // measurement variants (trace.cu only; profiles/r01g_kernel_experiments.md)
             if (v == 10) { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 8, 1, false, 7, 0>; coop = 3; }
             if (v == 11) { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 8, 2, false, 7, 0>; coop = 4; }
             if (v == 12) { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 8, 0, true, 7, 0>; coop = 5; }
             if (v == 13) { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 8, 0, false, 8, 0>; coop = 6; }
             if (v == 14) { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 8, 0, false, 6, 0>; coop = 7; }
-            if (v == 15) { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 4, 0, false, 7, 0>; coop = 8; }
-            if (v == 16) { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 12, 0, false, 7, 0>; coop = 9; }
-            if (v == 17) { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 16, 0, false, 7, 0>; coop = 10; }
+            if (v == 15 && ctx->sp.max_depth <= 14) { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 4, 0, false, 7, 16>; coop = 8; }
+            if (v == 16 && ctx->sp.max_depth <= 14) { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 6, 0, false, 7, 16>; coop = 9; }
+            if (v == 17 && ctx->sp.max_depth <= 14) { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 12, 0, false, 7, 16>; coop = 10; }
+            if (v == 25 && ctx->sp.max_depth <= 14) { kern = traceCoopPairKernel<ANY, COUNT, RayT, Out, 8, 5, 16>; coop = 16; }
+            if (v == 21 && ctx->sp.max_depth <= 14) { kern = traceCoopPairKernel<ANY, COUNT, RayT, Out, 8, 7, 16>; coop = 19; }
+            if (v == 22 && ctx->sp.max_depth <= 14) { kern = traceCoopPairKernel<ANY, COUNT, RayT, Out, 8, 8, 16>; coop = 17; }
+            if (v == 23 && ctx->sp.max_depth <= 14) { kern = traceCoopPairKernel<ANY, COUNT, RayT, Out, 12, 6, 16>; coop = 18; }
             if (v == 18 && ctx->sp.max_depth <= 10) { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 8, 0, false, 7, 12>; coop = 12; }
             if (v == 19 && ctx->sp.max_depth <= 14) { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 8, 0, false, 8, 16>; coop = 13; }
             if (v == 20 && ctx->sp.max_depth <= 14) { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 8, 0, false, 6, 16>; coop = 14; }
@@ -478,7 +618,7 @@ static int launchTraceTyped(spb_ctx* ctx, const RayT* d_rays, int64_t n, const u
         const int block = 128;
         int perSm = ctx->opt_ctas_per_sm;
         if (perSm <= 0) {
-            static int cached[16] = {0};   // one per kernel instantiation; the query is slow enough to matter per chunk
+            static int cached[20] = {0};   // one per kernel instantiation; the query is slow enough to matter per chunk
             if (cached[coop] <= 0) {
                 SPB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cached[coop], kern, block, 0));
                 if (cached[coop] < 1) cached[coop] = 1;
