@@ -53,6 +53,13 @@ SPB_HD int    popc32(uint32_t x) { return __builtin_popcount(x); }
 struct U4 { uint32_t x, y, z, w; };
 struct U2 { uint32_t x, y; };
 
+// x << (s mod 32): one SHF.L.W on the device, no masking of the shift amount
+#if defined(__CUDA_ARCH__)
+SPB_HD uint32_t shlWrap(uint32_t x, uint32_t s) { return __funnelshift_l(0u, x, s); }
+#else
+SPB_HD uint32_t shlWrap(uint32_t x, uint32_t s) { return x << (s & 31u); }
+#endif
+
 SPB_HD float asFloat(uint32_t u) {
 #if defined(__CUDA_ARCH__)
     return __uint_as_float(u);
@@ -312,12 +319,16 @@ SPB_HD uint32_t nodeHitMask(const U4& n0, const U4& n1, const U4& n2, const U4& 
     const float aoy = (asFloat(n0.y) - r.coy) * r.idy;
     const float aoz = (asFloat(n0.z) - r.coz) * r.idz;
     const bool nx = r.idx < 0.f, ny = r.idy < 0.f, nz = r.idz < 0.f;
+    const uint32_t oct4 = r.oct_inv * 0x01010101u;
     uint32_t hitmask = 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
     for (int h = 0; h < 2; h++) {
-        const uint32_t meta4 = h ? n1.w : n1.z;
+        // meta bytes of four slots at once: an inner child (position 24 + slot: bits 3 and 4 set) moves to
+        // its place in the ray's front-to-back order, 24 + (slot ^ oct_inv)
+        uint32_t meta4 = h ? n1.w : n1.z;
+        meta4 ^= oct4 & (((meta4 >> 3) & (meta4 >> 4) & 0x01010101u) * 7u);
         const uint32_t lox = h ? n2.y : n2.x, loy = h ? n2.w : n2.z, loz = h ? n3.y : n3.x;
         const uint32_t hix = h ? n3.w : n3.z, hiy = h ? n4.y : n4.x, hiz = h ? n4.w : n4.z;
         const uint32_t nearx = nx ? hix : lox, farx = nx ? lox : hix;
@@ -327,7 +338,6 @@ SPB_HD uint32_t nodeHitMask(const U4& n0, const U4& n1, const U4& n2, const U4& 
 #pragma unroll
 #endif
         for (int j = 0; j < 4; j++) {
-            const uint32_t m = byteOf(meta4, j);
             const float tnx = ffma((float)byteOf(nearx, j), adx, aox);
             const float tny = ffma((float)byteOf(neary, j), ady, aoy);
             const float tnz = ffma((float)byteOf(nearz, j), adz, aoz);
@@ -336,11 +346,8 @@ SPB_HD uint32_t nodeHitMask(const U4& n0, const U4& n1, const U4& n2, const U4& 
             const float tfz = ffma((float)byteOf(farz, j), adz, aoz);
             const float tmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
             const float tmax = fminf(fminf(tfx, tfy), fminf(tfz, r.ctmax));
-            if (m != 0u && tmin <= tmax) {
-                uint32_t pos = m & 31u;
-                if (pos >= 24u) pos ^= r.oct_inv;
-                hitmask |= (m >> 5) << pos;
-            }
+            // (unary count) << position; an empty slot has meta 0 and contributes nothing
+            if (tmin <= tmax) hitmask |= shlWrap((meta4 >> (8 * j + 5)) & 7u, meta4 >> (8 * j));
         }
     }
     return hitmask;

@@ -556,11 +556,18 @@ __global__ void __launch_bounds__(128, MINB) traceCoopPairKernel(SceneParams sp,
                 }
             }
             __syncwarp();
-            U2 tg;
-            tg.y = filtA[lane];
-            if (tg.y) { tg.x = tgsA[lane].x; tr.template triPhase<false>(sp, r, tg, COUNT ? &c : nullptr); }
-            tg.y = filtB[lane];
-            if (tg.y && !(ANY && r.best_prim >= 0)) { tg.x = tgsB[lane].x; tr.template triPhase<false>(sp, r, tg, COUNT ? &c : nullptr); }
+            // the exact tests of both groups in ONE loop: the lanes with a survivor in either group go
+            // through the double-precision code together (it is the most divergent part of the kernel)
+            uint32_t sA = filtA[lane], sB = filtB[lane];
+            if (sA | sB) {
+                const uint32_t bA = tgsA[lane].x, bB = tgsB[lane].x;
+                do {
+                    uint32_t index;
+                    if (sA) { index = bA + (uint32_t)(__ffs((int)sA) - 1); sA &= sA - 1u; }
+                    else { index = bB + (uint32_t)(__ffs((int)sB) - 1); sB &= sB - 1u; }
+                    tr.acceptExact(sp, r, index, COUNT ? &c : nullptr);
+                } while ((sA | sB) && !(ANY && r.best_prim >= 0));
+            }
         }
         if (active && tr.finished) { out.store(mine, r); active = false; }
     }
