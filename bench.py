@@ -44,22 +44,49 @@ def peaks():
 
 
 class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU while the timed region runs: NVML (nvidia_ml_py)
+    every 2 ms when it loads, else one nvidia-smi query per 100 ms."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NVML_REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, index):
         self.index = index
-        self.rows = []
+        self.rows = []          # (sm_mhz, sm_max_mhz, set(reasons))
         self.stop = False
         self.th = None
+        self.source = "nvidia-smi"
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nv = pynvml
+            self.source = "nvml"
+        except Exception:
+            self.nv = None
 
     def _run(self):
         while not self.stop:
             try:
+                if self.nv is not None:
+                    sm = float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                    try:
+                        bits = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                    except Exception:
+                        bits = int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                    self.rows.append((sm, self.mx, {n for b, n in self.NVML_REASONS if bits & b}))
+                    time.sleep(0.002)
+                    continue
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([x.strip() for x in out.strip().split(",")])
+                r = [x.strip() for x in out.strip().split(",")]
+                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                self.rows.append((float(r[0]), float(r[1]), {nme for k, nme in enumerate(names) if r[3 + k].lower().startswith("active")}))
             except Exception:
                 pass
             time.sleep(0.1)
@@ -74,18 +101,13 @@ class ClockSampler:
         self.th.join(timeout=6)
 
     def summary(self):
-        sm, mx, reasons = [], 0.0, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        sm = [r[0] for r in self.rows]
+        mx = max([r[1] for r in self.rows], default=0.0)
+        reasons = set()
         for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx = max(mx, float(r[1]))
-                for k, nme in enumerate(names):
-                    if r[3 + k].lower().startswith("active"):
-                        reasons.add(nme)
-            except Exception:
-                continue
+            reasons |= r[2]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": self.source}
 
 
 def visits():
@@ -183,7 +205,7 @@ def main():
     ap.add_argument("--rays", type=int, default=N_RAYS)
     ap.add_argument("--ref-rays", type=int, default=1 << 21)
     ap.add_argument("--variant", type=int, default=-1)
-    ap.add_argument("--max-leaf", type=int, default=1)
+    ap.add_argument("--max-leaf", type=int, default=0, help="triangles per leaf, 1..3 (0 = library default, 3)")
     ap.add_argument("--render-spp", type=int, default=32, help="spp per GPU of the side render measurement (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--chunk", type=int, default=0, help="rays per pipelined chunk of the host-buffer call (0 = library default)")

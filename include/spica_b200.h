@@ -212,7 +212,7 @@ int spb_comm_destroy(spb_ctx* ctx);
 typedef struct spb_build_opts {
     int32_t builder;        /* 0 = host binned-SAH (default; best trees), 1 = GPU LBVH (Morton sort +
                              * Karras hierarchy + refit on the device; fastest build)            */
-    int32_t max_leaf_tris;  /* 1..3, default 1                                                  */
+    int32_t max_leaf_tris;  /* 1..3, 0 = default (3)                                             */
     int32_t sah_bins;       /* default 32                                                       */
     int32_t reserved_;
 } spb_build_opts;

@@ -192,7 +192,7 @@ class Context:
         li = None if light_id is None else np.ascontiguousarray(light_id, dtype=np.int32)
         self._check(self.L.spb_scene_set_triangles(self.h, _ptr(tris), _ptr(nm), _ptr(uv), _ptr(mi), _ptr(li), n))
 
-    def build(self, max_leaf_tris=1, sah_bins=32, builder=0):
+    def build(self, max_leaf_tris=0, sah_bins=32, builder=0):
         o = BuildOpts(builder, max_leaf_tris, sah_bins, 0)
         self._check(self.L.spb_bvh_build(self.h, C.byref(o)))
 

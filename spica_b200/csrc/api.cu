@@ -172,7 +172,7 @@ int spb_bvh_build(spb_ctx* ctx, const spb_build_opts* opts) {
     cudaSetDevice(ctx->device);
     spb_build_opts o = {0, 1, 32, 0};
     if (opts) o = *opts;
-    if (o.max_leaf_tris <= 0) o.max_leaf_tris = 1;
+    if (o.max_leaf_tris <= 0) o.max_leaf_tris = 3;     // measured best with the cost-optimal collapse (profiles/r01g_kernel_experiments.md)
     if (o.sah_bins <= 0) o.sah_bins = 32;
     if (o.builder != 0 && o.builder != 1) return fail(ctx, SPB_ERR_UNSUPPORTED, "spb_bvh_build: builder must be 0 (host binned SAH) or 1 (GPU LBVH)");
     const auto t0 = std::chrono::steady_clock::now();

@@ -4,6 +4,7 @@
 #include <atomic>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <future>
 #include <queue>
@@ -264,6 +265,94 @@ bool encode_wide(const BinaryBVH& bin, const double* verts, int64_t n_tris, int 
     };
     const double rootArea = std::max(nodeArea(bin.root), 1e-300);
 
+    // ---- cost-optimal collapse (dynamic programme over the binary tree, after Ylitie, Karras, Laine,
+    // "Efficient Incoherent Ray Traversal on GPUs Through Compressed Wide BVHs", HPG 2017, sec. 3.1):
+    // C(n, i) = least SAH cost of turning the subtree of n into at most i children of one wide node,
+    //   C(n, 1) = min(leaf: A_n * count * c_tri [count <= max_leaf], inner: A_n * c_node + D(n, 8))
+    //   C(n, i) = min(C(n, i-1), D(n, i)),   D(n, j) = min_k C(left, k) + C(right, j - k).
+    // The greedy expansion below fills 57 % of the child slots of the C2 tree; the optimal cut packs
+    // the bottom of the tree better.  SPICA_BVH_COLLAPSE=0 keeps the greedy rule (also used above 12 M
+    // triangles, where the tables would take more than 1 GB of host memory).
+    bool dp = n_tris <= (int64_t)12 << 20;
+    if (const char* e = std::getenv("SPICA_BVH_COLLAPSE")) dp = std::atoi(e) != 0 && dp;
+    struct DpRow { float c[8]; uint8_t k[8]; uint8_t k8; uint8_t leaf; };   // c[i-1] = C(n, i), k[i-1] = left share (0: same as i-1)
+    std::vector<DpRow> row;
+    auto skipSingles = [&](int32_t b) {      // an inner node with one child stands for that child
+        for (;;) {
+            const BinNode& n = bin.nodes[b];
+            if (n.left >= 0 && n.right >= 0) return b;
+            if (n.left < 0 && n.right < 0) return b;
+            b = n.left >= 0 ? n.left : n.right;
+        }
+    };
+    if (dp) {
+        float cTri = 0.7f;
+        if (const char* e = std::getenv("SPICA_BVH_CTRI")) cTri = (float)std::atof(e);
+        const float cNode = 1.0f, inf = 3.0e38f;
+        row.resize(bin.nodes.size());
+        // children before parents: iterative post-order
+        std::vector<int32_t> stackv; std::vector<int32_t> orderv;
+        stackv.push_back(bin.root); orderv.reserve(bin.nodes.size());
+        while (!stackv.empty()) {
+            const int32_t b = stackv.back(); stackv.pop_back();
+            orderv.push_back(b);
+            if (bin.nodes[b].left >= 0) stackv.push_back(bin.nodes[b].left);
+            if (bin.nodes[b].right >= 0) stackv.push_back(bin.nodes[b].right);
+        }
+        for (size_t oi = orderv.size(); oi-- > 0;) {
+            const int32_t b = orderv[oi];
+            const BinNode& n = bin.nodes[b];
+            DpRow& R = row[b];
+            const float A = (float)(nodeArea(b) / rootArea);
+            const float cLeaf = (n.count <= max_leaf || (n.left < 0 && n.right < 0)) ? A * (float)n.count * cTri : inf;
+            if (n.left < 0 && n.right < 0) {
+                for (int i = 0; i < 8; i++) { R.c[i] = cLeaf; R.k[i] = 0; }
+                R.k8 = 0; R.leaf = 1;
+                continue;
+            }
+            if (n.left < 0 || n.right < 0) { R = row[n.left >= 0 ? n.left : n.right]; continue; }   // pass-through
+            const DpRow& L = row[n.left]; const DpRow& Rr = row[n.right];
+            float D[9]; uint8_t Dk[9];
+            for (int j = 2; j <= 8; j++) {
+                float best = inf; uint8_t bk = 1;
+                for (int k = 1; k < j; k++) {
+                    const float v = L.c[k - 1] + Rr.c[j - k - 1];
+                    if (v < best) { best = v; bk = (uint8_t)k; }
+                }
+                D[j] = best; Dk[j] = bk;
+            }
+            const float cInner = A * cNode + D[8];
+            R.k8 = Dk[8];
+            R.leaf = cLeaf <= cInner ? 1 : 0;
+            R.c[0] = R.leaf ? cLeaf : cInner; R.k[0] = 0;
+            for (int i = 2; i <= 7; i++) {
+                if (D[i] < R.c[i - 2]) { R.c[i - 1] = D[i]; R.k[i - 1] = Dk[i]; }
+                else { R.c[i - 1] = R.c[i - 2]; R.k[i - 1] = 0; }
+            }
+            R.c[7] = R.c[6]; R.k[7] = 0;
+        }
+    }
+    std::vector<uint8_t> dpLeaf;           // per binary node: chosen as a leaf child by the optimal cut
+    if (dp) dpLeaf.assign(bin.nodes.size(), 0);
+    // children of the forest C(b, i), appended to ch[]
+    struct Frame { int32_t b; int i; };
+    auto collectDp = [&](int32_t b0, int i0, int32_t* ch, int& nch) {
+        Frame fs[64]; int nf = 0;
+        fs[nf++] = {b0, i0};
+        while (nf > 0) {
+            Frame f = fs[--nf];
+            const int32_t b = skipSingles(f.b);
+            const BinNode& n = bin.nodes[b];
+            int i = f.i;
+            if (n.left < 0 && n.right < 0) { dpLeaf[b] = 1; ch[nch++] = b; continue; }
+            while (i > 1 && row[b].k[i - 1] == 0) i--;
+            if (i == 1) { dpLeaf[b] = row[b].leaf; ch[nch++] = b; continue; }
+            const int k = row[b].k[i - 1];
+            fs[nf++] = {n.right, i - k};       // (popped after the left part: children stay in left-to-right order)
+            fs[nf++] = {n.left, k};
+        }
+    };
+
     struct Work { int32_t bnode; int32_t depth; };
     std::vector<Work> work;               // work[i] describes wide node i (BFS order)
     work.push_back({bin.root, 1});
@@ -275,8 +364,14 @@ bool encode_wide(const BinaryBVH& bin, const double* verts, int64_t n_tris, int 
         // ---- gather up to 8 children by greedy surface-area expansion
         int32_t ch[8]; int nch = 0;
         const BinNode& bn = bin.nodes[w.bnode];
-        if (leafLike(w.bnode)) {
+        if (wi == 0 && leafLike(w.bnode)) {
             ch[nch++] = w.bnode;          // degenerate root: a single leaf child
+            if (dp) dpLeaf[w.bnode] = 1;
+        } else if (dp) {
+            const int32_t b = skipSingles(w.bnode);
+            const BinNode& n = bin.nodes[b];
+            if (n.left < 0 && n.right < 0) { dpLeaf[b] = 1; ch[nch++] = b; }
+            else { const int k = row[b].k8; collectDp(n.left, k, ch, nch); collectDp(n.right, 8 - k, ch, nch); }
         } else {
             if (bn.left >= 0) ch[nch++] = bn.left;
             if (bn.right >= 0) ch[nch++] = bn.right;
@@ -380,7 +475,7 @@ bool encode_wide(const BinaryBVH& bin, const double* verts, int64_t n_tris, int 
             const int32_t c = slotChild[s];
             if (c < 0) { wn.meta[s] = 0; continue; }
             const double relA = nodeArea(c) / rootArea;
-            if (leafLike(c)) {
+            if (dp ? dpLeaf[c] != 0 : leafLike(c)) {
                 const BinNode& cn = bin.nodes[c];
                 const int n = cn.count;     // 1..3
                 const uint8_t unary = (uint8_t)((1u << n) - 1u);

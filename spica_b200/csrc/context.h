@@ -50,9 +50,9 @@ struct spb_ctx {
     int opt_block = 128;
     int opt_ctas_per_sm = 0;             // 0 = occupancy query
     int opt_variant = 5;                 // 0 = one thread per ray, 1 = persistent dynamic fetch, 2 = 1 + warp-cooperative pre-test, 3 = 2 in early-select order,
-                                         // 4 = 3 with the stack in shared memory, 5 = 4 with two node visits per pooled triangle phase (default;
+                                         // 4 = 3 with the stack in shared memory, 5 = 4 with three node visits per pooled triangle phase (default;
                                          // falls back to 3 on trees deeper than the shared stack and to 2 on float64 triangles)
-    int64_t opt_chunk = 1 << 20;         // rays per pipelined chunk on the host-buffer path
+    int64_t opt_chunk = 1 << 19;         // rays per pipelined chunk on the host-buffer path (measured: 256K 1412, 512K 1574, 1M 1403, 2M 1364 Mrays/s; PCIe floor 1574)
     int64_t opt_wave_slots = 1 << 24;    // paths in flight per wave of the integrator (228 B each: 3.8 GB of the 180 GB; the nearly empty late bounces of a wave amortise over 4x more paths than at 4 Mi: C3 +28 %)
 
     // counters

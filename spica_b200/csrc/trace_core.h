@@ -590,21 +590,21 @@ SPB_HD void traceRayDeferred(const SceneParams& sp, RayState& r, bool valid, Tra
     if (!ANY_HIT || r.best_prim < 0) tr.resolvePending(sp, r, ctr);
 }
 
-// two node visits per triangle phase (kernel variant 5); the result is identical to traceRay's
-template <int TRI_FMT, bool ANY_HIT>
-SPB_HD void traceRayTwoVisits(const SceneParams& sp, RayState& r, bool valid, TraceCounters* ctr) {
+// K node visits per triangle phase (kernel variant 5 uses K = 3); the result is identical to traceRay's
+template <int TRI_FMT, bool ANY_HIT, int K>
+SPB_HD void traceRayKVisits(const SceneParams& sp, RayState& r, bool valid, TraceCounters* ctr) {
     Traverser<TRI_FMT, ANY_HIT> tr;
     tr.begin2(valid);
     if (tr.finished) return;
     for (;;) {
-        U2 g;
-        const U2 tg1 = tr.visitPhase(sp, r, &g, ctr);
-        tr.selectPhase(r, g);
-        U2 tg2; tg2.x = 0u; tg2.y = 0u;
-        if (!tr.finished) { tg2 = tr.visitPhase(sp, r, &g, ctr); tr.selectPhase(r, g); }
+        U2 tg[K];
+        for (int q = 0; q < K; q++) {
+            tg[q].x = 0u; tg[q].y = 0u;
+            if (!tr.finished) { U2 g; tg[q] = tr.visitPhase(sp, r, &g, ctr); tr.selectPhase(r, g); }
+        }
         const bool last = tr.finished;
-        tr.template triPhase<true>(sp, r, tg1, ctr);
-        if (!(ANY_HIT && r.best_prim >= 0)) tr.template triPhase<true>(sp, r, tg2, ctr);
+        for (int q = 0; q < K; q++)
+            if (!(ANY_HIT && r.best_prim >= 0)) tr.template triPhase<true>(sp, r, tg[q], ctr);
         if (last || tr.finished) break;
     }
 }

@@ -437,32 +437,31 @@ __global__ void __launch_bounds__(128, MINB) traceCoopAheadKernel(SceneParams sp
 }
 
 
-// ---- variant 5: two node visits per pooled triangle phase -----------------------------------------
-// Variant 4 with each lane visiting TWO nodes (visit, select, visit, select) before the warp pools
-// its triangle candidates.  The pool is twice as full (about 28 candidates for 32 lanes instead of
-// 14), and the scan / owner search / survivor hand-back and the divergent exact-test phase run half
-// as often per node.  Testing a node's triangles one visit later costs 0.6 % more node visits and
-// 3.8 % more candidates on the C2 rays (tests/emul mode 3) and never changes a result: the later
-// node is only visited with a larger ctmax than it could have had.
-// What the pooled pre-test needs of a lane (its two candidate groups and its culling ray) is parked
+// ---- variant 5: K node visits per pooled triangle phase -------------------------------------------
+// Variant 4 with each lane visiting K nodes (visit, select, visit, select, ...) before the warp pools
+// its triangle candidates.  With K = 3 the pool holds about 42 candidates for 32 lanes instead of 14,
+// and the scan / owner search / survivor hand-back and the divergent exact-test phase run a third as
+// often per node.  Testing a node's triangles up to two visits later costs about 1 % more node visits
+// and a few % more candidates on the C2 rays (tests/emul mode 3) and never changes a result: the later
+// nodes are only visited with a larger ctmax than they could have had.  Measured: K = 2 2244,
+// K = 3 2306, K = 4 2310 Mrays/s on C2; K = 3 is also the best of the three on the Cornell renders.
+// What the pooled pre-test needs of a lane (its candidate groups and its culling ray) is parked
 // in shared memory, where any lane can read it; the owner keeps neither in registers.
-template <int ANY_, bool COUNT, class RayT, class Out, int REFILL_MIN, int MINB, int SS>
+template <int ANY_, bool COUNT, class RayT, class Out, int REFILL_MIN, int MINB, int SS, int K>
 __global__ void __launch_bounds__(128, MINB) traceCoopPairKernel(SceneParams sp, const RayT* __restrict__ rays, int64_t n,
                                                                const uint32_t* __restrict__ n_dev, Out out,
                                                                unsigned long long* ctr) {
     constexpr bool ANY = ANY_ != 0;
-    __shared__ uint32_t s_filt[2][4][32];
-    __shared__ uint2 s_tg[2][4][32];          // (first triangle record, candidate mask) of the two visits
+    __shared__ uint32_t s_filt[K][4][32];
+    __shared__ uint2 s_tg[K][4][32];          // (first triangle record, candidate mask) of the K visits
     __shared__ float4 s_cull[2][4][32];       // (cox, coy, coz, ctmax), (fdx, fdy, fdz, -)
     __shared__ uint2 s_stack[SS * 128];
     const SharedStack sstack = {s_stack + threadIdx.x};
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int wid = threadIdx.x >> 5;
-    uint32_t* filtA = s_filt[0][wid];
-    uint32_t* filtB = s_filt[1][wid];
-    uint2* tgsA = s_tg[0][wid];
-    uint2* tgsB = s_tg[1][wid];
+    uint32_t* filt = &s_filt[0][wid][0];      // group q at filt + q * 128
+    uint2* tgs = &s_tg[0][wid][0];            // group q at tgs + q * 128
     float4* cullA = s_cull[0][wid];
     float4* cullB = s_cull[1][wid];
     if (n_dev) n = (int64_t)__ldg(n_dev);
@@ -501,25 +500,20 @@ __global__ void __launch_bounds__(128, MINB) traceCoopPairKernel(SceneParams sp,
             if (exhausted) break;
             continue;
         }
-        uint32_t mA = 0u, mB = 0u;
-        {
-            U2 tgA, tgB; tgA.x = tgA.y = tgB.x = tgB.y = 0u;
-            if (active) {
+        int cnt = 0;
+#pragma unroll
+        for (int q = 0; q < K; q++) {
+            U2 tg; tg.x = 0u; tg.y = 0u;
+            if (active && !tr.finished) {
                 U2 g;
-                tgA = tr.visitPhase(sp, r, &g, COUNT ? &c : nullptr);
+                tg = tr.visitPhase(sp, r, &g, COUNT ? &c : nullptr);
                 tr.selectPhaseOn(r, g, sstack);
-                if (!tr.finished) {
-                    tgB = tr.visitPhase(sp, r, &g, COUNT ? &c : nullptr);
-                    tr.selectPhaseOn(r, g, sstack);
-                }
-                reinterpret_cast<float*>(&cullA[lane])[3] = r.ctmax;
             }
-            tgsA[lane] = make_uint2(tgA.x, tgA.y);
-            tgsB[lane] = make_uint2(tgB.x, tgB.y);
-            mA = tgA.y; mB = tgB.y;
+            tgs[q * 128 + lane] = make_uint2(tg.x, tg.y);
+            cnt += __popc(tg.y);
         }
-        if (__any_sync(full, (mA | mB) != 0u)) {
-            const int cnt = __popc(mA) + __popc(mB);
+        if (active) reinterpret_cast<float*>(&cullA[lane])[3] = r.ctmax;
+        if (__any_sync(full, cnt != 0)) {
             if (COUNT) c.tris += (unsigned long long)cnt;
             int incl = cnt;
 #pragma unroll
@@ -528,7 +522,8 @@ __global__ void __launch_bounds__(128, MINB) traceCoopPairKernel(SceneParams sp,
                 if (lane >= d) incl += v;
             }
             const int total = __shfl_sync(full, incl, 31);
-            filtA[lane] = 0u; filtB[lane] = 0u;
+#pragma unroll
+            for (int q = 0; q < K; q++) filt[q * 128 + lane] = 0u;
             __syncwarp();
             for (int base = 0; base < total; base += 32) {
                 const int j = base + lane;
@@ -539,34 +534,49 @@ __global__ void __launch_bounds__(128, MINB) traceCoopPairKernel(SceneParams sp,
                     if (v <= j) L += s;
                 }
                 const int inclL = __shfl_sync(full, incl, L);
+                const int cntL = __shfl_sync(full, cnt, L);
                 if (j < total) {
-                    const uint2 a = tgsA[L], b = tgsB[L];
-                    const int nA = __popc(a.y);
-                    int k = j - (inclL - nA - __popc(b.y));
-                    const bool second = k >= nA;
-                    if (second) k -= nA;
-                    uint32_t m = second ? b.y : a.y;
+                    int k = j - (inclL - cntL);            // index among L's candidates, groups in visit order
+                    uint2 g = tgs[L];
+                    int which = 0;
+#pragma unroll
+                    for (int q = 1; q < K; q++) {
+                        const int nq = __popc(g.y);
+                        if (which == q - 1 && k >= nq) { k -= nq; which = q; g = tgs[q * 128 + L]; }
+                    }
+                    uint32_t m = g.y;
                     for (; k > 0; k--) m &= m - 1u;
                     const int bit = __ffs((int)m) - 1;
                     const float4 c0 = cullA[L], c1 = cullB[L];
                     const CullRay cr = {c0.x, c0.y, c0.z, c1.x, c1.y, c1.z, c0.w};
-                    const TriF32* tp = (const TriF32*)sp.tris + ((second ? b.x : a.x) + (uint32_t)bit);
+                    const TriF32* tp = (const TriF32*)sp.tris + (g.x + (uint32_t)bit);
                     const U4 ta = ldg4(&tp->v0[0]), tb = ldg4(&tp->v1[0]), tc = ldg4(&tp->v2[0]);
-                    if (triPretestMayHit(cr, sp.max_coord, ta, tb, tc)) atomicOr(second ? &filtB[L] : &filtA[L], 1u << bit);
+                    if (triPretestMayHit(cr, sp.max_coord, ta, tb, tc)) atomicOr(&filt[which * 128 + L], 1u << bit);
                 }
             }
             __syncwarp();
-            // the exact tests of both groups in ONE loop: the lanes with a survivor in either group go
-            // through the double-precision code together (it is the most divergent part of the kernel)
-            uint32_t sA = filtA[lane], sB = filtB[lane];
-            if (sA | sB) {
-                const uint32_t bA = tgsA[lane].x, bB = tgsB[lane].x;
+            // the exact tests of all groups in ONE loop: the lanes with a survivor in any group go through
+            // the double-precision code together (it is the most divergent part of the kernel)
+            uint32_t sv[K];
+            uint32_t any = 0u;
+#pragma unroll
+            for (int q = 0; q < K; q++) { sv[q] = filt[q * 128 + lane]; any |= sv[q]; }
+            if (any) {
                 do {
-                    uint32_t index;
-                    if (sA) { index = bA + (uint32_t)(__ffs((int)sA) - 1); sA &= sA - 1u; }
-                    else { index = bB + (uint32_t)(__ffs((int)sB) - 1); sB &= sB - 1u; }
+                    uint32_t index = 0u;
+                    bool taken = false;
+#pragma unroll
+                    for (int q = 0; q < K; q++) {
+                        if (!taken && sv[q]) {
+                            index = tgs[q * 128 + lane].x + (uint32_t)(__ffs((int)sv[q]) - 1);
+                            sv[q] &= sv[q] - 1u; taken = true;
+                        }
+                    }
                     tr.acceptExact(sp, r, index, COUNT ? &c : nullptr);
-                } while ((sA | sB) && !(ANY && r.best_prim >= 0));
+                    any = 0u;
+#pragma unroll
+                    for (int q = 0; q < K; q++) any |= sv[q];
+                } while (any && !(ANY && r.best_prim >= 0));
             }
         }
         if (active && tr.finished) { out.store(mine, r); active = false; }
@@ -599,9 +609,9 @@ static int launchTraceTyped(spb_ctx* ctx, const RayT* d_rays, int64_t n, const u
                 if (ctx->sp.max_depth <= 14) { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 8, 0, false, 7, 16>; coop = 11; }
                 else { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 8, 0, false, 7, 0>; coop = 2; }
             }
-            // 5: two node visits per pooled triangle phase, 6 CTAs per SM (80 registers); same fallbacks as 4
+            // 5: three node visits per pooled triangle phase, 6 CTAs per SM (80 registers); same fallbacks as 4
             if (v == 5) {
-                if (ctx->sp.max_depth <= 14) { kern = traceCoopPairKernel<ANY, COUNT, RayT, Out, 8, 6, 16>; coop = 15; }
+                if (ctx->sp.max_depth <= 14) { kern = traceCoopPairKernel<ANY, COUNT, RayT, Out, 8, 6, 16, 3>; coop = 15; }
                 else { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 8, 0, false, 7, 0>; coop = 2; }
             }
 #ifdef SPB_EXPERIMENTAL_VARIANTS      // measurement variants (trace.cu only; profiles/r01g_kernel_experiments.md)
@@ -613,10 +623,10 @@ static int launchTraceTyped(spb_ctx* ctx, const RayT* d_rays, int64_t n, const u
             if (v == 15 && ctx->sp.max_depth <= 14) { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 4, 0, false, 7, 16>; coop = 8; }
             if (v == 16 && ctx->sp.max_depth <= 14) { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 6, 0, false, 7, 16>; coop = 9; }
             if (v == 17 && ctx->sp.max_depth <= 14) { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 12, 0, false, 7, 16>; coop = 10; }
-            if (v == 25 && ctx->sp.max_depth <= 14) { kern = traceCoopPairKernel<ANY, COUNT, RayT, Out, 8, 5, 16>; coop = 16; }
-            if (v == 21 && ctx->sp.max_depth <= 14) { kern = traceCoopPairKernel<ANY, COUNT, RayT, Out, 8, 7, 16>; coop = 19; }
-            if (v == 22 && ctx->sp.max_depth <= 14) { kern = traceCoopPairKernel<ANY, COUNT, RayT, Out, 8, 8, 16>; coop = 17; }
-            if (v == 23 && ctx->sp.max_depth <= 14) { kern = traceCoopPairKernel<ANY, COUNT, RayT, Out, 12, 6, 16>; coop = 18; }
+            if (v == 25 && ctx->sp.max_depth <= 14) { kern = traceCoopPairKernel<ANY, COUNT, RayT, Out, 8, 5, 16, 3>; coop = 16; }
+            if (v == 21 && ctx->sp.max_depth <= 14) { kern = traceCoopPairKernel<ANY, COUNT, RayT, Out, 8, 7, 16, 3>; coop = 19; }
+            if (v == 22 && ctx->sp.max_depth <= 14) { kern = traceCoopPairKernel<ANY, COUNT, RayT, Out, 8, 6, 16, 2>; coop = 17; }
+            if (v == 23 && ctx->sp.max_depth <= 14) { kern = traceCoopPairKernel<ANY, COUNT, RayT, Out, 8, 6, 16, 4>; coop = 18; }
             if (v == 18 && ctx->sp.max_depth <= 10) { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 8, 0, false, 7, 12>; coop = 12; }
             if (v == 19 && ctx->sp.max_depth <= 14) { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 8, 0, false, 8, 16>; coop = 13; }
             if (v == 20 && ctx->sp.max_depth <= 14) { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 8, 0, false, 6, 16>; coop = 14; }

@@ -75,7 +75,7 @@ void uploadGeometry(spb_ctx* ctx, const FlatScene& f) {
                                        f.material_id.data(), f.light_id.data(), n), "spb_scene_set_triangles");
     spb_build_opts opts; std::memset(&opts, 0, sizeof(opts));
     if (const char* b = getenv("SPICA_BVH_BUILDER")) opts.builder = atoi(b);    // 0 host binned SAH (default), 1 GPU LBVH
-    if (const char* b = getenv("SPICA_BVH_MAX_LEAF")) opts.max_leaf_tris = atoi(b);   // 1..3 triangles per leaf (default 1)
+    if (const char* b = getenv("SPICA_BVH_MAX_LEAF")) opts.max_leaf_tris = atoi(b);   // 1..3 triangles per leaf (default 3)
     check(ctx, spb_bvh_build(ctx, &opts), "spb_bvh_build");
 }
 }  // namespace

@@ -74,9 +74,9 @@ void emul_trace(Emul* e, const void* rays, int f64, int64_t n, int any, int32_t*
                 const bool valid = rayBegin(e->sp, o[0], o[1], o[2], d[0], d[1], d[2], tmax, r);
                 if (mode == 2 && e->sp.tri_format == 0) {   // early select + deferred exact test (kernel variant 6)
                     if (any) traceRayDeferred<true>(e->sp, r, valid, &ctrs[th]); else traceRayDeferred<false>(e->sp, r, valid, &ctrs[th]);
-                } else if (mode == 3) {   // two node visits per triangle phase (kernel variant 5)
-                    if (e->sp.tri_format == 0) { if (any) traceRayTwoVisits<0, true>(e->sp, r, valid, &ctrs[th]); else traceRayTwoVisits<0, false>(e->sp, r, valid, &ctrs[th]); }
-                    else { if (any) traceRayTwoVisits<1, true>(e->sp, r, valid, &ctrs[th]); else traceRayTwoVisits<1, false>(e->sp, r, valid, &ctrs[th]); }
+                } else if (mode == 3) {   // three node visits per triangle phase (kernel variant 5)
+                    if (e->sp.tri_format == 0) { if (any) traceRayKVisits<0, true, 3>(e->sp, r, valid, &ctrs[th]); else traceRayKVisits<0, false, 3>(e->sp, r, valid, &ctrs[th]); }
+                    else { if (any) traceRayKVisits<1, true, 3>(e->sp, r, valid, &ctrs[th]); else traceRayKVisits<1, false, 3>(e->sp, r, valid, &ctrs[th]); }
                 } else if (mode == 1) {   // early-select phase order (kernel variants 3, 4)
                     if (e->sp.tri_format == 0) { if (any) traceRayEarlySelect<0, true>(e->sp, r, valid, &ctrs[th]); else traceRayEarlySelect<0, false>(e->sp, r, valid, &ctrs[th]); }
                     else { if (any) traceRayEarlySelect<1, true>(e->sp, r, valid, &ctrs[th]); else traceRayEarlySelect<1, false>(e->sp, r, valid, &ctrs[th]); }

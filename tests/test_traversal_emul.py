@@ -229,3 +229,21 @@ def test_deferred_exact_test_on_duplicates_and_shared_edges():
         q0 = e.trace(rays, mode=0); q2 = e.trace(rays, mode=2)
         assert all(np.array_equal(a, b) for a, b in zip(q0, q2))
         assert np.array_equal(e.trace(rays, any_hit=True, mode=0)[0] >= 0, e.trace(rays, any_hit=True, mode=2)[0] >= 0)
+
+
+@pytest.mark.parametrize("max_leaf", [1, 3])
+def test_three_visits_per_triangle_phase_give_identical_hits(max_leaf):
+    """Kernel variant 5 (default) visits three nodes before it tests their triangles
+    (traceRayKVisits): same (prim, t, u, v) and any-hit flags, a few % more visits."""
+    v, f = scenes.torus_mesh(200, 100)
+    tris = scenes.mesh_triangles(v, f)
+    rays = np.concatenate([scenes.incoherent_rays(30000, v.min(0), v.max(0), seed=8),
+                           scenes.primary_rays(64, 64)], 0)
+    anyr = scenes.incoherent_rays(30000, v.min(0), v.max(0), seed=8, anyhit=True)
+    e = Emul(tris, max_leaf=max_leaf)
+    q0 = e.trace(rays, mode=0); n0 = e.node_visits
+    q3 = e.trace(rays, mode=3)
+    assert all(np.array_equal(a, b) for a, b in zip(q0, q3))
+    assert e.node_visits <= 1.05 * n0
+    for rr in (rays, anyr):
+        assert np.array_equal(e.trace(rr, any_hit=True, mode=0)[0] >= 0, e.trace(rr, any_hit=True, mode=3)[0] >= 0)

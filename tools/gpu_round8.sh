@@ -11,7 +11,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --render-spp 2 > gpurun_out/ncu_bench.log 2>&1
 tail -2 gpurun_out/ncu_bench.log
 echo "== ncu full capture of the closest-hit kernel at the bench's ray count"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:traceCoop -s 2 -c 1 -f -o gpurun_out/prof_v5_16M \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:traceCoop -s 2 -c 1 -f -o gpurun_out/prof_v5k3_16M \
     python tools/sweep2.py 16777216 5 > gpurun_out/ncu_full.log 2>&1
 tail -2 gpurun_out/ncu_full.log
 ls -la gpurun_out
