@@ -234,8 +234,11 @@ __device__ __forceinline__ V3 evalTexture(const DeviceScene& sc, int id, float u
            (1.f - ds) * dt * texTexel(sc.texels, t, si, ti + 1) + ds * dt * texTexel(sc.texels, t, si + 1, ti + 1);
 }
 
-template <bool SORT>
-__global__ void __launch_bounds__(128, SORT ? 4 : 3) shadeKernel(RenderParamsPOD rp, DeviceScene sc, PathSoA paths, Queues q, int cur) {
+// MINB: resident CTAs per SM the kernel is compiled for.  4 (128 registers, 300 B of spills) beats 3 (167
+// registers, no spills) by 4 % on the diffuse Cornell box and ties on the glossy one; 5 and 6 lose 4-11 %
+// (tools/sweep_shade.py on a measurement build).
+template <bool SORT, int MINB = 4>
+__global__ void __launch_bounds__(128, MINB) shadeKernel(RenderParamsPOD rp, DeviceScene sc, PathSoA paths, Queues q, int cur) {
     const uint32_t n = q.count[cur];
     const spb_ray_f32* rays = q.ray[cur];
     spb_ray_f32* nextQ = q.ray[cur ^ 1];
@@ -997,6 +1000,22 @@ int spb_render_samples(spb_ctx* ctx, int32_t first, int32_t count, int32_t strid
         for (int bounce = 0; bounce <= R->rp.max_depth; bounce++) {
             // extend
             if ((rc = launchTrace<false>(ctx, R->q.ray[cur], n, R->q.count + cur, HitOut{R->q.hit}, R->d_cursor, st))) return rc;
+#ifdef SPB_EXPERIMENTAL_VARIANTS
+            if (ctx->opt_shade_minb > 0) {
+                const int mb = ctx->opt_shade_minb;
+                if (R->sort_materials) {
+                    if (mb == 3) shadeKernel<true, 3><<<shadeGrid, 128, 0, st>>>(R->rp, R->ds, R->paths, R->q, cur);
+                    else if (mb == 5) shadeKernel<true, 5><<<shadeGrid, 128, 0, st>>>(R->rp, R->ds, R->paths, R->q, cur);
+                    else if (mb == 6) shadeKernel<true, 6><<<shadeGrid, 128, 0, st>>>(R->rp, R->ds, R->paths, R->q, cur);
+                    else shadeKernel<true, 4><<<shadeGrid, 128, 0, st>>>(R->rp, R->ds, R->paths, R->q, cur);
+                } else {
+                    if (mb == 4) shadeKernel<false, 4><<<shadeGrid, 128, 0, st>>>(R->rp, R->ds, R->paths, R->q, cur);
+                    else if (mb == 5) shadeKernel<false, 5><<<shadeGrid, 128, 0, st>>>(R->rp, R->ds, R->paths, R->q, cur);
+                    else if (mb == 6) shadeKernel<false, 6><<<shadeGrid, 128, 0, st>>>(R->rp, R->ds, R->paths, R->q, cur);
+                    else shadeKernel<false, 3><<<shadeGrid, 128, 0, st>>>(R->rp, R->ds, R->paths, R->q, cur);
+                }
+            } else
+#endif
             if (R->sort_materials) shadeKernel<true><<<shadeGrid, 128, 0, st>>>(R->rp, R->ds, R->paths, R->q, cur);
             else shadeKernel<false><<<shadeGrid, 128, 0, st>>>(R->rp, R->ds, R->paths, R->q, cur);
             // connect + MIS (skipped by their own zero counts when empty)

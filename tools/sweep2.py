@@ -17,7 +17,7 @@ rays = scenes.incoherent_rays(n, v.min(0), v.max(0), seed=2)
 pri = scenes.primary_rays(4096, 4096)[:n]
 ctx = capi.Context(0)
 ctx.set_triangles(tris)
-ctx.build(max_leaf_tris=1)
+ctx.build()
 d_rays = ctx.dev_alloc(n * 32); d_pri = ctx.dev_alloc(len(pri) * 32); d_hits = ctx.dev_alloc(n * 16)
 ctx.dev_upload(d_rays, rays); ctx.dev_upload(d_pri, pri)
 ref = None
