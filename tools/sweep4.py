@@ -22,7 +22,7 @@ anyr = scenes.incoherent_rays(n, lo, hi, seed=2, anyhit=True)
 pri = scenes.primary_rays(4096, 4096)[:n]
 ctx = capi.Context(0)
 ctx.set_triangles(tris)
-ctx.build(max_leaf_tris=int(os.environ.get("SPB_MAX_LEAF", "1")))
+ctx.build(max_leaf_tris=int(os.environ.get("SPB_MAX_LEAF", "0")))
 d_rays = ctx.dev_alloc(n * 32); d_any = ctx.dev_alloc(n * 32); d_pri = ctx.dev_alloc(len(pri) * 32)
 d_hits = ctx.dev_alloc(n * 16); d_occ = ctx.dev_alloc(n)
 ctx.dev_upload(d_rays, rays); ctx.dev_upload(d_pri, pri); ctx.dev_upload(d_any, anyr)
