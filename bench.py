@@ -196,6 +196,31 @@ def reference_arm(args):
     print(json.dumps(line))
 
 
+def bind_to_gpu_numa(local):
+    """Multi-GPU runs: keep this rank (and so the first touch of its pinned host buffers) on the CPU socket its GPU
+    hangs off, when the process is allowed to run there.  Returns a short note for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.split(":", 1)
+        node = int(open("/sys/bus/pci/devices/%04x:%s/numa_node" % (int(dom, 16), rest.lower())).read())
+        if node < 0:
+            return "numa node unknown"
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return "gpu on numa node %d, none of its cpus in this process's cpuset" % node
+        os.sched_setaffinity(0, allowed)
+        return "bound to numa node %d (%d cpus)" % (node, len(allowed))
+    except Exception as e:      # noqa: BLE001
+        return "not bound (%s)" % type(e).__name__
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -221,6 +246,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    numa_note = bind_to_gpu_numa(local) if world > 1 else "single process, not bound"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -396,7 +422,8 @@ def main():
             "config": {"workload": "raycast 1M-triangle torus, 16,777,216 incoherent rays/GPU/step, closest-hit",
                        "triangles": len(tris), "rays_per_step_per_gpu": n, "bvh": "8-wide compressed, %d nodes, %d B nodes + %d B triangles" % (st["n_wide_nodes"], st["node_bytes"], st["tri_bytes"]),
                        "l2": "streamed inputs+outputs (%d MB/step) exceed the 126 MB L2; the BVH is meant to stay resident" % ((n * 48) >> 20),
-                       "parallelism": "rays sharded over %d GPU(s), scene replicated, no collective" % world},
+                       "parallelism": "rays sharded over %d GPU(s), scene replicated, no collective" % world,
+                       "host_numa": "rank 0: " + numa_note},
             "e2e": {"value": e2e_val, "unit": "Mrays/s", "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": n * 16},
             "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roof, "cpu_baseline": cpu,
             "parity": parity, "extra": extra, "bvh_build_s": st["build_seconds"]}

@@ -271,8 +271,14 @@ typedef struct spb_counters {
 int spb_get_counters(spb_ctx* ctx, spb_counters* out);
 
 /* Tunables: "counters" (0/1), "trace_block" (threads per CTA), "trace_ctas_per_sm",
- * "trace_variant" (kernel variant id), "chunk_rays" (rays per pipelined chunk of the host-buffer
- * calls), "wave_slots" (paths in flight per integrator wave). Unknown names return SPB_ERR_INVALID. */
+ * "trace_variant" (traversal kernel: 0 one thread per ray, 1 persistent CTAs with dynamic refill,
+ * 2 = 1 + warp-pooled float32 pre-test, 3 = 2 in visit / select / triangles order, 4 = 3 with the
+ * stack in shared memory, 5 = 4 with three node visits per pooled triangle phase (default); every
+ * variant returns the same records), "chunk_rays" (rays per pipelined chunk of the host-buffer calls,
+ * default 524288), "wave_slots" (paths in flight per integrator wave). Unknown names return
+ * SPB_ERR_INVALID.
+ * Environment read by spb_bvh_build / spb_bvh_import_binary: SPICA_BVH_COLLAPSE=0 selects the greedy
+ * 8-wide collapse instead of the cost-optimal one. */
 int spb_set_option(spb_ctx* ctx, const char* name, int64_t value);
 
 /* raw device memory helpers so that a host without the CUDA runtime (a plugin, ctypes) can keep

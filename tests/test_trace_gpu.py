@@ -38,9 +38,14 @@ def _check_closest(ctx, tris, rays, prim_ref, t_ref, max_ties=0):
     return hits
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
+DEFAULT_VARIANT = 5     # spica_b200/csrc/context.h: opt_variant
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
 @pytest.mark.parametrize("max_leaf", [1, 3])
 def test_golden_torus(gpu_ctx, golden_torus, variant, max_leaf):
+    """Every kernel variant against the compiled reference's answers: 0 one thread per ray, 1 persistent,
+    2 pooled pre-test, 3 early select, 4 shared-memory stack, 5 three visits per pooled phase (default)."""
     g = golden_torus
     gpu_ctx.set_option("trace_variant", variant)
     gpu_ctx.set_triangles(g["tris"])
@@ -50,7 +55,7 @@ def test_golden_torus(gpu_ctx, golden_torus, variant, max_leaf):
     h64 = gpu_ctx.trace_closest(g["rays64"])
     assert np.array_equal(h64["prim"], g["prim64"]) and np.array_equal(h64["t"], g["t64"])
     assert np.array_equal(gpu_ctx.trace_any(_as64(g["any_rays"])), g["occluded"])
-    gpu_ctx.set_option("trace_variant", 2)
+    gpu_ctx.set_option("trace_variant", DEFAULT_VARIANT)
 
 
 def test_golden_cube_own_and_imported_tree(gpu_ctx, golden_cube):
@@ -206,3 +211,36 @@ def test_gpu_lbvh_builder_gives_identical_hits(gpu_ctx, golden_torus, golden_cub
     _check_closest(gpu_ctx, tris, rays, p0, t0, max_ties=4)
     st = gpu_ctx.stats()
     assert st["n_binary_nodes"] == 2 * len(tris) - 1 and st["n_tris"] == len(tris)
+
+
+def test_deep_imported_tree_falls_back_to_the_local_stack(gpu_ctx):
+    """A chain-shaped imported tree is deeper than the shared-memory stack of variants 4 and 5: the launch
+    falls back to variant 3 and the answers are still the reference's."""
+    from tests.test_traversal_emul import chain_tree
+    v, f = scenes.torus_mesh(10, 7)
+    tris = scenes.mesh_triangles(v, f)
+    nodes = chain_tree(tris)
+    rays = scenes.incoherent_rays(20000, v.min(0), v.max(0), seed=3)
+    p0, t0, _, _ = ob.trace_closest(nodes, tris, rays)
+    gpu_ctx.set_triangles(tris)
+    gpu_ctx.import_binary(nodes.view(capi.IMPORT_NODE))
+    assert gpu_ctx.stats()["max_depth"] > 14
+    for variant in (2, 3, 4, 5):
+        gpu_ctx.set_option("trace_variant", variant)
+        _check_closest(gpu_ctx, tris, rays, p0, t0, max_ties=0)
+        assert np.array_equal(gpu_ctx.trace_any(rays), ob.trace_any(nodes, tris, rays))
+    gpu_ctx.set_option("trace_variant", DEFAULT_VARIANT)
+
+
+def test_greedy_and_cost_optimal_collapse_agree(gpu_ctx, monkeypatch):
+    v, f = scenes.torus_mesh(160, 80)
+    tris = scenes.mesh_triangles(v, f)
+    rays = scenes.incoherent_rays(100000, v.min(0), v.max(0), seed=9)
+    gpu_ctx.set_triangles(tris)
+    res = {}
+    for col in ("1", "0"):
+        monkeypatch.setenv("SPICA_BVH_COLLAPSE", col)
+        gpu_ctx.build()
+        res[col] = (gpu_ctx.trace_closest(rays), gpu_ctx.stats()["n_wide_nodes"])
+    assert np.array_equal(res["1"][0], res["0"][0])
+    assert res["1"][1] < res["0"][1]

@@ -247,3 +247,62 @@ def test_three_visits_per_triangle_phase_give_identical_hits(max_leaf):
     assert e.node_visits <= 1.05 * n0
     for rr in (rays, anyr):
         assert np.array_equal(e.trace(rr, any_hit=True, mode=0)[0] >= 0, e.trace(rr, any_hit=True, mode=3)[0] >= 0)
+
+
+def chain_tree(tris):
+    """A deliberately bad imported topology: every inner node holds one triangle on the left and the rest on
+    the right.  Its 8-wide collapse is about n/7 levels deep: deeper than the 16-entry shared-memory stack of
+    kernel variants 4 and 5, which must then fall back to variant 3 (40 entries in local memory)."""
+    tri = np.asarray(tris, dtype=np.float64).reshape(-1, 3, 3)
+    n = len(tri)
+    nodes = np.zeros(2 * n - 1, dtype=ob.NODE_DTYPE)
+    for i in range(n - 1):
+        nodes[i]["left"] = n - 1 + i
+        nodes[i]["right"] = i + 1 if i + 1 < n - 1 else 2 * n - 2
+        nodes[i]["prim"] = -1
+    for i in range(n):
+        k = n - 1 + i
+        nodes[k]["left"] = -1; nodes[k]["right"] = -1; nodes[k]["prim"] = i
+        nodes[k]["lo"] = tri[i].min(0); nodes[k]["hi"] = tri[i].max(0)
+    for i in range(n - 2, -1, -1):
+        l, r = nodes[i]["left"], nodes[i]["right"]
+        nodes[i]["lo"] = np.minimum(nodes[l]["lo"], nodes[r]["lo"]); nodes[i]["hi"] = np.maximum(nodes[l]["hi"], nodes[r]["hi"])
+    return nodes
+
+
+def test_deep_imported_tree():
+    v, f = scenes.torus_mesh(10, 7)
+    tris = scenes.mesh_triangles(v, f)
+    nodes = chain_tree(tris)
+    e = Emul(tris, import_nodes=nodes)
+    assert 14 < e.max_depth <= 38
+    rays = scenes.incoherent_rays(4000, v.min(0), v.max(0), seed=3)
+    p0, t0, _, _ = ob.trace_closest(nodes, tris, rays)
+    for mode in (0, 1, 3):
+        p, t, _, _ = e.trace(rays, mode=mode)
+        assert np.array_equal(p, p0) and np.array_equal(t[p0 >= 0], t0[p0 >= 0])
+    # a chain too deep for any traversal stack is refused, not mis-traversed
+    v2, f2 = scenes.torus_mesh(24, 12)
+    with pytest.raises(RuntimeError, match="deeper than the traversal stack"):
+        Emul(scenes.mesh_triangles(v2, f2), import_nodes=chain_tree(scenes.mesh_triangles(v2, f2)))
+
+
+def test_cost_optimal_collapse_against_greedy(monkeypatch):
+    """The dynamic-programme collapse (default) and the greedy one (SPICA_BVH_COLLAPSE=0) answer identically;
+    the optimal cut needs fewer wide nodes and fewer node visits."""
+    v, f = scenes.torus_mesh(160, 80)
+    tris = scenes.mesh_triangles(v, f)
+    rays = np.concatenate([scenes.incoherent_rays(20000, v.min(0), v.max(0), seed=9), scenes.primary_rays(48, 48)], 0)
+    out = {}
+    for col in ("1", "0"):
+        monkeypatch.setenv("SPICA_BVH_COLLAPSE", col)
+        for ml in (1, 3):
+            e = Emul(tris, max_leaf=ml)
+            q = e.trace(rays, mode=3)
+            out[(col, ml)] = (q, e.n_wide, e.node_visits)
+    ref = out[("0", 1)][0]
+    for k, (q, _, _) in out.items():
+        assert np.array_equal(q[0], ref[0]) and np.array_equal(q[1], ref[1]), k
+    for ml in (1, 3):
+        assert out[("1", ml)][1] < 0.85 * out[("0", ml)][1]          # wide nodes
+        assert out[("1", ml)][2] < out[("0", ml)][2] * 1.01          # node visits per ray
