@@ -12,12 +12,18 @@
 // The ray count may live in device memory (`n_dev`): the integrator's queues are filled by the
 // previous kernel and never round-trip through the host.
 //
-// Variant 1 (default) is a persistent-thread kernel: the grid is sized to the machine
-// (SMs x resident CTAs), every warp pulls rays from a global cursor with one warp-aggregated
-// atomic (ballot + popc + shuffle), and lanes whose ray has terminated are refilled while the
-// rest of the warp keeps traversing ("dynamic fetch"), so incoherent rays do not leave the warp
-// mostly idle while its longest ray finishes.  Variant 0 is the plain one-thread-per-ray kernel
-// kept as the measurement baseline.
+// Variants (spb_set_option "trace_variant"; every one returns the same records, tests/test_trace_gpu.py):
+//   0  one thread per ray: the measurement baseline.
+//   1  persistent threads: the grid is sized to the machine (SMs x resident CTAs), every warp pulls rays
+//      from a global cursor with one warp-aggregated atomic (ballot + popc + shuffle), and lanes whose ray
+//      has terminated are refilled while the rest of the warp keeps traversing ("dynamic fetch"), so
+//      incoherent rays do not leave the warp mostly idle while its longest ray finishes.
+//   2  1 + warp-pooled float32 triangle pre-test (traceCoopKernel); the fallback for float64 triangles.
+//   3  2 in visit -> select -> triangles order (traceCoopAheadKernel); the fallback for trees deeper
+//      than the shared-memory stack.
+//   4  3 with the traversal stack in shared memory.
+//   5  4 with three node visits per pooled triangle phase (traceCoopPairKernel): the default.
+//   10+ measurement variants, compiled with `make EXP=1` only (profiles/r01g_kernel_experiments.md).
 #pragma once
 #include <algorithm>
 
@@ -251,7 +257,7 @@ __global__ void __launch_bounds__(128, 7) traceCoopKernel(SceneParams sp, const 
 }
 
 
-// ---- variants 3, 4, 5: variant 2 in early-select order, with the next node fetched ahead ---------
+// ---- variants 3, 4 (and the measurement variants 10-17): variant 2 in early-select order ----------
 // Traverser::selectPhase picks the next node BEFORE the triangle phase, so its 80 bytes can be on
 // their way while the warp runs the pooled pre-test and the exact tests (ncu on variant 2: 31 % of
 // the stall samples sit on the node load and on the stack pop that feeds its address).
