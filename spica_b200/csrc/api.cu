@@ -230,6 +230,7 @@ int spb_set_option(spb_ctx* ctx, const char* name, int64_t value) {
         ctx->opt_block = (int)value;
     } else if (n == "trace_ctas_per_sm") ctx->opt_ctas_per_sm = (int)value;
     else if (n == "shade_minb") ctx->opt_shade_minb = (int)value;
+    else if (n == "shade_generic") ctx->opt_shade_generic = value ? 1 : 0;
     else if (n == "trace_variant") ctx->opt_variant = (int)value;
     else if (n == "wave_slots") { if (value < 1024) return fail(ctx, SPB_ERR_INVALID, "wave_slots too small"); ctx->opt_wave_slots = value; }
     else if (n == "chunk_rays") { if (value < 1024) return fail(ctx, SPB_ERR_INVALID, "chunk_rays too small"); ctx->opt_chunk = value; }

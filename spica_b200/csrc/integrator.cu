@@ -106,6 +106,7 @@ struct RenderState {
     int2* d_mat_tex = nullptr; spb_texture* d_texs = nullptr; float4* d_texels = nullptr; float* d_uvs = nullptr;
     bool scene_dirty = true;
     bool sort_materials = false;        // more than one BSDF type in the scene: shade in material order
+    uint32_t type_mask = 0x7fu;         // lobe types the scene's materials can produce: picks the shade kernel instance
     // envmap
     std::vector<float> env_rgb; int env_w = 0, env_h = 0; double env_l2w[16]; double env_scale = 1.0, env_center[3] = {0, 0, 0}, env_radius = 2.0;
     bool env_present = false, env_dirty = false;
@@ -237,7 +238,16 @@ __device__ __forceinline__ V3 evalTexture(const DeviceScene& sc, int id, float u
 // MINB: resident CTAs per SM the kernel is compiled for.  4 (128 registers, 300 B of spills) beats 3 (167
 // registers, no spills) by 4 % on the diffuse Cornell box and ties on the glossy one; 5 and 6 lose 4-11 %
 // (tools/sweep_shade.py on a measurement build).
-template <bool SORT, int MINB = 4>
+// TYPES: the lobe types (bit t = SPB_MAT_t) that can occur in the scene.  The kernel is instantiated for the sets
+// the BASELINE scenes need -- Lambertian only (C1, C3, C5's torus is rough dielectric: generic), the glossy Cornell
+// box's {diffuse, dielectric, rough conductor, conductor} -- and for all seven; every lobe outside the set is
+// compiled out (shading.cuh, lobeLive), which is what the registers of this kernel are spent on.
+constexpr int kShadeMinbDiffuse = 4;      // measured on the diffuse Cornell box: 4 -> 1729, 5 -> 1687, 6 -> 1625 Msamples/s (generic kernel: 1462)
+constexpr uint32_t kTypesAll = 0x7fu;
+constexpr uint32_t kTypesDiffuse = 1u << SPB_MAT_DIFFUSE;
+constexpr uint32_t kTypesGlossy = (1u << SPB_MAT_DIFFUSE) | (1u << SPB_MAT_DIELECTRIC) | (1u << SPB_MAT_ROUGHCONDUCTOR) | (1u << SPB_MAT_CONDUCTOR);
+
+template <bool SORT, int MINB = 4, uint32_t TYPES = kTypesAll>
 __global__ void __launch_bounds__(128, MINB) shadeKernel(RenderParamsPOD rp, DeviceScene sc, PathSoA paths, Queues q, int cur) {
     const uint32_t n = q.count[cur];
     const spb_ray_f32* rays = q.ray[cur];
@@ -360,7 +370,7 @@ __global__ void __launch_bounds__(128, MINB) shadeKernel(RenderParamsPOD rp, Dev
                             if (tx.y >= 0) { const V3 c = evalTexture(sc, tx.y, tu, tv); mat.kt[0] = c.x; mat.kt[1] = c.y; mat.kt[2] = c.z; }
                         }
                     }
-                    const Bsdf bsdf = makeBsdf(mat);
+                    const Bsdf bsdf = makeBsdf(mat, TYPES);
                     if (!hasMat || bsdf.type == SPB_MAT_NONE && false) {
                         // no material: pass through without counting a bounce (path.cc:71-75)
                         nO = offsetRayOrigin(sp.p, sp.ng, d); nD = d; pushNext = true;
@@ -710,6 +720,15 @@ static int uploadScene(spb_ctx* ctx, RenderState* R) {
     }
     R->sort_materials = false;
     for (const spb_material& m : R->mats) if (m.type != R->mats[0].type) R->sort_materials = true;
+    // every lobe type a material can turn into (makeBsdf: alpha 0 -> the specular lobe, a black coating -> Lambertian)
+    R->type_mask = 0u;
+    for (const spb_material& m : R->mats) {
+        if (m.type < 0 || m.type > 6) continue;
+        R->type_mask |= 1u << m.type;
+        if (m.type == SPB_MAT_ROUGHCONDUCTOR) R->type_mask |= 1u << SPB_MAT_CONDUCTOR;
+        if (m.type == SPB_MAT_ROUGHDIELECTRIC) R->type_mask |= 1u << SPB_MAT_DIELECTRIC;
+        if (m.type == SPB_MAT_ROUGHPLASTIC) R->type_mask |= 1u << SPB_MAT_DIFFUSE;
+    }
     R->scene_dirty = false;
     return SPB_OK;
 }
@@ -957,8 +976,9 @@ int spb_render_begin(spb_ctx* ctx, const spb_render_desc* desc) {
     {
         cudaFuncAttributes fa;
         cudaFuncGetAttributes(&fa, generateKernel);
-        cudaFuncGetAttributes(&fa, shadeKernel<true>);
-        cudaFuncGetAttributes(&fa, shadeKernel<false>);
+        if (!(R->type_mask & ~kTypesDiffuse)) cudaFuncGetAttributes(&fa, shadeKernel<false, kShadeMinbDiffuse, kTypesDiffuse>);
+        else if (!(R->type_mask & ~kTypesGlossy)) { cudaFuncGetAttributes(&fa, shadeKernel<true, 4, kTypesGlossy>); cudaFuncGetAttributes(&fa, shadeKernel<false, 4, kTypesGlossy>); }
+        else { cudaFuncGetAttributes(&fa, shadeKernel<true>); cudaFuncGetAttributes(&fa, shadeKernel<false>); }
         cudaFuncGetAttributes(&fa, bounceEndKernel);
         cudaFuncGetAttributes(&fa, filmKernel);
         if (ctx->sp.tri_format == 0) {
@@ -1016,7 +1036,16 @@ int spb_render_samples(spb_ctx* ctx, int32_t first, int32_t count, int32_t strid
                 }
             } else
 #endif
-            if (R->sort_materials) shadeKernel<true><<<shadeGrid, 128, 0, st>>>(R->rp, R->ds, R->paths, R->q, cur);
+            if (!(R->type_mask & ~kTypesDiffuse) && ctx->opt_shade_generic == 0) {
+                const int mb = ctx->opt_shade_minb > 0 ? ctx->opt_shade_minb : kShadeMinbDiffuse;
+                if (mb == 4) shadeKernel<false, 4, kTypesDiffuse><<<shadeGrid, 128, 0, st>>>(R->rp, R->ds, R->paths, R->q, cur);
+                else if (mb == 6) shadeKernel<false, 6, kTypesDiffuse><<<shadeGrid, 128, 0, st>>>(R->rp, R->ds, R->paths, R->q, cur);
+                else shadeKernel<false, 5, kTypesDiffuse><<<shadeGrid, 128, 0, st>>>(R->rp, R->ds, R->paths, R->q, cur);
+            }
+            else if (!(R->type_mask & ~kTypesGlossy) && ctx->opt_shade_generic == 0) {
+                if (R->sort_materials) shadeKernel<true, 4, kTypesGlossy><<<shadeGrid, 128, 0, st>>>(R->rp, R->ds, R->paths, R->q, cur);
+                else shadeKernel<false, 4, kTypesGlossy><<<shadeGrid, 128, 0, st>>>(R->rp, R->ds, R->paths, R->q, cur);
+            } else if (R->sort_materials) shadeKernel<true><<<shadeGrid, 128, 0, st>>>(R->rp, R->ds, R->paths, R->q, cur);
             else shadeKernel<false><<<shadeGrid, 128, 0, st>>>(R->rp, R->ds, R->paths, R->q, cur);
             // connect + MIS (skipped by their own zero counts when empty)
             if ((rc = launchTrace<true>(ctx, R->q.shadow, n, R->q.count + 2, SinkShadow{R->q.shadow, R->q.shadowC, R->paths}, R->d_cursor + 4, st))) return rc;

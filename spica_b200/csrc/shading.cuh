@@ -353,6 +353,9 @@ enum { kBxReflection = 1, kBxTransmission = 2, kBxDiffuse = 4, kBxGlossy = 8, kB
        kBxAll = 31, kBxNonSpecular = 15 };
 
 struct Bsdf {
+    uint32_t allowed;    // bit t set: lobe type t can occur in this scene.  The shade kernel is instantiated per
+                         // set of lobe types (integrator.cu, shadeKernel<.., TYPES>); with `allowed` a compile-time
+                         // constant every `lobeLive` test below folds and the code of the other lobes is never emitted.
     int type;            // SPB_MAT_*; SPB_MAT_NONE = no lobes
     int flags;           // BxDFType of the single lobe (core/bxdf.h)
     V3 kr, kt, eta, k;
@@ -362,8 +365,11 @@ struct Bsdf {
 
 // what the material plugins' setScatterFuncs build (bsdfs/diffuse.cc:23-32, dielectric.cc:30-42,
 // roughconductor.cc:38-75, roughdielectric.cc:41-83)
-SPB_SHD Bsdf makeBsdf(const spb_material& m) {
+SPB_SHD bool lobeLive(uint32_t allowed, int t) { return (allowed >> t) & 1u; }
+
+SPB_SHD Bsdf makeBsdf(const spb_material& m, uint32_t allowed = 0xffffffffu) {
     Bsdf b;
+    b.allowed = allowed;
     b.type = m.type; b.flags = 0;
     b.kr = v3(fmaxf(m.kr[0], 0.f), fmaxf(m.kr[1], 0.f), fmaxf(m.kr[2], 0.f));   // Spectrum::clamp
     b.kt = v3(fmaxf(m.kt[0], 0.f), fmaxf(m.kt[1], 0.f), fmaxf(m.kt[2], 0.f));
@@ -372,30 +378,30 @@ SPB_SHD Bsdf makeBsdf(const spb_material& m) {
     b.mf.ax = m.alpha_u; b.mf.ay = m.alpha_v; b.mf.ggx = m.distribution == SPB_DISTR_GGX;
     b.ior = m.eta[0];
     switch (m.type) {
-    case SPB_MAT_DIFFUSE:
+    case SPB_MAT_DIFFUSE: if (!lobeLive(allowed, SPB_MAT_DIFFUSE)) { b.type = SPB_MAT_NONE; break; }
         if (!isBlack(b.kr)) b.flags = kBxReflection | kBxDiffuse; else b.type = SPB_MAT_NONE;
         break;
-    case SPB_MAT_DIELECTRIC:
+    case SPB_MAT_DIELECTRIC: if (!lobeLive(allowed, SPB_MAT_DIELECTRIC)) { b.type = SPB_MAT_NONE; break; }
         if (isBlack(b.kr) && isBlack(b.kt)) b.type = SPB_MAT_NONE;
         else b.flags = kBxReflection | kBxTransmission | kBxSpecular;
         break;
-    case SPB_MAT_ROUGHCONDUCTOR:
+    case SPB_MAT_ROUGHCONDUCTOR: if (!lobeLive(allowed, SPB_MAT_ROUGHCONDUCTOR)) { b.type = SPB_MAT_NONE; break; }
         b.kr = v3(1.f);
         if (m.alpha_u == 0.f && m.alpha_v == 0.f) { b.type = SPB_MAT_CONDUCTOR; b.flags = kBxReflection | kBxSpecular; }
         else b.flags = kBxReflection | kBxGlossy;
         break;
-    case SPB_MAT_CONDUCTOR:
+    case SPB_MAT_CONDUCTOR: if (!lobeLive(allowed, SPB_MAT_CONDUCTOR)) { b.type = SPB_MAT_NONE; break; }
         b.flags = kBxReflection | kBxSpecular;
         break;
-    case SPB_MAT_ROUGHDIELECTRIC:
+    case SPB_MAT_ROUGHDIELECTRIC: if (!lobeLive(allowed, SPB_MAT_ROUGHDIELECTRIC)) { b.type = SPB_MAT_NONE; break; }
         if (isBlack(b.kr) && isBlack(b.kt)) b.type = SPB_MAT_NONE;
         else if (m.alpha_u == 0.f && m.alpha_v == 0.f) { b.type = SPB_MAT_DIELECTRIC; b.flags = kBxReflection | kBxTransmission | kBxSpecular; }
         else b.flags = kBxReflection | kBxTransmission | kBxGlossy;
         break;
-    case SPB_MAT_PLASTIC:                                                         // bsdfs/plastic.cc:22-33,118-128: kr = Ks, kt = Kd
+    case SPB_MAT_PLASTIC: if (!lobeLive(allowed, SPB_MAT_PLASTIC)) { b.type = SPB_MAT_NONE; break; }                                                         // bsdfs/plastic.cc:22-33,118-128: kr = Ks, kt = Kd
         b.flags = kBxReflection | kBxSpecular | kBxDiffuse;
         break;
-    case SPB_MAT_ROUGHPLASTIC: {                                                  // bsdfs/roughplastic.cc:22-33,130-165
+    case SPB_MAT_ROUGHPLASTIC: if (!lobeLive(allowed, SPB_MAT_ROUGHPLASTIC)) { b.type = SPB_MAT_NONE; break; } {                                                  // bsdfs/roughplastic.cc:22-33,130-165
         const float rough = fmaxf(0.001f, m.alpha_u);
         b.mf.ax = b.mf.ay = rough;
         if (isBlack(b.kr)) { b.type = SPB_MAT_DIFFUSE; b.kr = b.kt; b.flags = kBxReflection | kBxDiffuse; }   // LambertianReflection(kd), added even when kd is black
@@ -480,13 +486,13 @@ SPB_SHD V3 mfTransHalf(const Bsdf& b, V3 wo, V3 wi) {        // core/bxdf.cc:321
 // the lobe's f(wo, wi) in the local frame
 SPB_SHD V3 lobeF(const Bsdf& b, V3 wo, V3 wi) {
     switch (b.type) {
-    case SPB_MAT_DIFFUSE: return b.kr * kInvPi;                                   // core/bxdf.cc:56-58
-    case SPB_MAT_ROUGHCONDUCTOR: return mfReflF(b, wo, wi);
-    case SPB_MAT_ROUGHDIELECTRIC: return mfTransF(b, wo, wi, mfTransHalf(b, wo, wi));
-    case SPB_MAT_CONDUCTOR:                                                       // core/bxdf.cc:86-91
+    case SPB_MAT_DIFFUSE: if (!lobeLive(b.allowed, SPB_MAT_DIFFUSE)) break; return b.kr * kInvPi;                                   // core/bxdf.cc:56-58
+    case SPB_MAT_ROUGHCONDUCTOR: if (!lobeLive(b.allowed, SPB_MAT_ROUGHCONDUCTOR)) break; return mfReflF(b, wo, wi);
+    case SPB_MAT_ROUGHDIELECTRIC: if (!lobeLive(b.allowed, SPB_MAT_ROUGHDIELECTRIC)) break; return mfTransF(b, wo, wi, mfTransHalf(b, wo, wi));
+    case SPB_MAT_CONDUCTOR: if (!lobeLive(b.allowed, SPB_MAT_CONDUCTOR)) break;                                                       // core/bxdf.cc:86-91
         if (dot(v3(-wo.x, -wo.y, wo.z), wi) > 1.f - kDeltaEps) return b.kr / fabsf(wi.z);
         return v3(0.f);
-    case SPB_MAT_DIELECTRIC: {                                                    // core/bxdf.cc:170-191
+    case SPB_MAT_DIELECTRIC: if (!lobeLive(b.allowed, SPB_MAT_DIELECTRIC)) break; {                                                    // core/bxdf.cc:170-191
         const float F = frDielectric(wo.z, 1.f, b.ior);
         if (wo.z * wi.z > 0.f) {
             if (dot(v3(-wo.x, -wo.y, wo.z), wi) > 1.f - kDeltaEps) return b.kr * (F / fabsf(wi.z));
@@ -499,12 +505,12 @@ SPB_SHD V3 lobeF(const Bsdf& b, V3 wo, V3 wi) {
         }
         return v3(0.f);
     }
-    case SPB_MAT_PLASTIC: {                                                       // bsdfs/plastic.cc:32-46
+    case SPB_MAT_PLASTIC: if (!lobeLive(b.allowed, SPB_MAT_PLASTIC)) break; {                                                       // bsdfs/plastic.cc:32-46
         const float Fo = frDielectric(wo.z, 1.f, b.ior);
         if (plasticAlongNormal(wi)) return b.kr * (Fo / fabsf(wi.z));
         return plasticDiffuse(b, Fo, wi.z);
     }
-    case SPB_MAT_ROUGHPLASTIC: {                                                  // bsdfs/roughplastic.cc:35-47
+    case SPB_MAT_ROUGHPLASTIC: if (!lobeLive(b.allowed, SPB_MAT_ROUGHPLASTIC)) break; {                                                  // bsdfs/roughplastic.cc:35-47
         if (wo.z == 0.f || wi.z == 0.f) return v3(0.f);
         if (!(wo.z * wi.z > 0.f)) return v3(0.f);
         const V3 wh = normalize(wi + wo);
@@ -513,14 +519,15 @@ SPB_SHD V3 lobeF(const Bsdf& b, V3 wo, V3 wi) {
     }
     default: return v3(0.f);
     }
+    return v3(0.f);
 }
 SPB_SHD float lobePdf(const Bsdf& b, V3 wo, V3 wi) {
     switch (b.type) {
-    case SPB_MAT_DIFFUSE: return wo.z * wi.z > 0.f ? fabsf(wi.z) * kInvPi : 0.f;  // core/bxdf.cc:43-45
-    case SPB_MAT_ROUGHCONDUCTOR: return mfReflPdf(b, wo, wi);
-    case SPB_MAT_ROUGHDIELECTRIC: return mfTransPdf(b, wo, wi, mfTransHalf(b, wo, wi));
-    case SPB_MAT_CONDUCTOR: return dot(v3(-wo.x, -wo.y, wo.z), wi) > 1.f - kDeltaEps ? 1.f : 0.f;   // :103-108
-    case SPB_MAT_DIELECTRIC: {                                                    // core/bxdf.cc:228-248
+    case SPB_MAT_DIFFUSE: if (!lobeLive(b.allowed, SPB_MAT_DIFFUSE)) break; return wo.z * wi.z > 0.f ? fabsf(wi.z) * kInvPi : 0.f;  // core/bxdf.cc:43-45
+    case SPB_MAT_ROUGHCONDUCTOR: if (!lobeLive(b.allowed, SPB_MAT_ROUGHCONDUCTOR)) break; return mfReflPdf(b, wo, wi);
+    case SPB_MAT_ROUGHDIELECTRIC: if (!lobeLive(b.allowed, SPB_MAT_ROUGHDIELECTRIC)) break; return mfTransPdf(b, wo, wi, mfTransHalf(b, wo, wi));
+    case SPB_MAT_CONDUCTOR: if (!lobeLive(b.allowed, SPB_MAT_CONDUCTOR)) break; return dot(v3(-wo.x, -wo.y, wo.z), wi) > 1.f - kDeltaEps ? 1.f : 0.f;   // :103-108
+    case SPB_MAT_DIELECTRIC: if (!lobeLive(b.allowed, SPB_MAT_DIELECTRIC)) break; {                                                    // core/bxdf.cc:228-248
         const float F = frDielectric(wo.z, 1.f, b.ior);
         if (wo.z * wi.z > 0.f) {
             if (dot(v3(-wo.x, -wo.y, wo.z), wi) > 1.f - kDeltaEps) return F;
@@ -533,12 +540,12 @@ SPB_SHD float lobePdf(const Bsdf& b, V3 wo, V3 wi) {
         }
         return 0.f;
     }
-    case SPB_MAT_PLASTIC: {                                                       // bsdfs/plastic.cc:70-82
+    case SPB_MAT_PLASTIC: if (!lobeLive(b.allowed, SPB_MAT_PLASTIC)) break; {                                                       // bsdfs/plastic.cc:70-82
         const float ps = plasticProbSpecular(b, frDielectric(wo.z, 1.f, b.ior));
         if (plasticAlongNormal(wi)) return ps;
         return (1.f - ps) * fabsf(wi.z) * kInvPi;
     }
-    case SPB_MAT_ROUGHPLASTIC: {                                                  // bsdfs/roughplastic.cc:88-96
+    case SPB_MAT_ROUGHPLASTIC: if (!lobeLive(b.allowed, SPB_MAT_ROUGHPLASTIC)) break; {                                                  // bsdfs/roughplastic.cc:88-96
         if (!(wo.z * wi.z > 0.f)) return 0.f;
         const V3 wh = normalize(wi + wo);
         const float F = frDielectric(dot(wo, wh), 1.f, b.ior);
@@ -546,24 +553,25 @@ SPB_SHD float lobePdf(const Bsdf& b, V3 wo, V3 wi) {
     }
     default: return 0.f;
     }
+    return 0.f;
 }
 // the lobe's sample(); u2 replaces the hidden thread_local Random of MicrofacetTransmission::sample
 // (core/bxdf.cc:18,364). Returns f; *pdf = 0 means "no sample".
 SPB_SHD V3 lobeSample(const Bsdf& b, V3 wo, float u0, float u1, float u2, V3* wi, float* pdf, int* sampled) {
     *pdf = 0.f; *sampled = b.flags;
     switch (b.type) {
-    case SPB_MAT_DIFFUSE: {                                                       // core/bxdf.cc:35-41
+    case SPB_MAT_DIFFUSE: if (!lobeLive(b.allowed, SPB_MAT_DIFFUSE)) break; {                                                       // core/bxdf.cc:35-41
         *wi = cosineHemisphere(u0, u1);
         if (wo.z < 0.f) wi->z = -wi->z;
         *pdf = lobePdf(b, wo, *wi);
         return b.kr * kInvPi;
     }
-    case SPB_MAT_CONDUCTOR: {                                                     // core/bxdf.cc:93-101
+    case SPB_MAT_CONDUCTOR: if (!lobeLive(b.allowed, SPB_MAT_CONDUCTOR)) break; {                                                     // core/bxdf.cc:93-101
         *wi = v3(-wo.x, -wo.y, wo.z);
         *pdf = 1.f;
         return frConductor(fabsf(wi->z), b.eta, b.k) * b.kr / fabsf(wi->z);
     }
-    case SPB_MAT_DIELECTRIC: {                                                    // core/bxdf.cc:193-226
+    case SPB_MAT_DIELECTRIC: if (!lobeLive(b.allowed, SPB_MAT_DIELECTRIC)) break; {                                                    // core/bxdf.cc:193-226
         const float F = frDielectric(wo.z, 1.f, b.ior);
         if (u0 < F) {
             *wi = v3(-wo.x, -wo.y, wo.z);
@@ -580,7 +588,7 @@ SPB_SHD V3 lobeSample(const Bsdf& b, V3 wo, float u0, float u1, float u2, V3* wi
         *pdf = 1.f - F;
         return ft / fabsf(wi->z);
     }
-    case SPB_MAT_ROUGHCONDUCTOR: {                                                // core/bxdf.cc:284-295
+    case SPB_MAT_ROUGHCONDUCTOR: if (!lobeLive(b.allowed, SPB_MAT_ROUGHCONDUCTOR)) break; {                                                // core/bxdf.cc:284-295
         if (wo.z == 0.f) return v3(0.f);
         const V3 wh = mfSample(b.mf, wo, u0, u1);
         *wi = -wo + wh * (2.f * dot(wh, wo));                                      // vect::reflect
@@ -588,7 +596,7 @@ SPB_SHD V3 lobeSample(const Bsdf& b, V3 wo, float u0, float u1, float u2, V3* wi
         *pdf = mfPdf(b.mf, wo, wh) / (4.f * dot(wo, wh));
         return mfReflF(b, wo, *wi);
     }
-    case SPB_MAT_ROUGHDIELECTRIC: {                                               // core/bxdf.cc:361-393
+    case SPB_MAT_ROUGHDIELECTRIC: if (!lobeLive(b.allowed, SPB_MAT_ROUGHDIELECTRIC)) break; {                                               // core/bxdf.cc:361-393
         if (wo.z == 0.f) return v3(0.f);
         const V3 wh = mfSample(b.mf, wo, u0, u1);
         const float co = dot(wo, wh.z > 0.f ? wh : -wh);
@@ -607,7 +615,7 @@ SPB_SHD V3 lobeSample(const Bsdf& b, V3 wo, float u0, float u1, float u2, V3* wi
         *pdf = mfTransPdf(b, wo, *wi, whp);
         return mfTransF(b, wo, *wi, whp);
     }
-    case SPB_MAT_PLASTIC: {                                                       // bsdfs/plastic.cc:48-68 (u2: its thread_local Random)
+    case SPB_MAT_PLASTIC: if (!lobeLive(b.allowed, SPB_MAT_PLASTIC)) break; {                                                       // bsdfs/plastic.cc:48-68 (u2: its thread_local Random)
         const float Fo = frDielectric(wo.z, 1.f, b.ior);
         const float ps = plasticProbSpecular(b, Fo);
         if (u2 < ps) {
@@ -619,7 +627,7 @@ SPB_SHD V3 lobeSample(const Bsdf& b, V3 wo, float u0, float u1, float u2, V3* wi
         *pdf = (1.f - ps) * fabsf(wi->z) * kInvPi;
         return plasticDiffuse(b, Fo, wi->z);
     }
-    case SPB_MAT_ROUGHPLASTIC: {                                                  // bsdfs/roughplastic.cc:49-86
+    case SPB_MAT_ROUGHPLASTIC: if (!lobeLive(b.allowed, SPB_MAT_ROUGHPLASTIC)) break; {                                                  // bsdfs/roughplastic.cc:49-86
         if (wo.z == 0.f) return v3(0.f);
         const V3 wh = mfSample(b.mf, wo, u0, u1);
         const float Fo = frDielectric(dot(wo, wh), 1.f, b.ior);
@@ -636,6 +644,7 @@ SPB_SHD V3 lobeSample(const Bsdf& b, V3 wo, float u0, float u1, float u2, V3* wi
     }
     default: return v3(0.f);
     }
+    return v3(0.f);
 }
 
 SPB_SHD V3 toLocal(const SurfacePoint& s, V3 v) { return v3(dot(s.ss, v), dot(s.ts, v), dot(s.ns, v)); }       // core/bsdf.cc:38-43
