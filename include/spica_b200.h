@@ -275,8 +275,10 @@ int spb_get_counters(spb_ctx* ctx, spb_counters* out);
  * 2 = 1 + warp-pooled float32 pre-test, 3 = 2 in visit / select / triangles order, 4 = 3 with the
  * stack in shared memory, 5 = 4 with three node visits per pooled triangle phase (default); every
  * variant returns the same records), "chunk_rays" (rays per pipelined chunk of the host-buffer calls,
- * default 524288), "wave_slots" (paths in flight per integrator wave). Unknown names return
- * SPB_ERR_INVALID.
+ * default 524288), "wave_slots" (paths in flight per integrator wave), "shade_generic" (1 = always the
+ * all-lobes shade kernel instead of the instance for the scene's set of lobe types; same image),
+ * "shade_minb" (4/5/6: occupancy the Lambertian-only shade instance is compiled for). Unknown names
+ * return SPB_ERR_INVALID.
  * Environment read by spb_bvh_build / spb_bvh_import_binary: SPICA_BVH_COLLAPSE=0 selects the greedy
  * 8-wide collapse instead of the cost-optimal one. */
 int spb_set_option(spb_ctx* ctx, const char* name, int64_t value);

@@ -50,7 +50,7 @@ struct spb_ctx {
     int opt_block = 128;
     int opt_ctas_per_sm = 0;             // 0 = occupancy query
     int opt_shade_generic = 0;           // 1: always the all-lobes shade kernel (to compare with the scene-specialised instances)
-    int opt_shade_minb = 0;              // measurement builds only: resident shade CTAs per SM the kernel is compiled for (0 = default)
+    int opt_shade_minb = 0;              // Lambertian-only shade instance compiled for 4, 5 or 6 resident CTAs per SM (0 = default, 4)
     int opt_variant = 5;                 // 0 = one thread per ray, 1 = persistent dynamic fetch, 2 = 1 + warp-cooperative pre-test, 3 = 2 in early-select order,
                                          // 4 = 3 with the stack in shared memory, 5 = 4 with three node visits per pooled triangle phase (default;
                                          // falls back to 3 on trees deeper than the shared stack and to 2 on float64 triangles)

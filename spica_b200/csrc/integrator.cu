@@ -1020,22 +1020,6 @@ int spb_render_samples(spb_ctx* ctx, int32_t first, int32_t count, int32_t strid
         for (int bounce = 0; bounce <= R->rp.max_depth; bounce++) {
             // extend
             if ((rc = launchTrace<false>(ctx, R->q.ray[cur], n, R->q.count + cur, HitOut{R->q.hit}, R->d_cursor, st))) return rc;
-#ifdef SPB_EXPERIMENTAL_VARIANTS
-            if (ctx->opt_shade_minb > 0) {
-                const int mb = ctx->opt_shade_minb;
-                if (R->sort_materials) {
-                    if (mb == 3) shadeKernel<true, 3><<<shadeGrid, 128, 0, st>>>(R->rp, R->ds, R->paths, R->q, cur);
-                    else if (mb == 5) shadeKernel<true, 5><<<shadeGrid, 128, 0, st>>>(R->rp, R->ds, R->paths, R->q, cur);
-                    else if (mb == 6) shadeKernel<true, 6><<<shadeGrid, 128, 0, st>>>(R->rp, R->ds, R->paths, R->q, cur);
-                    else shadeKernel<true, 4><<<shadeGrid, 128, 0, st>>>(R->rp, R->ds, R->paths, R->q, cur);
-                } else {
-                    if (mb == 4) shadeKernel<false, 4><<<shadeGrid, 128, 0, st>>>(R->rp, R->ds, R->paths, R->q, cur);
-                    else if (mb == 5) shadeKernel<false, 5><<<shadeGrid, 128, 0, st>>>(R->rp, R->ds, R->paths, R->q, cur);
-                    else if (mb == 6) shadeKernel<false, 6><<<shadeGrid, 128, 0, st>>>(R->rp, R->ds, R->paths, R->q, cur);
-                    else shadeKernel<false, 3><<<shadeGrid, 128, 0, st>>>(R->rp, R->ds, R->paths, R->q, cur);
-                }
-            } else
-#endif
             if (!(R->type_mask & ~kTypesDiffuse) && ctx->opt_shade_generic == 0) {
                 const int mb = ctx->opt_shade_minb > 0 ? ctx->opt_shade_minb : kShadeMinbDiffuse;
                 if (mb == 4) shadeKernel<false, 4, kTypesDiffuse><<<shadeGrid, 128, 0, st>>>(R->rp, R->ds, R->paths, R->q, cur);
