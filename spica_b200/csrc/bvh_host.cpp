@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <future>
 #include <queue>
 #include <thread>
@@ -290,17 +291,7 @@ bool encode_wide(const BinaryBVH& bin, const double* verts, int64_t n_tris, int 
         if (const char* e = std::getenv("SPICA_BVH_CTRI")) cTri = (float)std::atof(e);
         const float cNode = 1.0f, inf = 3.0e38f;
         row.resize(bin.nodes.size());
-        // children before parents: iterative post-order
-        std::vector<int32_t> stackv; std::vector<int32_t> orderv;
-        stackv.push_back(bin.root); orderv.reserve(bin.nodes.size());
-        while (!stackv.empty()) {
-            const int32_t b = stackv.back(); stackv.pop_back();
-            orderv.push_back(b);
-            if (bin.nodes[b].left >= 0) stackv.push_back(bin.nodes[b].left);
-            if (bin.nodes[b].right >= 0) stackv.push_back(bin.nodes[b].right);
-        }
-        for (size_t oi = orderv.size(); oi-- > 0;) {
-            const int32_t b = orderv[oi];
+        auto computeRow = [&](int32_t b) {          // the rows of b's children are final
             const BinNode& n = bin.nodes[b];
             DpRow& R = row[b];
             const float A = (float)(nodeArea(b) / rootArea);
@@ -308,9 +299,9 @@ bool encode_wide(const BinaryBVH& bin, const double* verts, int64_t n_tris, int 
             if (n.left < 0 && n.right < 0) {
                 for (int i = 0; i < 8; i++) { R.c[i] = cLeaf; R.k[i] = 0; }
                 R.k8 = 0; R.leaf = 1;
-                continue;
+                return;
             }
-            if (n.left < 0 || n.right < 0) { R = row[n.left >= 0 ? n.left : n.right]; continue; }   // pass-through
+            if (n.left < 0 || n.right < 0) { R = row[n.left >= 0 ? n.left : n.right]; return; }   // pass-through
             const DpRow& L = row[n.left]; const DpRow& Rr = row[n.right];
             float D[9]; uint8_t Dk[9];
             for (int j = 2; j <= 8; j++) {
@@ -330,7 +321,32 @@ bool encode_wide(const BinaryBVH& bin, const double* verts, int64_t n_tris, int 
                 else { R.c[i - 1] = R.c[i - 2]; R.k[i - 1] = 0; }
             }
             R.c[7] = R.c[6]; R.k[7] = 0;
-        }
+        };
+        // children before parents: the reverse of a pre-order walk of the subtree
+        auto solveSerial = [&](int32_t root) {
+            std::vector<int32_t> stackv, orderv;
+            stackv.push_back(root);
+            while (!stackv.empty()) {
+                const int32_t b = stackv.back(); stackv.pop_back();
+                orderv.push_back(b);
+                if (bin.nodes[b].left >= 0) stackv.push_back(bin.nodes[b].left);
+                if (bin.nodes[b].right >= 0) stackv.push_back(bin.nodes[b].right);
+            }
+            for (size_t oi = orderv.size(); oi-- > 0;) computeRow(orderv[oi]);
+        };
+        // the big subtrees near the root on their own threads (rows of different subtrees never alias)
+        std::function<void(int32_t, int)> solve = [&](int32_t b, int depth) {
+            const BinNode& n = bin.nodes[b];
+            if (n.count > 65536 && depth < 5 && n.left >= 0 && n.right >= 0) {
+                auto fut = std::async(std::launch::async, [&solve, &n, depth]() { solve(n.left, depth + 1); });
+                solve(n.right, depth + 1);
+                fut.get();
+                computeRow(b);
+            } else {
+                solveSerial(b);
+            }
+        };
+        solve(bin.root, 0);
     }
     std::vector<uint8_t> dpLeaf;           // per binary node: chosen as a leaf child by the optimal cut
     if (dp) dpLeaf.assign(bin.nodes.size(), 0);
