@@ -35,26 +35,52 @@ inline Box triBox(const double* v) {
     return b;
 }
 
-struct PrimRef { Box b; double c[3]; };
+struct PrimRef { Box b; double c[3]; int32_t id; };   // kept physically in leaf order while the tree is built: every pass below is sequential
 
 struct SahBuilder {
-    const std::vector<PrimRef>& prims;
+    std::vector<PrimRef>& prims;           // partitioned in place (position i <-> order[i])
     std::vector<int32_t>& order;
     std::vector<BinNode>& nodes;
     std::atomic<int32_t> nextNode{0};
     int bins;
 
-    SahBuilder(const std::vector<PrimRef>& p, std::vector<int32_t>& o, std::vector<BinNode>& n, int b)
+    SahBuilder(std::vector<PrimRef>& p, std::vector<int32_t>& o, std::vector<BinNode>& n, int b)
         : prims(p), order(o), nodes(n), bins(b) {}
+
+    // The few nodes near the root hold most of the primitives while only one or two threads are busy with
+    // them: their bounds and bin passes run in slices on all cores (min / max / counts merge exactly, so the
+    // tree is the one the serial passes give).
+    static constexpr int32_t kSliceMin = 1 << 17;
+    int slicesFor(int32_t count, int depth) const {
+        if (count < 2 * kSliceMin || depth > 4) return 1;
+        const int hw = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        return std::max(1, std::min(hw >> depth, (int)(count / kSliceMin)));
+    }
+    template <class F>
+    static void forSlices(int slices, int32_t first, int32_t count, F&& fn) {      // fn(slice, first, count)
+        if (slices <= 1) { fn(0, first, count); return; }
+        std::vector<std::future<void>> futs;
+        for (int s = 1; s < slices; s++) {
+            const int32_t a = first + (int32_t)((int64_t)count * s / slices), b = first + (int32_t)((int64_t)count * (s + 1) / slices);
+            futs.push_back(std::async(std::launch::async, [&fn, s, a, b]() { fn(s, a, b - a); }));
+        }
+        fn(0, first, (int32_t)((int64_t)count / slices));
+        for (auto& f : futs) f.get();
+    }
 
     int32_t build(int32_t first, int32_t count, int depth) {
         const int32_t me = nextNode.fetch_add(1);
         Box bounds, cb;
         bounds.reset(); cb.reset();
-        for (int32_t i = first; i < first + count; i++) {
-            const PrimRef& p = prims[order[i]];
-            bounds.grow(p.b);
-            cb.grow(p.c);
+        const int slices = slicesFor(count, depth);
+        {
+            std::vector<Box> sb((size_t)slices), sc((size_t)slices);
+            forSlices(slices, first, count, [&](int sl, int32_t a, int32_t n) {
+                Box b1, c1; b1.reset(); c1.reset();
+                for (int32_t i = a; i < a + n; i++) { const PrimRef& p = prims[i]; b1.grow(p.b); c1.grow(p.c); }
+                sb[sl] = b1; sc[sl] = c1;
+            });
+            for (int sl = 0; sl < slices; sl++) { bounds.grow(sb[sl]); cb.grow(sc[sl]); }
         }
         BinNode nd;
         for (int k = 0; k < 3; k++) { nd.lo[k] = bounds.lo[k]; nd.hi[k] = bounds.hi[k]; }
@@ -65,19 +91,72 @@ struct SahBuilder {
         const int B = bins;
         double bestCost = DBL_MAX;
         int bestAxis = -1, bestSplit = -1;
-        std::vector<Box> bb(B), rightAcc(B);
-        std::vector<int32_t> cnt(B);
+        // per-thread scratch: the bins are dead before the recursion below starts, and a million small nodes
+        // would otherwise pay three heap allocations each
+        thread_local std::vector<Box> bb, rightAcc;
+        thread_local std::vector<int32_t> cnt;
+        if ((int)bb.size() < B) { bb.resize(B); rightAcc.resize(B); cnt.resize(B); }
         for (int axis = 0; axis < 3; axis++) {
             const double cmin = cb.lo[axis], cmax = cb.hi[axis];
             if (!(cmax > cmin)) continue;
             const double scale = B / (cmax - cmin);
+            if (count * 2 <= B) {
+                // Few primitives: only the occupied bins are built and swept (at most `count` of them, in
+                // ascending order).  The full sweep below gives every split position inside a run of empty
+                // bins the cost of the occupied bin before it and keeps the first strict minimum, i.e. that
+                // occupied bin: same cost, same split, same tree -- without touching 3 x B bins for each of
+                // the million nodes at the bottom of the tree.
+                int ob[128]; Box obox[128], racc[128]; int32_t ocnt[128]; int m = 0;
+                for (int32_t i = first; i < first + count; i++) {
+                    const PrimRef& p = prims[i];
+                    int b = (int)((p.c[axis] - cmin) * scale);
+                    b = b < 0 ? 0 : (b >= B ? B - 1 : b);
+                    int k = 0;
+                    while (k < m && ob[k] < b) k++;
+                    if (k == m || ob[k] != b) {
+                        for (int j = m; j > k; j--) { ob[j] = ob[j - 1]; obox[j] = obox[j - 1]; ocnt[j] = ocnt[j - 1]; }
+                        ob[k] = b; obox[k].reset(); ocnt[k] = 0; m++;
+                    }
+                    ocnt[k]++;
+                    obox[k].grow(p.b);
+                }
+                Box acc; acc.reset();
+                for (int k = m - 1; k > 0; k--) { acc.grow(obox[k]); racc[k] = acc; }
+                acc.reset();
+                int32_t nl = 0;
+                for (int k = 0; k + 1 < m; k++) {
+                    acc.grow(obox[k]);
+                    nl += ocnt[k];
+                    const double cost = acc.area() * nl + racc[k + 1].area() * (count - nl);
+                    if (cost < bestCost) { bestCost = cost; bestAxis = axis; bestSplit = ob[k]; }
+                }
+                continue;
+            }
             for (int b = 0; b < B; b++) { bb[b].reset(); cnt[b] = 0; }
-            for (int32_t i = first; i < first + count; i++) {
-                const PrimRef& p = prims[order[i]];
-                int b = (int)((p.c[axis] - cmin) * scale);
-                b = b < 0 ? 0 : (b >= B ? B - 1 : b);
-                cnt[b]++;
-                bb[b].grow(p.b);
+            if (slices <= 1) {
+                for (int32_t i = first; i < first + count; i++) {
+                    const PrimRef& p = prims[i];
+                    int b = (int)((p.c[axis] - cmin) * scale);
+                    b = b < 0 ? 0 : (b >= B ? B - 1 : b);
+                    cnt[b]++;
+                    bb[b].grow(p.b);
+                }
+            } else {
+                std::vector<Box> sbb((size_t)slices * B);
+                std::vector<int32_t> scnt((size_t)slices * B, 0);
+                for (auto& x : sbb) x.reset();
+                forSlices(slices, first, count, [&](int sl, int32_t a, int32_t n) {
+                    Box* mb = &sbb[(size_t)sl * B]; int32_t* mc = &scnt[(size_t)sl * B];
+                    for (int32_t i = a; i < a + n; i++) {
+                        const PrimRef& p = prims[i];
+                        int b = (int)((p.c[axis] - cmin) * scale);
+                        b = b < 0 ? 0 : (b >= B ? B - 1 : b);
+                        mc[b]++;
+                        mb[b].grow(p.b);
+                    }
+                });
+                for (int sl = 0; sl < slices; sl++)
+                    for (int b = 0; b < B; b++) { cnt[b] += scnt[(size_t)sl * B + b]; if (scnt[(size_t)sl * B + b]) bb[b].grow(sbb[(size_t)sl * B + b]); }
             }
             Box acc; acc.reset();
             for (int b = B - 1; b > 0; b--) { acc.grow(bb[b]); rightAcc[b] = acc; }
@@ -99,12 +178,12 @@ struct SahBuilder {
         } else {
             const double cmin = cb.lo[bestAxis];
             const double scale = B / (cb.hi[bestAxis] - cmin);
-            auto it = std::partition(order.begin() + first, order.begin() + first + count, [&](int32_t id) {
-                int b = (int)((prims[id].c[bestAxis] - cmin) * scale);
+            auto it = std::partition(prims.begin() + first, prims.begin() + first + count, [&](const PrimRef& p) {
+                int b = (int)((p.c[bestAxis] - cmin) * scale);
                 b = b < 0 ? 0 : (b >= B ? B - 1 : b);
                 return b <= bestSplit;
             });
-            mid = (int32_t)(it - order.begin());
+            mid = (int32_t)(it - prims.begin());
             if (mid == first || mid == first + count) mid = first + count / 2;
         }
 
@@ -142,13 +221,14 @@ void build_binary_sah(const double* verts, int64_t n, int bins, BinaryBVH* out) 
     for (int64_t i = 0; i < n; i++) {
         prims[i].b = triBox(verts + i * 9);
         for (int k = 0; k < 3; k++) prims[i].c[k] = 0.5 * (prims[i].b.lo[k] + prims[i].b.hi[k]);
+        prims[i].id = (int32_t)i;
     }
     out->order.resize((size_t)n);
-    for (int64_t i = 0; i < n; i++) out->order[i] = (int32_t)i;
     out->nodes.resize((size_t)(2 * n - 1));
     SahBuilder b(prims, out->order, out->nodes, bins);
     out->root = b.build(0, (int32_t)n, 0);
     out->nodes.resize((size_t)b.nextNode.load());
+    for (int64_t i = 0; i < n; i++) out->order[i] = prims[i].id;
 }
 
 bool import_binary(const spb_import_node* in, int64_t n_nodes, int32_t root, const double* verts,
