@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SPB_VERSION 1
+#define SPB_VERSION 2
 
 typedef enum spb_status {
     SPB_OK = 0,
@@ -170,13 +170,22 @@ typedef struct spb_render_desc {
     int32_t integrator;             /* SPB_INTEGRATOR_* (0 = path)                                       */
 } spb_render_desc;
 
-/* Allocates (or re-uses) and clears the device film and the wavefront queues. */
+/* Allocates (or re-uses) and clears the device film and the wavefront queues, uploads whatever changed in the scene,
+ * and prepares the render loop (kernels loaded, its iteration captured into a CUDA graph).  max_depth <= 4095.
+ * Any later change to the scene (triangles, attributes, materials, lights, textures, environment, a new
+ * acceleration structure) invalidates the render: spb_render_samples* then return SPB_ERR_INVALID until
+ * spb_render_begin is called again. */
 int spb_render_begin(spb_ctx* ctx, const spb_render_desc* desc);
 /* Renders sample indices first, first+stride, ... (count of them) for every pixel and accumulates
  * them into the device film: one iteration of the spp loop of SamplerIntegrator::render per index.
- * A rank of an N-GPU job passes (first = rank, stride = N). Stream-ordered; returns after the
- * work is enqueued and complete (synchronous). */
+ * A rank of an N-GPU job passes (first = rank, stride = N).  Synchronous: returns when the samples are in the film. */
 int spb_render_samples(spb_ctx* ctx, int32_t first, int32_t count, int32_t stride);
+/* The same, asynchronous: returns at once; the context's render worker drives the loop.  Calls queue up in order
+ * (so do spb_film_reduce_async calls between them).  spb_render_wait blocks until everything queued has finished
+ * and returns the first error any of it reported (spb_last_error has the text).  Every other call that reads or
+ * changes the film, the scene or the statistics waits for the queue first. */
+int spb_render_samples_async(spb_ctx* ctx, int32_t first, int32_t count, int32_t stride);
+int spb_render_wait(spb_ctx* ctx);
 /* Raw accumulators, height x width x 4 floats {sum w*r, sum w*g, sum w*b, sum w}, pixel (x, y) as
  * Film::addPixel indexed them (the horizontal flip of core/integrator.cc:88 already applied). */
 int spb_film_read(spb_ctx* ctx, float* rgbw);
@@ -197,6 +206,8 @@ typedef struct spb_render_stats {
     int64_t paths, rays_closest, rays_shadow, rays_mis;   /* rays traced since spb_render_begin   */
     int64_t kernel_launches;
     double  render_ms;                                    /* device time of all spb_render_samples */
+    double  reduce_ms;                                    /* device time of all film reductions (includes waiting for the slowest rank) */
+    int64_t iterations;                                   /* iterations of the streaming loop (one extend + shade + connect + MIS each) */
 } spb_render_stats;
 int spb_render_get_stats(spb_ctx* ctx, spb_render_stats* out);
 
@@ -204,7 +215,14 @@ int spb_render_get_stats(spb_ctx* ctx, spb_render_stats* out);
 #define SPB_COMM_ID_BYTES 128
 int spb_comm_get_unique_id(char id[SPB_COMM_ID_BYTES]);                 /* rank 0; ship to the others */
 int spb_comm_init(spb_ctx* ctx, const char id[SPB_COMM_ID_BYTES], int32_t n_ranks, int32_t rank);
-int spb_film_allreduce(spb_ctx* ctx);   /* ncclAllReduce(sum, float32) of the RGBW film, in place     */
+/* One sum (float32) over the RGBW films of all ranks per frame, in place, stream-ordered behind the frame's last kernel:
+ * root < 0: ncclAllReduce, every rank gets the frame; root >= 0: ncclReduce, only rank `root` does (half the traffic;
+ * the other ranks' films are left as they were).  The communicator's asynchronous error state is checked while the
+ * call waits and after it: a peer that died turns into SPB_ERR_CUDA here (and the communicator is aborted), never into
+ * a hang or a half-summed frame.  spb_film_reduce_async queues the reduction behind spb_render_samples_async calls. */
+int spb_film_reduce(spb_ctx* ctx, int32_t root);
+int spb_film_reduce_async(spb_ctx* ctx, int32_t root);
+int spb_film_allreduce(spb_ctx* ctx);   /* = spb_film_reduce(ctx, -1)                                  */
 int spb_comm_destroy(spb_ctx* ctx);
 
 /* ---- acceleration structure ---------------------------------------------------------------- */
@@ -275,8 +293,8 @@ int spb_get_counters(spb_ctx* ctx, spb_counters* out);
  * 2 = 1 + warp-pooled float32 pre-test, 3 = 2 in visit / select / triangles order, 4 = 3 with the
  * stack in shared memory, 5 = 4 with three node visits per pooled triangle phase (default); every
  * variant returns the same records), "chunk_rays" (rays per pipelined chunk of the host-buffer calls,
- * default 524288), "wave_slots" (paths in flight per integrator wave), "shade_generic" (1 = always the
- * all-lobes shade kernel instead of the instance for the scene's set of lobe types; same image),
+ * default 524288), "wave_slots" (capacity of the integrator's queues = paths in flight, default 8 Mi, takes effect at
+ * the next spb_render_begin), "render_graph" (0 = plain launches instead of the CUDA graph),
  * "shade_minb" (4/5/6: occupancy the Lambertian-only shade instance is compiled for). Unknown names
  * return SPB_ERR_INVALID.
  * Environment read by spb_bvh_build / spb_bvh_import_binary: SPICA_BVH_COLLAPSE=0 selects the greedy

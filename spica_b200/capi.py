@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libspica_b200.so")
+LIB_PATH = os.environ.get("SPICA_B200_LIB") or os.path.join(HERE, "lib", "libspica_b200.so")     # the override is for A/B measurement builds (tools/)
 
 RAY_F32 = np.dtype([("o", "<f4", 3), ("d", "<f4", 3), ("tmin", "<f4"), ("tmax", "<f4")])
 RAY_F64 = np.dtype([("o", "<f8", 3), ("d", "<f8", 3), ("tmin", "<f8"), ("tmax", "<f8")])
@@ -63,7 +63,8 @@ class RenderDesc(C.Structure):
 
 class RenderStats(C.Structure):
     _fields_ = [("paths", C.c_int64), ("rays_closest", C.c_int64), ("rays_shadow", C.c_int64),
-                ("rays_mis", C.c_int64), ("kernel_launches", C.c_int64), ("render_ms", C.c_double)]
+                ("rays_mis", C.c_int64), ("kernel_launches", C.c_int64), ("render_ms", C.c_double),
+                ("reduce_ms", C.c_double), ("iterations", C.c_int64)]
 
 
 MAT_TYPES = {"none": -1, "diffuse": 0, "dielectric": 1, "roughconductor": 2, "roughdielectric": 3, "conductor": 4,
@@ -89,7 +90,7 @@ SYMBOLS = [
     "spb_ctx_stream",
     "spb_scene_set_triangle_attributes", "spb_scene_set_materials", "spb_scene_set_lights", "spb_scene_set_envmap",
     "spb_scene_set_textures", "spb_scene_set_material_textures",
-    "spb_render_begin", "spb_render_samples", "spb_film_read", "spb_film_resolve", "spb_film_resolve_rgbe", "spb_film_resolve_ldr",
+    "spb_render_begin", "spb_render_samples", "spb_render_samples_async", "spb_render_wait", "spb_film_reduce", "spb_film_reduce_async", "spb_film_read", "spb_film_resolve", "spb_film_resolve_rgbe", "spb_film_resolve_ldr",
     "spb_film_add",
     "spb_render_get_stats", "spb_comm_get_unique_id", "spb_comm_init", "spb_film_allreduce", "spb_comm_destroy",
 ]
@@ -131,6 +132,10 @@ def load():
     L.spb_scene_set_envmap.argtypes = [vp, vp, i32, i32, vp, C.c_double, vp, C.c_double]
     L.spb_render_begin.argtypes = [vp, C.POINTER(RenderDesc)]
     L.spb_render_samples.argtypes = [vp, i32, i32, i32]
+    L.spb_render_samples_async.argtypes = [vp, i32, i32, i32]
+    L.spb_render_wait.argtypes = [vp]
+    L.spb_film_reduce.argtypes = [vp, i32]
+    L.spb_film_reduce_async.argtypes = [vp, i32]
     L.spb_film_read.argtypes = [vp, vp]
     L.spb_film_resolve.argtypes = [vp, vp]
     L.spb_film_add.argtypes = [vp, vp]
@@ -389,6 +394,18 @@ class Context:
 
     def film_allreduce(self):
         self._check(self.L.spb_film_allreduce(self.h))
+
+    def film_reduce(self, root=0):
+        self._check(self.L.spb_film_reduce(self.h, root))
+
+    def render_samples_async(self, first, count, stride=1):
+        self._check(self.L.spb_render_samples_async(self.h, first, count, stride))
+
+    def film_reduce_async(self, root=0):
+        self._check(self.L.spb_film_reduce_async(self.h, root))
+
+    def render_wait(self):
+        self._check(self.L.spb_render_wait(self.h))
 
 
 def comm_unique_id():

@@ -34,6 +34,11 @@ static void freeBvhDevice(spb_ctx* ctx) {
     if (ctx->d_tris) cudaFree(ctx->d_tris);
     ctx->d_nodes = ctx->d_tris = nullptr;
     ctx->bvh_ready = false;
+    // nothing may keep pointing at the freed tree: the kernels' parameter block goes back to "no geometry" and a
+    // render that was begun on the old tree needs a new spb_render_begin
+    std::memset(&ctx->sp, 0, sizeof(ctx->sp));
+    ctx->sp.empty = 1; ctx->sp.f32_one = 0x3f800000u;
+    renderSceneChanged(ctx);
 }
 
 static int uploadBvh(spb_ctx* ctx) {
@@ -41,6 +46,7 @@ static int uploadBvh(spb_ctx* ctx) {
     const HostBVH& b = ctx->bvh;
     SceneParams& sp = ctx->sp;
     std::memset(&sp, 0, sizeof(sp));
+    sp.f32_one = 0x3f800000u;
     sp.empty = (b.n_tris == 0 || b.nodes.empty()) ? 1 : 0;
     sp.n_tris = (int32_t)b.n_tris;
     sp.tri_format = b.tri_format;
@@ -117,7 +123,7 @@ int spb_ctx_create(int device, spb_ctx** out) {
     if ((e = cudaMalloc(&ctx->d_work, 4 * (spb_ctx::kPipe + 1) * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
     cudaMemset(ctx->d_work, 0, 4 * (spb_ctx::kPipe + 1) * sizeof(unsigned long long));
     std::memset(&ctx->sp, 0, sizeof(ctx->sp));
-    ctx->sp.empty = 1;
+    ctx->sp.empty = 1; ctx->sp.f32_one = 0x3f800000u;
     *out = ctx;
     return SPB_OK;
 }
@@ -228,10 +234,22 @@ int spb_set_option(spb_ctx* ctx, const char* name, int64_t value) {
     else if (n == "trace_block") {
         if (value < 32 || value > 1024 || (value % 32)) return fail(ctx, SPB_ERR_INVALID, "trace_block must be a multiple of 32 in [32,1024]");
         ctx->opt_block = (int)value;
-    } else if (n == "trace_ctas_per_sm") ctx->opt_ctas_per_sm = (int)value;
-    else if (n == "shade_minb") ctx->opt_shade_minb = (int)value;
-    else if (n == "shade_generic") ctx->opt_shade_generic = value ? 1 : 0;
-    else if (n == "trace_variant") ctx->opt_variant = (int)value;
+    } else if (n == "trace_ctas_per_sm") {
+        if (value < 0 || value > 32) return fail(ctx, SPB_ERR_INVALID, "trace_ctas_per_sm must be in [0,32] (0 = occupancy query)");
+        ctx->opt_ctas_per_sm = (int)value;
+    } else if (n == "shade_minb") {
+        if (value != 0 && (value < 4 || value > 6)) return fail(ctx, SPB_ERR_INVALID, "shade_minb must be 0 (default), 4, 5 or 6");
+        ctx->opt_shade_minb = (int)value;
+    } else if (n == "trace_variant") {
+#ifdef SPB_EXPERIMENTAL_VARIANTS
+        const bool ok = value >= 0 && value <= 25;
+#else
+        const bool ok = value >= 0 && value <= 5;
+#endif
+        if (!ok) return fail(ctx, SPB_ERR_INVALID, "trace_variant must be in [0,5] (measurement variants need a `make EXP=1` build)");
+        ctx->opt_variant = (int)value;
+    }
+    else if (n == "render_graph") ctx->opt_render_graph = value ? 1 : 0;
     else if (n == "wave_slots") { if (value < 1024) return fail(ctx, SPB_ERR_INVALID, "wave_slots too small"); ctx->opt_wave_slots = value; }
     else if (n == "chunk_rays") { if (value < 1024) return fail(ctx, SPB_ERR_INVALID, "chunk_rays too small"); ctx->opt_chunk = value; }
     else return fail(ctx, SPB_ERR_INVALID, "spb_set_option: unknown option " + n);

@@ -48,6 +48,7 @@ struct SceneParams {                    // small POD passed to kernels by value
     int32_t n_tris;
     int32_t empty;                      // 1: no geometry
     int32_t max_depth;                  // depth of the wide tree = the most stack entries a ray can hold
+    uint32_t f32_one;                   // 0x3f800000, as a parameter-block operand of the node test's PRMT (trace_core.h, byteMant)
 };
 
 }  // namespace spb

@@ -4,6 +4,7 @@
 
 #include <cstdint>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/spica_b200.h"
@@ -49,13 +50,16 @@ struct spb_ctx {
     int opt_counters = 0;
     int opt_block = 128;
     int opt_ctas_per_sm = 0;             // 0 = occupancy query
-    int opt_shade_generic = 0;           // 1: always the all-lobes shade kernel (to compare with the scene-specialised instances)
+    int opt_render_graph = 1;            // the integrator's iteration pair as a CUDA graph (0: plain launches; same image)
     int opt_shade_minb = 0;              // Lambertian-only shade instance compiled for 4, 5 or 6 resident CTAs per SM (0 = default, 4)
     int opt_variant = 5;                 // 0 = one thread per ray, 1 = persistent dynamic fetch, 2 = 1 + warp-cooperative pre-test, 3 = 2 in early-select order,
                                          // 4 = 3 with the stack in shared memory, 5 = 4 with three node visits per pooled triangle phase (default;
                                          // falls back to 3 on trees deeper than the shared stack and to 2 on float64 triangles)
     int64_t opt_chunk = 1 << 19;         // rays per pipelined chunk on the host-buffer path (measured: 256K 1412, 512K 1574, 1M 1403, 2M 1364 Mrays/s; PCIe floor 1574)
-    int64_t opt_wave_slots = 1 << 24;    // paths in flight per wave of the integrator (228 B each: 3.8 GB of the 180 GB; the nearly empty late bounces of a wave amortise over 4x more paths than at 4 Mi: C3 +28 %)
+    int64_t opt_wave_slots = 1 << 23;    // capacity of the integrator's queues = paths in flight (240 B each); the streaming loop keeps them full, so the size only has to amortise the ~6 launches of an iteration
+
+    // resident CTAs per SM of each traversal kernel instantiation on THIS device (the occupancy query is slow enough to matter per chunk)
+    std::unordered_map<const void*, int> occupancy;
 
     // counters
     double last_kernel_ms = 0.0;
@@ -71,7 +75,7 @@ int  fail(spb_ctx* ctx, int code, const std::string& msg);
 bool cudaOk(spb_ctx* ctx, cudaError_t e, const char* what);
 void setGlobalError(const std::string& msg);
 void renderStateDestroy(spb_ctx* ctx);   // integrator.cu
-void renderSceneChanged(spb_ctx* ctx);   // integrator.cu
+void renderSceneChanged(spb_ctx* ctx);   // integrator.cu: geometry / attributes changed, a new spb_render_begin is required
 int  buildLbvhDevice(spb_ctx* ctx, BinaryBVH* out);   // lbvh.cu
 }  // namespace spb
 

@@ -14,11 +14,24 @@
 //                 added inside the traversal kernel when the expected light is hit
 //   K5 film       adds every finished path into the RGBW film              film.cc:65-74, integrator.cc:88-90
 //
-// Queue sizes never visit the host: every kernel reads its count from device memory, so a wave is
-// one uninterrupted stream of launches.  A path keeps one slot for its whole life (beta, L, pixel,
-// sampler key); queues carry (ray, slot) records.
+//   K5 film       every radiance term (emission, unoccluded light sample, MIS hit) goes straight   film.cc:65-74, integrator.cc:88-90
+//                 into the RGBW film with one 128-bit reduction (RED.ADD.F32x4)
+//
+// STREAMING, not waves: the extend queue is topped up with new camera paths at the start of every
+// iteration (path regeneration), so every launch works on a full queue until the samples of the call
+// run out; a path's whole state (beta, sampler key, flags, filter weight) travels WITH its ray record,
+// indexed by queue position, so the shade kernel reads and writes it coalesced and nothing is indexed
+// by a per-path slot.  Queue sizes never visit the host: every kernel reads its count from device
+// memory, the loop's bookkeeping runs in a one-thread control kernel, and two iterations (queue A,
+// queue B) are captured once into a CUDA graph that the host re-launches until the control kernel
+// reports an empty pipeline through mapped host memory (polled one launch behind, so the stream never drains).
 #include <chrono>
+#include <condition_variable>
 #include <cstring>
+#include <deque>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include <dlfcn.h>
@@ -30,22 +43,27 @@
 namespace spb {
 
 // ---- device state -----------------------------------------------------------------------------------
-struct PathSoA {
-    float* beta[3];
-    float* L[3];
-    uint32_t* pixel;      // pixel index y * width + x (unflipped)
-    uint32_t* key;        // sampler key of (pixel, sample)
-    uint32_t* flags;      // [7:0] bounces, [8] specularBounce, [31:16] path vertex counter (sampler dimension base)
+struct Queues {
+    float4* ray[2];       // extend queue (double buffered), 2 x float4 per entry = one spb_ray_f32 whose tmin carries the film index
+    float4* state[2];     // parallel to ray[]: {beta.rgb, key0}, {flags, filter weight, key1, -}
+                          //   flags: [11:0] bounces, [12] specularBounce, [31:16] path vertex counter (sampler dimension base)
+    spb_hit* hit;         // parallel to ray[cur]
+    float4*  shadow;      // connect queue (2 x float4 per entry), tmin = film index
+    float4*  shadowC;     // contribution rgb, already multiplied by the path's filter weight
+    float4*  mis;         // MIS closest-hit queue
+    float4*  misC;        // contribution rgb (weighted), w = expected primitive id (bits) or -1 for "escapes"
+    uint32_t* count;      // [0],[1] extend queue sizes, [2] shadow, [3] mis
 };
 
-struct Queues {
-    spb_ray_f32* ray[2];  // extend queue (double buffered); ray.tmin carries the slot id (bit pattern)
-    spb_hit*     hit;     // parallel to ray[cur]
-    spb_ray_f32* shadow;  // connect queue
-    float4*      shadowC; // contribution rgb
-    spb_ray_f32* mis;     // MIS closest-hit queue
-    float4*      misC;    // contribution rgb, w = expected primitive id (bits) or -1 for "escapes"
-    uint32_t*    count;   // [0],[1] extend queue sizes, [2] shadow, [3] mis
+// Control block of the streaming loop (device memory; written by controlKernel only).
+struct LoopCtl {
+    unsigned long long cursor, total;   // work items (pixel, sample) handed out so far / in this call
+    unsigned long long stats[4];        // [0] paths [1] closest-hit rays [2] shadow rays [3] MIS rays, since spb_render_begin
+    unsigned long long iterations;
+    unsigned long long gen_item0;       // this iteration's regeneration: items [gen_item0, gen_item0 + gen_n) -> queue positions [gen_dst, ...)
+    uint32_t gen_n, gen_dst;
+    uint32_t capacity;
+    int32_t  first, stride;             // sample index of item k: first + (k / pixels) * stride
 };
 
 struct DeviceScene {
@@ -74,23 +92,38 @@ struct RenderParamsPOD {
     uint64_t seed;
 };
 
+// radiance into the film: one vector reduction per term (sm_90+: RED.E.ADD.F32x4)
+__device__ __forceinline__ void filmAdd(float4* film, uint32_t index, float r, float g, float b, float w) {
+    atomicAdd(film + index, make_float4(r, g, b, w));
+}
+
 struct SinkShadow {      // connect: add the contribution when NOTHING was hit
-    const spb_ray_f32* rays; const float4* contrib; PathSoA paths;
+    const float4* rays; const float4* contrib; float4* film;
     __device__ __forceinline__ void store(int64_t i, const RayState& r) const {
         if (r.best_prim >= 0) return;
-        const uint32_t slot = __float_as_uint(rays[i].tmin);
         const float4 c = contrib[i];
-        paths.L[0][slot] += c.x; paths.L[1][slot] += c.y; paths.L[2][slot] += c.z;
+        filmAdd(film, __float_as_uint(rays[2 * i + 1].z), c.x, c.y, c.z, 0.f);
     }
 };
 struct SinkMis {         // MIS: add the contribution when exactly the expected light (or nothing) was hit
-    const spb_ray_f32* rays; const float4* contrib; PathSoA paths;
+    const float4* rays; const float4* contrib; float4* film;
     __device__ __forceinline__ void store(int64_t i, const RayState& r) const {
         const float4 c = contrib[i];
         if (r.best_prim != (int32_t)__float_as_uint(c.w)) return;
-        const uint32_t slot = __float_as_uint(rays[i].tmin);
-        paths.L[0][slot] += c.x; paths.L[1][slot] += c.y; paths.L[2][slot] += c.z;
+        filmAdd(film, __float_as_uint(rays[2 * i + 1].z), c.x, c.y, c.z, 0.f);
     }
+};
+
+// One context's render worker: spb_render_samples_async / spb_film_reduce_async hand their host-side loops to it.
+struct RenderWorker {
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv, cvDone;
+    std::deque<std::function<int()>> tasks;
+    int pending = 0;
+    bool stop = false;
+    int firstError = SPB_OK;
+    std::string firstMessage;
 };
 
 struct RenderState {
@@ -105,24 +138,37 @@ struct RenderState {
     std::vector<spb_texture> texs; std::vector<float> texels; std::vector<int32_t> mat_tex;   // textures + per-material bindings
     int2* d_mat_tex = nullptr; spb_texture* d_texs = nullptr; float4* d_texels = nullptr; float* d_uvs = nullptr;
     bool scene_dirty = true;
-    bool sort_materials = false;        // more than one BSDF type in the scene: shade in material order
+    bool sort_materials = false;        // more than one BSDF type in the scene: classify, then one shade instance per bucket
+    uint32_t bucket_mask = 0u;          // buckets (kBucket*) the scene can produce
+    uint8_t* d_prim_bucket = nullptr;   // per triangle: its bucket
+    uint32_t* d_lists = nullptr; uint32_t* d_list_count = nullptr; int64_t list_stride = 0;
     uint32_t type_mask = 0x7fu;         // lobe types the scene's materials can produce: picks the shade kernel instance
     // envmap
     std::vector<float> env_rgb; int env_w = 0, env_h = 0; double env_l2w[16]; double env_scale = 1.0, env_center[3] = {0, 0, 0}, env_radius = 2.0;
     bool env_present = false, env_dirty = false;
     float4* d_env_texels = nullptr; float* d_env_floats = nullptr;
     DeviceScene ds{};
-    // film + paths
+    // film + queues
     float4* d_film = nullptr; int64_t film_pixels = 0;
-    int64_t slots = 0;
+    int64_t slots = 0;                       // capacity of each queue
     void* d_pool = nullptr;
-    PathSoA paths{}; Queues q{};
-    unsigned long long* d_stats = nullptr;   // [0] paths [1] closest [2] shadow [3] mis
-    unsigned long long* d_cursor = nullptr;  // 3 x 4 u64 cursors for the three trace launches of a bounce
-    int64_t launches = 0, paths_total = 0; double render_ms = 0.0;
+    Queues q{};
+    LoopCtl* d_ctl = nullptr;
+    unsigned long long* d_cursor = nullptr;  // 3 x 4 u64 ray cursors for the three trace launches of an iteration
+    uint32_t* h_status = nullptr;            // mapped host memory: [0] pipeline empty, [1] iterations run
+    uint32_t* d_status = nullptr;            // its device address
+    cudaGraphExec_t graph_exec = nullptr;    // two iterations (queue 0, queue 1)
+    cudaEvent_t poll[4] = {};                // the host polls h_status one graph launch behind
+    cudaEvent_t ev_r0 = nullptr, ev_r1 = nullptr;
+    int64_t launches = 0; int launches_per_iteration = 6; double render_ms = 0.0, reduce_ms = 0.0;
+    void* d_scratch = nullptr; size_t scratch_bytes = 0;    // grow-only staging of spb_film_resolve* / spb_film_add
+    RenderWorker* worker = nullptr;
     // nccl
     void* nccl_lib = nullptr; void* comm = nullptr;
 };
+
+static void workerStop(RenderState* R);
+static int workerDrain(spb_ctx* ctx, RenderState* R);
 
 static RenderState* rs(spb_ctx* ctx) {
     if (!ctx->render) ctx->render = new RenderState();
@@ -143,59 +189,35 @@ __device__ __forceinline__ void applyVector(const double* m, double x, double y,
     for (int i = 0; i < 3; i++) o[i] = m[i * 4 + 0] * x + m[i * 4 + 1] * y + m[i * 4 + 2] * z;
 }
 
-__global__ void __launch_bounds__(256) generateKernel(RenderParamsPOD rp, CameraPOD cam, PathSoA paths, Queues q,
-                                                    int64_t item0, int64_t n, int first, int stride) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int64_t item = item0 + i;
-    const int64_t npix = (int64_t)rp.width * rp.height;
-    const uint32_t pixel = (uint32_t)(item % npix);
-    const uint32_t sample = (uint32_t)(first + (int)(item / npix) * stride);
-    const uint32_t key = samplerKey(rp.seed, pixel, sample);
-    const int x = pixel % rp.width, y = pixel / rp.width;
-    // core/integrator.cc:84-86, cameras/perspective.cc:53-74
-    const float f0 = sample1D(key, kDimFilm), f1 = sample1D(key, kDimFilm + 1);
-    double pc[3];
-    applyPoint(cam.r2c, (double)x + (double)f0, (double)y + (double)f1, 0.0, pc);
-    double nrm = sqrt(pc[0] * pc[0] + pc[1] * pc[1] + pc[2] * pc[2]);
-    double dir[3] = {pc[0] / nrm, pc[1] / nrm, pc[2] / nrm};
-    double org[3] = {0.0, 0.0, 0.0};
-    if (cam.lens_radius > 0.0) {
-        float lx, ly;
-        concentricDisk(sample1D(key, kDimLens), sample1D(key, kDimLens + 1), &lx, &ly);
-        const double ft = cam.focal / dir[2];
-        const double pf[3] = {dir[0] * ft, dir[1] * ft, dir[2] * ft};
-        org[0] = cam.lens_radius * lx; org[1] = cam.lens_radius * ly;
-        double d2[3] = {pf[0] - org[0], pf[1] - org[1], pf[2] - org[2]};
-        nrm = sqrt(d2[0] * d2[0] + d2[1] * d2[1] + d2[2] * d2[2]);
-        dir[0] = d2[0] / nrm; dir[1] = d2[1] / nrm; dir[2] = d2[2] / nrm;
-    }
-    double ow[3], dw[3];
-    applyPoint(cam.c2w, org[0], org[1], org[2], ow);
-    applyVector(cam.c2w, dir[0], dir[1], dir[2], dw);
-    const double s = 1.0 / sqrt(dw[0] * dw[0] + dw[1] * dw[1] + dw[2] * dw[2]);   // Ray ctor, core/ray.cc:15
-    spb_ray_f32 r;
-    r.ox = (float)ow[0]; r.oy = (float)ow[1]; r.oz = (float)ow[2];
-    r.dx = (float)(dw[0] * s); r.dy = (float)(dw[1] * s); r.dz = (float)(dw[2] * s);
-    r.tmin = __uint_as_float((uint32_t)i); r.tmax = kRayInf;
-    q.ray[0][i] = r;
-    paths.beta[0][i] = 1.f; paths.beta[1][i] = 1.f; paths.beta[2][i] = 1.f;
-    paths.L[0][i] = 0.f; paths.L[1][i] = 0.f; paths.L[2][i] = 0.f;
-    paths.pixel[i] = pixel; paths.key[i] = key; paths.flags[i] = 0u;
-    if (i == 0) { q.count[0] = (uint32_t)n; q.count[1] = 0u; q.count[2] = 0u; q.count[3] = 0u; }
+// ---- loop control: one thread, once per iteration, BEFORE the iteration's kernels -------------------------------
+// Folds the sizes of the queues the previous iteration consumed into the statistics, clears them and the three
+// ray cursors, and plans this iteration's regeneration: the extend queue `cur` (which holds the paths that
+// survived the previous shade) is topped up to capacity with the next work items of the call.
+__global__ void controlKernel(LoopCtl* ctl, Queues q, int cur, unsigned long long* cursors, uint32_t* status, uint32_t* bucketCount) {
+    if (bucketCount && blockIdx.x == 0 && threadIdx.x < 16) bucketCount[threadIdx.x] = 0u;      // classifyKernel's lists (kNumBuckets <= 16 counters)
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int prev = cur ^ 1;
+    ctl->stats[1] += q.count[prev]; ctl->stats[2] += q.count[2]; ctl->stats[3] += q.count[3];
+    q.count[prev] = 0u; q.count[2] = 0u; q.count[3] = 0u;
+    cursors[0] = 0ull; cursors[4] = 0ull; cursors[8] = 0ull;
+    const uint32_t n0 = q.count[cur];
+    const unsigned long long room = (unsigned long long)(ctl->capacity - n0), left = ctl->total - ctl->cursor;
+    const uint32_t gen = (uint32_t)(room < left ? room : left);
+    ctl->gen_n = gen; ctl->gen_dst = n0; ctl->gen_item0 = ctl->cursor;
+    ctl->cursor += gen; ctl->stats[0] += gen;
+    q.count[cur] = n0 + gen;
+    ctl->iterations++;
+    status[1] = (uint32_t)ctl->iterations;
+    status[0] = (n0 + gen == 0u) ? 1u : 0u;       // nothing in flight and nothing left to start: the call is finished
+    __threadfence_system();
 }
-
-// ---- K4: shade ---------------------------------------------------------------------------------------
-__device__ __forceinline__ TriGeom loadTri(const ShadeTri* tris, int prim) {
-    const float4* p = (const float4*)(tris + prim);
-    const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3), e = __ldg(p + 4), f = __ldg(p + 5), g = __ldg(p + 6);
-    TriGeom t;
-    t.p0 = v3(a.x, a.y, a.z); t.e1 = v3(a.w, b.x, b.y); t.e2 = v3(b.z, b.w, c.x);
-    t.ng = v3(c.y, c.z, c.w); t.fn = v3(d.x, d.y, d.z); t.area = d.w;
-    t.ss = v3(e.x, e.y, e.z); t.material = __float_as_int(e.w);
-    t.ts = v3(f.x, f.y, f.z); t.light = __float_as_int(f.w);
-    t.has_normals = __float_as_int(g.x);
-    return t;
+// start of a spb_render_samples call
+__global__ void loopBeginKernel(LoopCtl* ctl, Queues q, int first, int stride, unsigned long long total, uint32_t capacity, uint32_t* status) {
+    ctl->cursor = 0ull; ctl->total = total; ctl->first = first; ctl->stride = stride; ctl->capacity = capacity;
+    ctl->gen_n = 0u; ctl->gen_dst = 0u; ctl->gen_item0 = 0ull;
+    q.count[0] = 0u; q.count[1] = 0u; q.count[2] = 0u; q.count[3] = 0u;
+    status[0] = 0u;
+    __threadfence_system();
 }
 
 // warp-aggregated queue push: one atomic per warp per queue
@@ -210,10 +232,78 @@ __device__ __forceinline__ uint32_t queuePush(uint32_t* counter, bool want) {
     return base + __popc(mask & ((1u << lane) - 1u));
 }
 
-__device__ __forceinline__ void writeRay(spb_ray_f32* q, uint32_t idx, V3 o, V3 d, uint32_t slot, float tmax) {
-    float4* p = (float4*)(q + idx);
-    p[0] = make_float4(o.x, o.y, o.z, d.x);
-    p[1] = make_float4(d.y, d.z, __uint_as_float(slot), tmax);
+__device__ __forceinline__ void writeRay(float4* q, uint32_t idx, V3 o, V3 d, uint32_t tag, float tmax) {
+    q[2 * idx] = make_float4(o.x, o.y, o.z, d.x);
+    q[2 * idx + 1] = make_float4(d.y, d.z, __uint_as_float(tag), tmax);
+}
+__device__ __forceinline__ void writeState(float4* q, uint32_t idx, V3 beta, uint2 key, uint32_t flags, float fw) {
+    q[2 * idx] = make_float4(beta.x, beta.y, beta.z, __uint_as_float(key.x));
+    q[2 * idx + 1] = make_float4(__uint_as_float(flags), fw, __uint_as_float(key.y), 0.f);
+}
+
+__device__ __forceinline__ float filterWeight(const RenderParamsPOD& rp, float dx, float dy) {
+    switch (rp.filter) {
+    case SPB_FILTER_TENT: return fmaxf(0.f, rp.frx - fabsf(dx)) * fmaxf(0.f, rp.fry - fabsf(dy));                 // filters/tent.cc:27-30
+    case SPB_FILTER_GAUSSIAN: return fmaxf(0.f, expf(-rp.fbeta * dx * dx) - rp.fexpx) * fmaxf(0.f, expf(-rp.fbeta * dy * dy) - rp.fexpy);  // gaussian.cc:34-40
+    default: return 1.f;                                                                                             // filters/box.cc:22
+    }
+}
+
+// K3: the camera rays of this iteration's regeneration (core/integrator.cc:80-86, cameras/perspective.cc:53-74),
+// appended to the extend queue `cur` behind the surviving paths.  Film::addPixel's weight w = filter(randFilm - 0.5)
+// (core/film.cc:65-74) is fixed here and travels with the path; the pixel is stored as the FILM index, i.e. with
+// the horizontal flip of core/integrator.cc:88 applied.
+__global__ void __launch_bounds__(256) generateKernel(RenderParamsPOD rp, CameraPOD cam, Queues q, const LoopCtl* __restrict__ ctl, int cur) {
+    const uint32_t n = ctl->gen_n, dst = ctl->gen_dst;
+    const unsigned long long item0 = ctl->gen_item0;
+    const int first = ctl->first, stride = ctl->stride;
+    const unsigned long long npix = (unsigned long long)rp.width * rp.height;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned long long item = item0 + i;
+        const uint32_t pixel = (uint32_t)(item % npix);
+        const uint32_t sample = (uint32_t)(first + (int)(item / npix) * stride);
+        const uint2 key = samplerKey(rp.seed, pixel, sample);
+        const int x = pixel % rp.width, y = pixel / rp.width;
+        // core/integrator.cc:84-86, cameras/perspective.cc:53-74
+        const float f0 = sample1D(key, kDimFilm), f1 = sample1D(key, kDimFilm + 1);
+        double pc[3];
+        applyPoint(cam.r2c, (double)x + (double)f0, (double)y + (double)f1, 0.0, pc);
+        double nrm = sqrt(pc[0] * pc[0] + pc[1] * pc[1] + pc[2] * pc[2]);
+        double dir[3] = {pc[0] / nrm, pc[1] / nrm, pc[2] / nrm};
+        double org[3] = {0.0, 0.0, 0.0};
+        if (cam.lens_radius > 0.0) {
+            float lx, ly;
+            concentricDisk(sample1D(key, kDimLens), sample1D(key, kDimLens + 1), &lx, &ly);
+            const double ft = cam.focal / dir[2];
+            const double pf[3] = {dir[0] * ft, dir[1] * ft, dir[2] * ft};
+            org[0] = cam.lens_radius * lx; org[1] = cam.lens_radius * ly;
+            double d2[3] = {pf[0] - org[0], pf[1] - org[1], pf[2] - org[2]};
+            nrm = sqrt(d2[0] * d2[0] + d2[1] * d2[1] + d2[2] * d2[2]);
+            dir[0] = d2[0] / nrm; dir[1] = d2[1] / nrm; dir[2] = d2[2] / nrm;
+        }
+        double ow[3], dw[3];
+        applyPoint(cam.c2w, org[0], org[1], org[2], ow);
+        applyVector(cam.c2w, dir[0], dir[1], dir[2], dw);
+        const double s = 1.0 / sqrt(dw[0] * dw[0] + dw[1] * dw[1] + dw[2] * dw[2]);   // Ray ctor, core/ray.cc:15
+        const uint32_t filmIndex = (uint32_t)y * (uint32_t)rp.width + (uint32_t)(rp.width - 1 - x);
+        const float fw = filterWeight(rp, f0 - 0.5f, f1 - 0.5f);
+        writeRay(q.ray[cur], dst + i, v3((float)ow[0], (float)ow[1], (float)ow[2]),
+                 v3((float)(dw[0] * s), (float)(dw[1] * s), (float)(dw[2] * s)), filmIndex, kRayInf);
+        writeState(q.state[cur], dst + i, v3(1.f), key, 0u, fw);
+    }
+}
+
+// ---- K4: shade ---------------------------------------------------------------------------------------
+__device__ __forceinline__ TriGeom loadTri(const ShadeTri* tris, int prim) {
+    const float4* p = (const float4*)(tris + prim);
+    const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3), e = __ldg(p + 4), f = __ldg(p + 5), g = __ldg(p + 6);
+    TriGeom t;
+    t.p0 = v3(a.x, a.y, a.z); t.e1 = v3(a.w, b.x, b.y); t.e2 = v3(b.z, b.w, c.x);
+    t.ng = v3(c.y, c.z, c.w); t.fn = v3(d.x, d.y, d.z); t.area = d.w;
+    t.ss = v3(e.x, e.y, e.z); t.material = __float_as_int(e.w);
+    t.ts = v3(f.x, f.y, f.z); t.light = __float_as_int(f.w);
+    t.has_normals = __float_as_int(g.x);
+    return t;
 }
 
 // Texture<Spectrum>::evaluate for the two texture plugins (textures/bitmap.cc:22-26, checkerboard.cc:31-40)
@@ -235,88 +325,92 @@ __device__ __forceinline__ V3 evalTexture(const DeviceScene& sc, int id, float u
            (1.f - ds) * dt * texTexel(sc.texels, t, si, ti + 1) + ds * dt * texTexel(sc.texels, t, si + 1, ti + 1);
 }
 
-// MINB: resident CTAs per SM the kernel is compiled for.  4 (128 registers, 300 B of spills) beats 3 (167
-// registers, no spills) by 4 % on the diffuse Cornell box and ties on the glossy one; 5 and 6 lose 4-11 %
-// (tools/sweep_shade.py on a measurement build).
-// TYPES: the lobe types (bit t = SPB_MAT_t) that can occur in the scene.  The kernel is instantiated for the sets
-// the BASELINE scenes need -- Lambertian only (C1, C3, C5's torus is rough dielectric: generic), the glossy Cornell
-// box's {diffuse, dielectric, rough conductor, conductor} -- and for all seven; every lobe outside the set is
-// compiled out (shading.cuh, lobeLive), which is what the registers of this kernel are spent on.
-constexpr int kShadeMinbDiffuse = 4;      // measured on the diffuse Cornell box: 4 -> 1729, 5 -> 1687, 6 -> 1625 Msamples/s (generic kernel: 1462)
+// ---- material-sorted shading -------------------------------------------------------------------------------------------
+// A scene with more than one BSDF type is shaded by ONE KERNEL INSTANCE PER BUCKET: classifyKernel sorts the queue
+// positions of an iteration into index lists by the BSDF type of the surface that was hit, and each list is shaded by
+// the instance that contains the code of that lobe only.  ncu on the r01 kernel (one instance carrying every lobe of
+// the glossy Cornell box, sorted per 512-entry tile inside the kernel): 15 % issue-slot utilisation with 12.8 of every
+// 16 stall cycles waiting for INSTRUCTIONS -- warps on different materials thrash the instruction cache
+// (profiles/r02a_shade_glossy_ncu.txt).  Records are 32-byte aligned, so gathering them through an index list costs
+// no extra sectors.  A scene with a single BSDF type skips the classification and shades in queue order.
+enum { kBucketMiss = 0, kBucketNone = 1, kBucketMat0 = 2, kNumBuckets = 9 };      // 2 + SPB_MAT_*
+
+struct ShadeLists {
+    uint32_t* index;       // kNumBuckets lists of `stride` entries each (only the buckets a scene can produce are touched)
+    uint32_t* count;       // kNumBuckets counters
+    uint32_t  stride;
+};
+
+__global__ void __launch_bounds__(256) classifyKernel(Queues q, int cur, const uint8_t* __restrict__ primBucket, ShadeLists L) {
+    const uint32_t n = q.count[cur];
+    const int lane = threadIdx.x & 31;
+    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += gridDim.x * blockDim.x) {
+        const uint32_t i = base + (uint32_t)lane;
+        uint32_t key = 0xffu;
+        if (i < n) {
+            const int prim = __float_as_int(__ldcs((const float*)(q.hit + i) + 1));
+            key = prim < 0 ? (uint32_t)kBucketMiss : (uint32_t)__ldg(primBucket + prim);
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        if (key == 0xffu) continue;
+        const int leader = __ffs(peers) - 1;
+        uint32_t at = 0u;
+        if (lane == leader) at = atomicAdd(L.count + key, (uint32_t)__popc(peers));
+        at = __shfl_sync(peers, at, leader);
+        L.index[(size_t)key * L.stride + at + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = i;
+    }
+}
+
+// TYPES: the lobe types (bit t = SPB_MAT_t) this instance contains; every other lobe is compiled out (shading.cuh,
+// lobeLive).  MINB: resident CTAs per SM it is compiled for.  LIST: shade the queue positions of an index list
+// (a bucket of classifyKernel) instead of the whole queue in order.
+constexpr int kShadeMinbDiffuse = 4;
 constexpr uint32_t kTypesAll = 0x7fu;
 constexpr uint32_t kTypesDiffuse = 1u << SPB_MAT_DIFFUSE;
-constexpr uint32_t kTypesGlossy = (1u << SPB_MAT_DIFFUSE) | (1u << SPB_MAT_DIELECTRIC) | (1u << SPB_MAT_ROUGHCONDUCTOR) | (1u << SPB_MAT_CONDUCTOR);
+constexpr uint32_t typeClosure(int t) {     // what a material of type t can turn into (makeBsdf: alpha 0 -> the specular lobe, a black coating -> Lambertian)
+    return (1u << t) | (t == SPB_MAT_ROUGHCONDUCTOR ? 1u << SPB_MAT_CONDUCTOR : 0u) | (t == SPB_MAT_ROUGHDIELECTRIC ? 1u << SPB_MAT_DIELECTRIC : 0u) |
+           (t == SPB_MAT_ROUGHPLASTIC ? 1u << SPB_MAT_DIFFUSE : 0u);
+}
 
-template <bool SORT, int MINB = 4, uint32_t TYPES = kTypesAll>
-__global__ void __launch_bounds__(128, MINB) shadeKernel(RenderParamsPOD rp, DeviceScene sc, PathSoA paths, Queues q, int cur) {
-    const uint32_t n = q.count[cur];
-    const spb_ray_f32* rays = q.ray[cur];
-    spb_ray_f32* nextQ = q.ray[cur ^ 1];
+template <uint32_t TYPES, int MINB, bool LIST>
+__global__ void __launch_bounds__(128, MINB) shadeKernel(RenderParamsPOD rp, DeviceScene sc, Queues q, float4* film, int cur,
+                                                       const uint32_t* __restrict__ list, const uint32_t* __restrict__ listCount) {
+    const uint32_t n = LIST ? *listCount : q.count[cur];
+    const float4* rays = q.ray[cur];
+    const float4* states = q.state[cur];
+    float4* nextQ = q.ray[cur ^ 1];
+    float4* nextS = q.state[cur ^ 1];
     uint32_t* nextCount = q.count + (cur ^ 1);
-    // Material-sorted shading: the block takes a tile of kTile queue entries, buckets them by the BSDF type of
-    // the surface that was hit (counting sort in shared memory, one warp-aggregated atomic per key and warp)
-    // and shades them in bucket order, so a warp runs ONE material's code instead of the sum of all of them
-    // (the microfacet lobes cost ~10x the Lambertian one).  SORT = false (every material has the same BSDF
-    // type) shades in queue order.  Whole warps iterate together so that the warp-aggregated queue pushes see
-    // converged lanes.
-    constexpr uint32_t kTile = SORT ? 512 : 128, kPer = kTile / 128;
-    __shared__ uint32_t s_cnt[16], s_start[16];
-    __shared__ uint16_t s_order[kTile];
-    const uint32_t nTiles = (n + kTile - 1) / kTile;
-    for (uint32_t tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
-      const uint32_t tileBase = tile * kTile;
-      if (SORT) {
-      if (threadIdx.x < 16) s_cnt[threadIdx.x] = 0u;
-      __syncthreads();
-      uint32_t keys[kPer], ranks[kPer];
-#pragma unroll
-      for (uint32_t k = 0; k < kPer; k++) {
-          const uint32_t e = tileBase + k * 128u + threadIdx.x;
-          uint32_t key = 15u;                                        // past the end of the queue: sorted last, skipped
-          if (e < n) {
-              const int prim = __float_as_int(((const float*)(q.hit + e))[1]);
-              key = 0u;                                              // escaped rays
-              if (prim >= 0) {
-                  const int mat = __ldg((const int*)(sc.tris + prim) + 19);       // ShadeTri::material
-                  key = (mat >= 0 && mat < sc.n_mats) ? (uint32_t)(sc.mats[mat].type + 2) & 15u : 1u;
-              }
-          }
-          const unsigned peers = __match_any_sync(0xffffffffu, key);
-          const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
-          uint32_t r = 0u;
-          if (lane == leader) r = atomicAdd(&s_cnt[key], (uint32_t)__popc(peers));
-          r = __shfl_sync(0xffffffffu, r, leader);
-          keys[k] = key; ranks[k] = r + (uint32_t)__popc(peers & ((1u << lane) - 1u));
-      }
-      __syncthreads();
-      if (threadIdx.x == 0) { uint32_t run = 0u; for (int j = 0; j < 16; j++) { s_start[j] = run; run += s_cnt[j]; } }
-      __syncthreads();
-#pragma unroll
-      for (uint32_t k = 0; k < kPer; k++) s_order[s_start[keys[k]] + ranks[k]] = (uint16_t)(k * 128u + threadIdx.x);
-      __syncthreads();
-      }
-      for (uint32_t k = 0; k < kPer; k++) {
-        const uint32_t i = tileBase + (SORT ? (uint32_t)s_order[k * 128u + threadIdx.x] : k * 128u + threadIdx.x);
-        const bool valid = i < n;
+    // whole warps iterate together so that the warp-aggregated queue pushes see converged lanes
+    for (uint32_t base = blockIdx.x * 128u; base < n; base += gridDim.x * 128u) {
+      {
+        const uint32_t j = base + threadIdx.x;
+        const bool valid = j < n;
+        const uint32_t i = (LIST && valid) ? __ldg(list + j) : j;
         bool pushNext = false, pushShadow = false, pushMis = false;
         V3 nO = v3(0.f), nD = v3(0.f), sO = v3(0.f), sD = v3(0.f), mO = v3(0.f), mD = v3(0.f);
         float sT = 0.f;
         V3 sC = v3(0.f), mC = v3(0.f);
         int mExpect = -1;
-        uint32_t slot = 0;
+        uint32_t pix = 0, flags = 0;
+        uint2 key = make_uint2(0u, 0u);
+        float fw = 0.f;
+        V3 beta = v3(0.f);
         if (valid) {
-            const float4 r0 = __ldcs((const float4*)(rays + i)), r1 = __ldcs((const float4*)(rays + i) + 1);
+            const float4 r0 = __ldcs(rays + 2 * i), r1 = __ldcs(rays + 2 * i + 1);
+            const float4 s0 = __ldcs(states + 2 * i), s1 = __ldcs(states + 2 * i + 1);
             const float4 hv = __ldcs((const float4*)(q.hit + i));
-            slot = __float_as_uint(r1.z);
+            pix = __float_as_uint(r1.z);
             const V3 d = v3(r0.w, r1.x, r1.y);
             const int prim = __float_as_int(hv.y);
-            uint32_t flags = paths.flags[slot];
-            const int bounces = (int)(flags & 0xffu);
-            const bool specularBounce = (flags >> 8) & 1u;
+            flags = __float_as_uint(s1.x);
+            fw = s1.y;
+            key = make_uint2(__float_as_uint(s0.w), __float_as_uint(s1.z));
+            const int bounces = (int)(flags & 0xfffu);
+            const bool specularBounce = (flags >> 12) & 1u;
             const uint32_t vertex = flags >> 16;
-            V3 beta = v3(paths.beta[0][slot], paths.beta[1][slot], paths.beta[2][slot]);
+            beta = v3(s0.x, s0.y, s0.z);
             V3 Ladd = v3(0.f);
-            const uint32_t key = paths.key[slot];
             const uint32_t dim = kDimBounce0 + vertex * kDimsPerBounce;
 
             // directlighting (integrators/directlighting/directlighting.cc:21-57): emitted light only at depth 0, one
@@ -475,7 +569,7 @@ __global__ void __launch_bounds__(128, MINB) shadeKernel(RenderParamsPOD rp, Dev
                             if (!isBlack(f) && pdf > 0.f) {
                                 beta = beta * f * (absDot(wi, sp.ns) / pdf);
                                 nO = offsetRayOrigin(sp.p, sp.ng, wi); nD = wi; pushNext = true;
-                                flags = (uint32_t)(bounces + 1) | 0x100u | ((vertex + 1u) << 16);
+                                flags = (uint32_t)(bounces + 1) | 0x1000u | ((vertex + 1u) << 16);
                             }
                         } else if (!isBlack(f) && pdf != 0.f) {
                             beta = beta * f * (absDot(wi, sp.ns) / pdf);
@@ -487,57 +581,51 @@ __global__ void __launch_bounds__(128, MINB) shadeKernel(RenderParamsPOD rp, Dev
                             }
                             if (alive) {
                                 nO = offsetRayOrigin(sp.p, sp.ng, wi); nD = wi; pushNext = true;
-                                flags = (uint32_t)(bounces + 1) | ((sampled & kBxSpecular) ? 0x100u : 0u) | ((vertex + 1u) << 16);
+                                flags = (uint32_t)(bounces + 1) | ((sampled & kBxSpecular) ? 0x1000u : 0u) | ((vertex + 1u) << 16);
                             }
                         }
                     }
                 }
             }
-            if (!isBlack(Ladd)) { paths.L[0][slot] += Ladd.x; paths.L[1][slot] += Ladd.y; paths.L[2][slot] += Ladd.z; }
-            if (pushNext) {
-                paths.beta[0][slot] = beta.x; paths.beta[1][slot] = beta.y; paths.beta[2][slot] = beta.z;
-                paths.flags[slot] = flags;
-            }
+            // K5: this vertex's emitted light, and -- when the path ends here -- the sample's filter weight
+            // (Film::addPixel, core/film.cc:65-74: img += w L, wsum += w), in one reduction
+            if (!pushNext || !isBlack(Ladd)) filmAdd(film, pix, fw * Ladd.x, fw * Ladd.y, fw * Ladd.z, pushNext ? 0.f : fw);
+            sC = sC * fw; mC = mC * fw;
         }
         __syncwarp();
         const uint32_t in = queuePush(nextCount, pushNext);
-        if (pushNext) writeRay(nextQ, in, nO, nD, slot, kRayInf);
+        if (pushNext) { writeRay(nextQ, in, nO, nD, pix, kRayInf); writeState(nextS, in, beta, key, flags, fw); }
         __syncwarp();
         const uint32_t is = queuePush(q.count + 2, pushShadow);
-        if (pushShadow) { writeRay(q.shadow, is, sO, sD, slot, sT); q.shadowC[is] = make_float4(sC.x, sC.y, sC.z, 0.f); }
+        if (pushShadow) { writeRay(q.shadow, is, sO, sD, pix, sT); q.shadowC[is] = make_float4(sC.x, sC.y, sC.z, 0.f); }
         __syncwarp();
         const uint32_t im = queuePush(q.count + 3, pushMis);
-        if (pushMis) { writeRay(q.mis, im, mO, mD, slot, kRayInf); q.misC[im] = make_float4(mC.x, mC.y, mC.z, __uint_as_float((uint32_t)mExpect)); }
+        if (pushMis) { writeRay(q.mis, im, mO, mD, pix, kRayInf); q.misC[im] = make_float4(mC.x, mC.y, mC.z, __uint_as_float((uint32_t)mExpect)); }
         __syncwarp();
       }
-      if (SORT) __syncthreads();      // s_order / s_cnt are rewritten by the next tile
     }
 }
 
-// after a bounce: fold the queue sizes into the statistics and clear the consumed counters
-__global__ void bounceEndKernel(Queues q, int cur, unsigned long long* stats) {
-    stats[1] += q.count[cur]; stats[2] += q.count[2]; stats[3] += q.count[3];
-    q.count[cur] = 0u; q.count[2] = 0u; q.count[3] = 0u;
-}
-
-// ---- K5: film --------------------------------------------------------------------------------------
-__device__ __forceinline__ float filterWeight(const RenderParamsPOD& rp, float dx, float dy) {
-    switch (rp.filter) {
-    case SPB_FILTER_TENT: return fmaxf(0.f, rp.frx - fabsf(dx)) * fmaxf(0.f, rp.fry - fabsf(dy));                 // filters/tent.cc:27-30
-    case SPB_FILTER_GAUSSIAN: return fmaxf(0.f, expf(-rp.fbeta * dx * dx) - rp.fexpx) * fmaxf(0.f, expf(-rp.fbeta * dy * dy) - rp.fexpy);  // gaussian.cc:34-40
-    default: return 1.f;                                                                                             // filters/box.cc:22
+// escaped rays of a classified iteration: only the environment answers (path.cc:62-65, directlighting.cc:30-35), and the path ends
+__global__ void __launch_bounds__(256) shadeMissKernel(RenderParamsPOD rp, DeviceScene sc, Queues q, float4* film, int cur,
+                                                     const uint32_t* __restrict__ list, const uint32_t* __restrict__ listCount) {
+    const uint32_t n = *listCount;
+    int nEnv = 0;
+    if (sc.env.present) for (int l = 0; l < sc.n_lights; l++) nEnv += (sc.lights[l].type == SPB_LIGHT_ENVMAP);
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const uint32_t i = __ldg(list + j);
+        const float4 r0 = __ldcs(q.ray[cur] + 2 * i), r1 = __ldcs(q.ray[cur] + 2 * i + 1);
+        const float4 s0 = __ldcs(q.state[cur] + 2 * i), s1 = __ldcs(q.state[cur] + 2 * i + 1);
+        const uint32_t flags = __float_as_uint(s1.x);
+        const float fw = s1.y;
+        V3 L = v3(0.f);
+        if (nEnv > 0 && (rp.integrator == SPB_INTEGRATOR_DIRECT || (flags & 0xfffu) == 0u || ((flags >> 12) & 1u)))
+            L = v3(s0.x, s0.y, s0.z) * envLe(sc.env, v3(r0.w, r1.x, r1.y)) * (float)nEnv;
+        filmAdd(film, __float_as_uint(r1.z), fw * L.x, fw * L.y, fw * L.z, fw);
     }
 }
-__global__ void __launch_bounds__(256) filmKernel(RenderParamsPOD rp, PathSoA paths, float4* film, int64_t n) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t pixel = paths.pixel[i], key = paths.key[i];
-    const int x = pixel % rp.width, y = pixel / rp.width;
-    const float w = filterWeight(rp, sample1D(key, kDimFilm) - 0.5f, sample1D(key, kDimFilm + 1) - 0.5f);
-    float Lr = paths.L[0][i], Lg = paths.L[1][i], Lb = paths.L[2][i];
-    float4* dst = film + (size_t)y * rp.width + (rp.width - 1 - x);      // core/integrator.cc:88: pixel (width - x - 1, y)
-    atomicAdd(dst, make_float4(w * Lr, w * Lg, w * Lb, w));
-}
+
+// ---- film read-out ------------------------------------------------------------------------------------
 __global__ void resolveKernel(const float4* film, float* rgb, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -588,6 +676,8 @@ static void freeScene(RenderState* R) {
     if (R->d_texs) cudaFree(R->d_texs);
     if (R->d_texels) cudaFree(R->d_texels);
     if (R->d_uvs) cudaFree(R->d_uvs);
+    if (R->d_prim_bucket) cudaFree(R->d_prim_bucket);
+    R->d_prim_bucket = nullptr;
     R->d_tris = nullptr; R->d_vnormals = nullptr; R->d_mats = nullptr; R->d_lights = nullptr;
     R->d_mat_tex = nullptr; R->d_texs = nullptr; R->d_texels = nullptr; R->d_uvs = nullptr;
 }
@@ -600,11 +690,21 @@ static void freeEnv(RenderState* R) {
 void renderStateDestroy(spb_ctx* ctx) {
     RenderState* R = ctx->render;
     if (!R) return;
+    workerDrain(ctx, R);
+    workerStop(R);
     freeScene(R); freeEnv(R);
+    if (R->graph_exec) cudaGraphExecDestroy(R->graph_exec);
     if (R->d_film) cudaFree(R->d_film);
     if (R->d_pool) cudaFree(R->d_pool);
-    if (R->d_stats) cudaFree(R->d_stats);
+    if (R->d_ctl) cudaFree(R->d_ctl);
     if (R->d_cursor) cudaFree(R->d_cursor);
+    if (R->d_scratch) cudaFree(R->d_scratch);
+    if (R->d_lists) cudaFree(R->d_lists);
+    if (R->d_list_count) cudaFree(R->d_list_count);
+    if (R->h_status) cudaFreeHost(R->h_status);
+    for (cudaEvent_t e : R->poll) if (e) cudaEventDestroy(e);
+    if (R->ev_r0) cudaEventDestroy(R->ev_r0);
+    if (R->ev_r1) cudaEventDestroy(R->ev_r1);
     if (R->comm && R->nccl_lib) {
         typedef int (*destroy_t)(void*);
         destroy_t f = (destroy_t)dlsym(R->nccl_lib, "ncclCommDestroy");
@@ -614,7 +714,15 @@ void renderStateDestroy(spb_ctx* ctx) {
     ctx->render = nullptr;
 }
 
-void renderSceneChanged(spb_ctx* ctx) { if (ctx->render) ctx->render->scene_dirty = true; }
+// Geometry, attributes, materials, lights, textures or the environment changed: what spb_render_begin uploaded is stale
+// (or, after spb_scene_set_triangles, freed).  Rendering needs a new spb_render_begin (SPB_ERR_INVALID otherwise).
+void renderSceneChanged(spb_ctx* ctx) {
+    RenderState* R = ctx->render;
+    if (!R) return;
+    workerDrain(ctx, R);
+    R->scene_dirty = true;
+    R->begun = false;
+}
 
 namespace {
 struct D3 { double x, y, z; };
@@ -718,17 +826,23 @@ static int uploadScene(spb_ctx* ctx, RenderState* R) {
         SPB_CUDA(ctx, cudaMemcpy(R->d_uvs, uv.data(), uv.size() * sizeof(float), cudaMemcpyHostToDevice));
         R->ds.mat_tex = R->d_mat_tex; R->ds.texs = R->d_texs; R->ds.texels = R->d_texels; R->ds.uvs = R->d_uvs;
     }
-    R->sort_materials = false;
-    for (const spb_material& m : R->mats) if (m.type != R->mats[0].type) R->sort_materials = true;
-    // every lobe type a material can turn into (makeBsdf: alpha 0 -> the specular lobe, a black coating -> Lambertian)
+    // every lobe type a material can turn into, and the shading bucket of every triangle
     R->type_mask = 0u;
-    for (const spb_material& m : R->mats) {
-        if (m.type < 0 || m.type > 6) continue;
-        R->type_mask |= 1u << m.type;
-        if (m.type == SPB_MAT_ROUGHCONDUCTOR) R->type_mask |= 1u << SPB_MAT_CONDUCTOR;
-        if (m.type == SPB_MAT_ROUGHDIELECTRIC) R->type_mask |= 1u << SPB_MAT_DIELECTRIC;
-        if (m.type == SPB_MAT_ROUGHPLASTIC) R->type_mask |= 1u << SPB_MAT_DIFFUSE;
+    for (const spb_material& m : R->mats) if (m.type >= 0 && m.type <= 6) R->type_mask |= typeClosure(m.type);
+    R->bucket_mask = 1u << kBucketMiss;
+    if (n > 0) {
+        std::vector<uint8_t> pb((size_t)n);
+        for (int64_t i = 0; i < n; i++) {
+            const int32_t m = ctx->material_id[(size_t)i];
+            const int t = (m >= 0 && m < (int32_t)R->mats.size()) ? R->mats[(size_t)m].type : -1;
+            pb[(size_t)i] = (uint8_t)((t >= 0 && t <= 6) ? kBucketMat0 + t : kBucketNone);
+            R->bucket_mask |= 1u << pb[(size_t)i];
+        }
+        SPB_CUDA(ctx, cudaMalloc(&R->d_prim_bucket, (size_t)n));
+        SPB_CUDA(ctx, cudaMemcpy(R->d_prim_bucket, pb.data(), (size_t)n, cudaMemcpyHostToDevice));
     }
+    // a scene of Lambertian surfaces only (the diffuse Cornell boxes) is shaded in queue order by one instance
+    R->sort_materials = (R->bucket_mask & ~((1u << kBucketMiss) | (1u << (kBucketMat0 + SPB_MAT_DIFFUSE)))) != 0u;
     R->scene_dirty = false;
     return SPB_OK;
 }
@@ -837,29 +951,190 @@ static int uploadEnv(spb_ctx* ctx, RenderState* R) {
     return SPB_OK;
 }
 
-static int allocWave(spb_ctx* ctx, RenderState* R, int64_t slots) {
-    if (R->d_pool && R->slots >= slots) return SPB_OK;
+static int allocQueues(spb_ctx* ctx, RenderState* R, int64_t slots) {
+    if (R->d_pool && R->slots == slots) return SPB_OK;
+    if (R->graph_exec) { cudaGraphExecDestroy(R->graph_exec); R->graph_exec = nullptr; }
     if (R->d_pool) cudaFree(R->d_pool);
     R->d_pool = nullptr; R->slots = 0;
-    // 9 u32/float per slot + 4 queues x 32 B + hits 16 B + 2 contributions x 16 B
-    const size_t per = 9 * 4 + 4 * 32 + 16 + 2 * 16;
+    // per entry: 2 extend queues x (32 B ray + 32 B state) + 16 B hit + 2 x (32 B ray + 16 B contribution) = 240 B
+    const size_t per = 2 * 64 + 16 + 2 * 48;
     const size_t bytes = (size_t)slots * per + 4096;
     cudaError_t e = cudaMalloc(&R->d_pool, bytes);
     if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); return fail(ctx, SPB_ERR_OOM, "out of device memory for the wavefront queues"); }
     SPB_CUDA(ctx, e);
     char* p = (char*)R->d_pool;
     auto take = [&](size_t b) { void* r = p; p += (b + 255) & ~(size_t)255; return r; };
-    R->q.ray[0] = (spb_ray_f32*)take((size_t)slots * 32); R->q.ray[1] = (spb_ray_f32*)take((size_t)slots * 32);
-    R->q.shadow = (spb_ray_f32*)take((size_t)slots * 32); R->q.mis = (spb_ray_f32*)take((size_t)slots * 32);
+    for (int k = 0; k < 2; k++) { R->q.ray[k] = (float4*)take((size_t)slots * 32); R->q.state[k] = (float4*)take((size_t)slots * 32); }
+    R->q.shadow = (float4*)take((size_t)slots * 32); R->q.mis = (float4*)take((size_t)slots * 32);
     R->q.hit = (spb_hit*)take((size_t)slots * 16);
     R->q.shadowC = (float4*)take((size_t)slots * 16); R->q.misC = (float4*)take((size_t)slots * 16);
-    for (int k = 0; k < 3; k++) { R->paths.beta[k] = (float*)take((size_t)slots * 4); R->paths.L[k] = (float*)take((size_t)slots * 4); }
-    R->paths.pixel = (uint32_t*)take((size_t)slots * 4); R->paths.key = (uint32_t*)take((size_t)slots * 4);
-    R->paths.flags = (uint32_t*)take((size_t)slots * 4);
     R->q.count = (uint32_t*)take(64);
-    if ((size_t)(p - (char*)R->d_pool) > bytes + 0) { /* the 256 B rounding of 14 arrays fits in the 4 KiB slack */ }
     R->slots = slots;
     return SPB_OK;
+}
+
+// the index lists of classifyKernel: one per bucket, each able to hold a whole queue
+static int allocLists(spb_ctx* ctx, RenderState* R) {
+    if (!R->sort_materials) return SPB_OK;
+    if (R->d_lists && R->list_stride == R->slots) return SPB_OK;
+    if (R->graph_exec) { cudaGraphExecDestroy(R->graph_exec); R->graph_exec = nullptr; }
+    if (R->d_lists) cudaFree(R->d_lists);
+    R->d_lists = nullptr; R->list_stride = 0;
+    cudaError_t e = cudaMalloc(&R->d_lists, (size_t)kNumBuckets * (size_t)R->slots * sizeof(uint32_t));
+    if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); return fail(ctx, SPB_ERR_OOM, "out of device memory for the shading lists"); }
+    SPB_CUDA(ctx, e);
+    if (!R->d_list_count) { SPB_CUDA(ctx, cudaMalloc(&R->d_list_count, 16 * sizeof(uint32_t))); }
+    SPB_CUDA(ctx, cudaMemset(R->d_list_count, 0, 16 * sizeof(uint32_t)));
+    R->list_stride = R->slots;
+    return SPB_OK;
+}
+
+static int scratch(spb_ctx* ctx, RenderState* R, size_t bytes, void** out) {
+    if (R->scratch_bytes < bytes) {
+        if (R->d_scratch) cudaFree(R->d_scratch);
+        R->d_scratch = nullptr; R->scratch_bytes = 0;
+        SPB_CUDA(ctx, cudaMalloc(&R->d_scratch, bytes));
+        R->scratch_bytes = bytes;
+    }
+    *out = R->d_scratch;
+    return SPB_OK;
+}
+
+// ---- one iteration of the streaming loop on queue `cur` (enqueue only) -------------------------------------------------
+template <uint32_t TYPES, int MINB>
+static void launchShadeList(spb_ctx* ctx, RenderState* R, int cur, int bucket, cudaStream_t st) {
+    shadeKernel<TYPES, MINB, true><<<ctx->sm_count * 8, 128, 0, st>>>(R->rp, R->ds, R->q, R->d_film, cur, R->d_lists + (size_t)bucket * (size_t)R->list_stride,
+                                                                   R->d_list_count + bucket);
+}
+static int launchShade(spb_ctx* ctx, RenderState* R, int cur, cudaStream_t st, int* launches) {
+    const int grid = ctx->sm_count * 8;
+    *launches = 0;
+    if (!R->sort_materials) {
+        const int mb = ctx->opt_shade_minb > 0 ? ctx->opt_shade_minb : kShadeMinbDiffuse;
+        if (mb == 4) shadeKernel<kTypesDiffuse, 4, false><<<grid, 128, 0, st>>>(R->rp, R->ds, R->q, R->d_film, cur, nullptr, nullptr);
+        else if (mb == 6) shadeKernel<kTypesDiffuse, 6, false><<<grid, 128, 0, st>>>(R->rp, R->ds, R->q, R->d_film, cur, nullptr, nullptr);
+        else shadeKernel<kTypesDiffuse, 5, false><<<grid, 128, 0, st>>>(R->rp, R->ds, R->q, R->d_film, cur, nullptr, nullptr);
+        *launches = 1;
+    } else {
+        const ShadeLists L = {R->d_lists, R->d_list_count, (uint32_t)R->list_stride};
+        classifyKernel<<<grid, 256, 0, st>>>(R->q, cur, R->d_prim_bucket, L);
+        shadeMissKernel<<<grid, 256, 0, st>>>(R->rp, R->ds, R->q, R->d_film, cur, R->d_lists + (size_t)kBucketMiss * (size_t)R->list_stride, R->d_list_count + kBucketMiss);
+        *launches = 2;
+        const uint32_t bm = R->bucket_mask;
+        auto has = [&](int b) { return (bm >> b) & 1u; };
+        // surfaces without a material pass the path straight through: any instance does that (the Lambertian one is the smallest)
+        if (has(kBucketNone)) { launchShadeList<kTypesDiffuse, 4>(ctx, R, cur, kBucketNone, st); ++*launches; }
+        if (has(kBucketMat0 + SPB_MAT_DIFFUSE)) { launchShadeList<typeClosure(SPB_MAT_DIFFUSE), 4>(ctx, R, cur, kBucketMat0 + SPB_MAT_DIFFUSE, st); ++*launches; }
+        if (has(kBucketMat0 + SPB_MAT_DIELECTRIC)) { launchShadeList<typeClosure(SPB_MAT_DIELECTRIC), 5>(ctx, R, cur, kBucketMat0 + SPB_MAT_DIELECTRIC, st); ++*launches; }
+        if (has(kBucketMat0 + SPB_MAT_ROUGHCONDUCTOR)) { launchShadeList<typeClosure(SPB_MAT_ROUGHCONDUCTOR), 4>(ctx, R, cur, kBucketMat0 + SPB_MAT_ROUGHCONDUCTOR, st); ++*launches; }
+        if (has(kBucketMat0 + SPB_MAT_ROUGHDIELECTRIC)) { launchShadeList<typeClosure(SPB_MAT_ROUGHDIELECTRIC), 4>(ctx, R, cur, kBucketMat0 + SPB_MAT_ROUGHDIELECTRIC, st); ++*launches; }
+        if (has(kBucketMat0 + SPB_MAT_CONDUCTOR)) { launchShadeList<typeClosure(SPB_MAT_CONDUCTOR), 5>(ctx, R, cur, kBucketMat0 + SPB_MAT_CONDUCTOR, st); ++*launches; }
+        if (has(kBucketMat0 + SPB_MAT_PLASTIC)) { launchShadeList<typeClosure(SPB_MAT_PLASTIC), 5>(ctx, R, cur, kBucketMat0 + SPB_MAT_PLASTIC, st); ++*launches; }
+        if (has(kBucketMat0 + SPB_MAT_ROUGHPLASTIC)) { launchShadeList<typeClosure(SPB_MAT_ROUGHPLASTIC), 4>(ctx, R, cur, kBucketMat0 + SPB_MAT_ROUGHPLASTIC, st); ++*launches; }
+    }
+    SPB_CUDA(ctx, cudaGetLastError());
+    return SPB_OK;
+}
+
+static int enqueueIteration(spb_ctx* ctx, RenderState* R, int cur, cudaStream_t st) {
+    const int64_t cap = R->slots;
+    int rc;
+    controlKernel<<<1, 32, 0, st>>>(R->d_ctl, R->q, cur, R->d_cursor, R->d_status, R->sort_materials ? R->d_list_count : nullptr);
+    generateKernel<<<ctx->sm_count * 8, 256, 0, st>>>(R->rp, R->cam, R->q, R->d_ctl, cur);
+    SPB_CUDA(ctx, cudaGetLastError());
+    // extend
+    if ((rc = launchTrace<false>(ctx, (const spb_ray_f32*)R->q.ray[cur], cap, R->q.count + cur, HitOut{R->q.hit}, R->d_cursor, st, true))) return rc;
+    int shadeLaunches = 0;
+    if ((rc = launchShade(ctx, R, cur, st, &shadeLaunches))) return rc;
+    R->launches_per_iteration = 5 + shadeLaunches;
+    // connect + MIS (skipped by their own zero counts when empty)
+    if ((rc = launchTrace<true>(ctx, (const spb_ray_f32*)R->q.shadow, cap, R->q.count + 2, SinkShadow{R->q.shadow, R->q.shadowC, R->d_film}, R->d_cursor + 4, st, true))) return rc;
+    if ((rc = launchTrace<false>(ctx, (const spb_ray_f32*)R->q.mis, cap, R->q.count + 3, SinkMis{R->q.mis, R->q.misC, R->d_film}, R->d_cursor + 8, st, true))) return rc;
+    return SPB_OK;
+}
+
+// Runs the loop for sample indices first, first + stride, ... (count of them); host thread of the caller or of the worker.
+static int renderLoop(spb_ctx* ctx, RenderState* R, int32_t first, int32_t count, int32_t stride) {
+    cudaSetDevice(ctx->device);
+    if (!R->begun) return fail(ctx, SPB_ERR_INVALID, "spb_render_samples: the scene changed since spb_render_begin (call it again)");
+    const int64_t npix = (int64_t)R->rp.width * R->rp.height;
+    const unsigned long long total = (unsigned long long)npix * (unsigned long long)count;
+    if (total == 0) return SPB_OK;
+    cudaStream_t st = ctx->stream;
+    SPB_CUDA(ctx, cudaEventRecord(R->ev_r0, st));
+    loopBeginKernel<<<1, 1, 0, st>>>(R->d_ctl, R->q, first, stride, total, (uint32_t)R->slots, R->d_status);
+    R->launches++;
+    // every iteration before this one certainly has work (regeneration alone needs that many): no polling until then
+    const int64_t surePairs = (int64_t)((total + (unsigned long long)R->slots - 1) / (unsigned long long)R->slots + 1) / 2;
+    int rc;
+    for (int64_t pair = 0;; pair++) {
+        if (R->graph_exec) { SPB_CUDA(ctx, cudaGraphLaunch(R->graph_exec, st)); }
+        else {
+            if ((rc = enqueueIteration(ctx, R, 0, st))) return rc;
+            if ((rc = enqueueIteration(ctx, R, 1, st))) return rc;
+        }
+        R->launches += 2 * R->launches_per_iteration;
+        SPB_CUDA(ctx, cudaEventRecord(R->poll[pair & 3], st));
+        if (pair >= surePairs && pair >= 1) {
+            // the PREVIOUS pair has finished (this one keeps the GPU busy meanwhile); the flag only ever goes 0 -> 1 within a call
+            SPB_CUDA(ctx, cudaEventSynchronize(R->poll[(pair - 1) & 3]));
+            if (*(volatile uint32_t*)R->h_status) break;
+        }
+    }
+    SPB_CUDA(ctx, cudaEventRecord(R->ev_r1, st));
+    SPB_CUDA(ctx, cudaStreamSynchronize(st));
+    SPB_CUDA(ctx, cudaGetLastError());
+    if (!*(volatile uint32_t*)R->h_status) return fail(ctx, SPB_ERR_CUDA, "internal: the streaming loop ended with paths in flight");
+    float ms = 0.f;
+    SPB_CUDA(ctx, cudaEventElapsedTime(&ms, R->ev_r0, R->ev_r1));
+    R->render_ms += ms;
+    return SPB_OK;
+}
+
+// ---- the render worker --------------------------------------------------------------------------------------------------
+static void workerMain(RenderWorker* w) {
+    for (;;) {
+        std::function<int()> task;
+        {
+            std::unique_lock<std::mutex> lk(w->mu);
+            w->cv.wait(lk, [&] { return w->stop || !w->tasks.empty(); });
+            if (w->tasks.empty()) return;
+            task = std::move(w->tasks.front());
+            w->tasks.pop_front();
+        }
+        const int rc = task();
+        {
+            std::lock_guard<std::mutex> lk(w->mu);
+            if (rc != SPB_OK && w->firstError == SPB_OK) w->firstError = rc;
+            w->pending--;
+        }
+        w->cvDone.notify_all();
+    }
+}
+static void workerSubmit(spb_ctx* ctx, RenderState* R, std::function<int()> fn) {
+    if (!R->worker) { R->worker = new RenderWorker(); R->worker->th = std::thread(workerMain, R->worker); }
+    RenderWorker* w = R->worker;
+    { std::lock_guard<std::mutex> lk(w->mu); w->tasks.push_back(std::move(fn)); w->pending++; }
+    w->cv.notify_one();
+}
+// Waits for everything handed to the worker; returns (and clears) the first error a task reported.
+static int workerDrain(spb_ctx* ctx, RenderState* R) {
+    if (!R || !R->worker) return SPB_OK;
+    RenderWorker* w = R->worker;
+    std::unique_lock<std::mutex> lk(w->mu);
+    w->cvDone.wait(lk, [&] { return w->pending == 0; });
+    const int rc = w->firstError;
+    w->firstError = SPB_OK;
+    return rc;
+}
+static void workerStop(RenderState* R) {
+    if (!R->worker) return;
+    RenderWorker* w = R->worker;
+    { std::lock_guard<std::mutex> lk(w->mu); w->stop = true; }
+    w->cv.notify_all();
+    if (w->th.joinable()) w->th.join();
+    delete w;
+    R->worker = nullptr;
 }
 
 }  // namespace spb
@@ -872,9 +1147,10 @@ int spb_scene_set_materials(spb_ctx* ctx, const spb_material* mats, int32_t n) {
     if (!ctx) return fail(nullptr, SPB_ERR_INVALID, "ctx is NULL");
     if (n < 0 || (n > 0 && !mats)) return fail(ctx, SPB_ERR_INVALID, "spb_scene_set_materials: bad arguments");
     RenderState* R = rs(ctx);
+    workerDrain(ctx, R);
     R->mats.assign(mats, mats + n);
     R->mat_tex.clear();
-    R->scene_dirty = true;
+    R->scene_dirty = true; R->begun = false;
     return SPB_OK;
 }
 
@@ -884,19 +1160,21 @@ int spb_scene_set_textures(spb_ctx* ctx, const spb_texture* texs, int32_t n, con
     for (int32_t i = 0; i < n; i++)
         if (texs[i].type != SPB_TEX_BITMAP && texs[i].type != SPB_TEX_CHECKERBOARD) return fail(ctx, SPB_ERR_INVALID, "spb_scene_set_textures: unknown texture type");
     RenderState* R = rs(ctx);
+    workerDrain(ctx, R);
     R->texs.assign(texs, texs + n);
     R->texels.assign(texels_rgb, texels_rgb + n_texels * 3);
-    R->scene_dirty = true;
+    R->scene_dirty = true; R->begun = false;
     return SPB_OK;
 }
 
 int spb_scene_set_material_textures(spb_ctx* ctx, const int32_t* tex_ids, int32_t n_mats) {
     if (!ctx) return fail(nullptr, SPB_ERR_INVALID, "ctx is NULL");
     RenderState* R = rs(ctx);
-    if (!tex_ids) { R->mat_tex.clear(); R->scene_dirty = true; return SPB_OK; }
+    workerDrain(ctx, R);
+    if (!tex_ids) { R->mat_tex.clear(); R->scene_dirty = true; R->begun = false; return SPB_OK; }
     if (n_mats != (int32_t)R->mats.size()) return fail(ctx, SPB_ERR_INVALID, "spb_scene_set_material_textures: call spb_scene_set_materials first (counts differ)");
     R->mat_tex.assign(tex_ids, tex_ids + (size_t)n_mats * 2);
-    R->scene_dirty = true;
+    R->scene_dirty = true; R->begun = false;
     return SPB_OK;
 }
 
@@ -904,8 +1182,9 @@ int spb_scene_set_lights(spb_ctx* ctx, const spb_light* lights, int32_t n) {
     if (!ctx) return fail(nullptr, SPB_ERR_INVALID, "ctx is NULL");
     if (n < 0 || (n > 0 && !lights)) return fail(ctx, SPB_ERR_INVALID, "spb_scene_set_lights: bad arguments");
     RenderState* R = rs(ctx);
+    workerDrain(ctx, R);
     R->lights.assign(lights, lights + n);
-    R->scene_dirty = true;
+    R->scene_dirty = true; R->begun = false;
     return SPB_OK;
 }
 
@@ -913,6 +1192,8 @@ int spb_scene_set_envmap(spb_ctx* ctx, const float* rgb, int32_t w, int32_t h, c
                          const double center[3], double radius) {
     if (!ctx) return fail(nullptr, SPB_ERR_INVALID, "ctx is NULL");
     RenderState* R = rs(ctx);
+    workerDrain(ctx, R);
+    R->begun = false;
     if (!rgb) { R->env_present = false; R->env_dirty = true; return SPB_OK; }
     if (w <= 0 || h <= 0) return fail(ctx, SPB_ERR_INVALID, "spb_scene_set_envmap: bad size");
     R->env_rgb.assign(rgb, rgb + (size_t)w * h * 3);
@@ -926,10 +1207,15 @@ int spb_scene_set_envmap(spb_ctx* ctx, const float* rgb, int32_t w, int32_t h, c
 int spb_render_begin(spb_ctx* ctx, const spb_render_desc* desc) {
     if (!ctx || !desc) return fail(ctx, SPB_ERR_INVALID, "spb_render_begin: NULL argument");
     if (desc->width <= 0 || desc->height <= 0 || desc->max_depth < 0) return fail(ctx, SPB_ERR_INVALID, "spb_render_begin: bad film size or depth");
+    if (desc->max_depth > 4095) return fail(ctx, SPB_ERR_INVALID, "spb_render_begin: max_depth above 4095 (the bounce counter of a path has 12 bits)");
+    if ((int64_t)desc->width * desc->height >= ((int64_t)1 << 31)) return fail(ctx, SPB_ERR_UNSUPPORTED, "spb_render_begin: more than 2^31 pixels");
     if (desc->integrator != SPB_INTEGRATOR_PATH && desc->integrator != SPB_INTEGRATOR_DIRECT) return fail(ctx, SPB_ERR_INVALID, "spb_render_begin: unknown integrator");
     if (!ctx->bvh_ready) return fail(ctx, SPB_ERR_INVALID, "spb_render_begin: no acceleration structure (call spb_bvh_build first)");
     cudaSetDevice(ctx->device);
     RenderState* R = rs(ctx);
+    int rc = workerDrain(ctx, R);
+    if (rc) return rc;
+    R->begun = false;
     for (int32_t m : ctx->material_id)
         if (m >= (int32_t)R->mats.size()) return fail(ctx, SPB_ERR_INVALID, "spb_render_begin: a triangle refers to a material that was not set");
     for (size_t i = 0; i < R->lights.size(); i++) {
@@ -939,7 +1225,6 @@ int spb_render_begin(spb_ctx* ctx, const spb_render_desc* desc) {
     }
     for (int32_t l : ctx->light_id)
         if (l >= (int32_t)R->lights.size()) return fail(ctx, SPB_ERR_INVALID, "spb_render_begin: a triangle refers to a light that was not set");
-    int rc;
     if (R->scene_dirty && (rc = uploadScene(ctx, R))) return rc;
     if (R->env_dirty || (R->env_present && !R->ds.env.present)) { if ((rc = uploadEnv(ctx, R))) return rc; }
     R->desc = *desc;
@@ -957,105 +1242,101 @@ int spb_render_begin(spb_ctx* ctx, const spb_render_desc* desc) {
     std::memcpy(R->cam.c2w, desc->camera_to_world, sizeof(double) * 16);
     R->cam.lens_radius = desc->lens_radius; R->cam.focal = desc->focal_distance;
     const int64_t npix = (int64_t)desc->width * desc->height;
+    cudaStream_t st = ctx->stream;
     if (R->film_pixels != npix) {
         if (R->d_film) cudaFree(R->d_film);
-        R->d_film = nullptr;
+        R->d_film = nullptr; R->film_pixels = 0;
+        if (R->graph_exec) { cudaGraphExecDestroy(R->graph_exec); R->graph_exec = nullptr; }
         SPB_CUDA(ctx, cudaMalloc(&R->d_film, (size_t)npix * sizeof(float4)));
         R->film_pixels = npix;
     }
-    SPB_CUDA(ctx, cudaMemsetAsync(R->d_film, 0, (size_t)npix * sizeof(float4), ctx->stream));
-    if (!R->d_stats) { SPB_CUDA(ctx, cudaMalloc(&R->d_stats, 8 * sizeof(unsigned long long))); }
+    SPB_CUDA(ctx, cudaMemsetAsync(R->d_film, 0, (size_t)npix * sizeof(float4), st));
+    if (!R->d_ctl) { SPB_CUDA(ctx, cudaMalloc(&R->d_ctl, sizeof(LoopCtl))); }
     if (!R->d_cursor) { SPB_CUDA(ctx, cudaMalloc(&R->d_cursor, 16 * sizeof(unsigned long long))); }
-    SPB_CUDA(ctx, cudaMemsetAsync(R->d_stats, 0, 8 * sizeof(unsigned long long), ctx->stream));
-    SPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    R->launches = 0; R->render_ms = 0.0; R->paths_total = 0;
-    // Set-up that would otherwise land in the first spb_render_samples: the wavefront pool (capacity for 64 spp
-    // or one full wave, whichever is smaller) and the lazy loading of the loop's kernels -- with several
-    // contexts driven from one process the driver serialises those loads across the GPUs.
-    if ((rc = allocWave(ctx, R, std::min<int64_t>(ctx->opt_wave_slots, npix * 64)))) return rc;
-    {
-        cudaFuncAttributes fa;
-        cudaFuncGetAttributes(&fa, generateKernel);
-        if (!(R->type_mask & ~kTypesDiffuse)) cudaFuncGetAttributes(&fa, shadeKernel<false, kShadeMinbDiffuse, kTypesDiffuse>);
-        else if (!(R->type_mask & ~kTypesGlossy)) { cudaFuncGetAttributes(&fa, shadeKernel<true, 4, kTypesGlossy>); cudaFuncGetAttributes(&fa, shadeKernel<false, 4, kTypesGlossy>); }
-        else { cudaFuncGetAttributes(&fa, shadeKernel<true>); cudaFuncGetAttributes(&fa, shadeKernel<false>); }
-        cudaFuncGetAttributes(&fa, bounceEndKernel);
-        cudaFuncGetAttributes(&fa, filmKernel);
-        if (ctx->sp.tri_format == 0) {
-            cudaFuncGetAttributes(&fa, traceCoopKernel<0, false, false, spb_ray_f32, HitOut, 8>);
-            cudaFuncGetAttributes(&fa, traceCoopKernel<0, true, false, spb_ray_f32, SinkShadow, 8>);
-            cudaFuncGetAttributes(&fa, traceCoopKernel<0, false, false, spb_ray_f32, SinkMis, 8>);
-        } else {
-            cudaFuncGetAttributes(&fa, traceCoopKernel<1, false, false, spb_ray_f32, HitOut, 8>);
-            cudaFuncGetAttributes(&fa, traceCoopKernel<1, true, false, spb_ray_f32, SinkShadow, 8>);
-            cudaFuncGetAttributes(&fa, traceCoopKernel<1, false, false, spb_ray_f32, SinkMis, 8>);
-        }
-        cudaGetLastError();
+    if (!R->h_status) {
+        SPB_CUDA(ctx, cudaHostAlloc(&R->h_status, 64, cudaHostAllocMapped));
+        SPB_CUDA(ctx, cudaHostGetDevicePointer(&R->d_status, R->h_status, 0));
+        for (cudaEvent_t& e : R->poll) SPB_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        SPB_CUDA(ctx, cudaEventCreate(&R->ev_r0)); SPB_CUDA(ctx, cudaEventCreate(&R->ev_r1));
     }
+    R->h_status[0] = 0u; R->h_status[1] = 0u;
+    SPB_CUDA(ctx, cudaMemsetAsync(R->d_ctl, 0, sizeof(LoopCtl), st));
+    SPB_CUDA(ctx, cudaMemsetAsync(R->d_cursor, 0, 16 * sizeof(unsigned long long), st));
+    R->launches = 0; R->render_ms = 0.0; R->reduce_ms = 0.0;
+    // The queues: one allocation sized by "wave_slots" (but never more than 64 samples of the whole image).
+    const int64_t slots = std::max<int64_t>(1024, std::min<int64_t>(ctx->opt_wave_slots, npix * 64));
+    if ((rc = allocQueues(ctx, R, slots))) return rc;
+    if ((rc = allocLists(ctx, R))) return rc;
+    SPB_CUDA(ctx, cudaMemsetAsync(R->q.count, 0, 64, st));
+    // One empty pair of iterations outside the timed region: loads every kernel of the loop (with several contexts
+    // driven from one process the driver serialises module loading across the GPUs) and fills the occupancy cache.
     R->begun = true;
+    loopBeginKernel<<<1, 1, 0, st>>>(R->d_ctl, R->q, 0, 1, 0ull, (uint32_t)R->slots, R->d_status);
+    if ((rc = enqueueIteration(ctx, R, 0, st)) || (rc = enqueueIteration(ctx, R, 1, st))) { R->begun = false; return rc; }
+    SPB_CUDA(ctx, cudaStreamSynchronize(st));
+    SPB_CUDA(ctx, cudaMemsetAsync(R->d_ctl, 0, sizeof(LoopCtl), st));
+    // ... and the same pair captured into a graph: the host re-launches it until the pipeline is empty.
+    // (every parameter of the kernels is fixed until the next spb_render_begin; the sample range of a call lives in LoopCtl)
+    if (R->graph_exec) { cudaGraphExecDestroy(R->graph_exec); R->graph_exec = nullptr; }
+    if (ctx->opt_render_graph) {
+        cudaGraph_t graph = nullptr;
+        cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+        if (e == cudaSuccess) {
+            const int r0 = enqueueIteration(ctx, R, 0, st), r1 = r0 ? r0 : enqueueIteration(ctx, R, 1, st);
+            e = cudaStreamEndCapture(st, &graph);
+            if (e == cudaSuccess && r1 == SPB_OK) e = cudaGraphInstantiate(&R->graph_exec, graph, 0);
+            else if (e == cudaSuccess) e = cudaErrorUnknown;
+            if (graph) cudaGraphDestroy(graph);
+        }
+        if (e != cudaSuccess) { cudaGetLastError(); R->graph_exec = nullptr; }      // plain launches instead
+    }
+    SPB_CUDA(ctx, cudaStreamSynchronize(st));
+    return SPB_OK;
+}
+
+static int renderArgs(spb_ctx* ctx, int32_t first, int32_t count, int32_t stride, const char* who) {
+    if (!ctx) return fail(nullptr, SPB_ERR_INVALID, "ctx is NULL");
+    RenderState* R = ctx->render;
+    if (!R || !R->begun) return fail(ctx, SPB_ERR_INVALID, std::string(who) + ": call spb_render_begin first (and again after any scene change)");
+    if (count < 0 || stride <= 0 || first < 0) return fail(ctx, SPB_ERR_INVALID, std::string(who) + ": bad sample range");
     return SPB_OK;
 }
 
 int spb_render_samples(spb_ctx* ctx, int32_t first, int32_t count, int32_t stride) {
-    if (!ctx) return fail(nullptr, SPB_ERR_INVALID, "ctx is NULL");
-    RenderState* R = ctx->render;
-    if (!R || !R->begun) return fail(ctx, SPB_ERR_INVALID, "spb_render_samples: call spb_render_begin first");
-    if (count < 0 || stride <= 0 || first < 0) return fail(ctx, SPB_ERR_INVALID, "spb_render_samples: bad sample range");
-    if (count == 0) return SPB_OK;
-    cudaSetDevice(ctx->device);
-    const int64_t npix = (int64_t)R->rp.width * R->rp.height;
-    const int64_t total = npix * count;
-    const int64_t maxSlots = ctx->opt_wave_slots;
-    const int64_t slots = std::min(total, maxSlots);
-    int rc = allocWave(ctx, R, slots);
+    int rc = renderArgs(ctx, first, count, stride, "spb_render_samples");
     if (rc) return rc;
-    cudaStream_t st = ctx->stream;
-    SPB_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
-    const int shadeGrid = ctx->sm_count * 8;
-    for (int64_t item0 = 0; item0 < total; item0 += slots) {
-        const int64_t n = std::min(slots, total - item0);
-        generateKernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(R->rp, R->cam, R->paths, R->q, item0, n, first, stride);
-        R->launches++;
-        int cur = 0;
-        for (int bounce = 0; bounce <= R->rp.max_depth; bounce++) {
-            // extend
-            if ((rc = launchTrace<false>(ctx, R->q.ray[cur], n, R->q.count + cur, HitOut{R->q.hit}, R->d_cursor, st))) return rc;
-            if (!(R->type_mask & ~kTypesDiffuse) && ctx->opt_shade_generic == 0) {
-                const int mb = ctx->opt_shade_minb > 0 ? ctx->opt_shade_minb : kShadeMinbDiffuse;
-                if (mb == 4) shadeKernel<false, 4, kTypesDiffuse><<<shadeGrid, 128, 0, st>>>(R->rp, R->ds, R->paths, R->q, cur);
-                else if (mb == 6) shadeKernel<false, 6, kTypesDiffuse><<<shadeGrid, 128, 0, st>>>(R->rp, R->ds, R->paths, R->q, cur);
-                else shadeKernel<false, 5, kTypesDiffuse><<<shadeGrid, 128, 0, st>>>(R->rp, R->ds, R->paths, R->q, cur);
-            }
-            else if (!(R->type_mask & ~kTypesGlossy) && ctx->opt_shade_generic == 0) {
-                if (R->sort_materials) shadeKernel<true, 4, kTypesGlossy><<<shadeGrid, 128, 0, st>>>(R->rp, R->ds, R->paths, R->q, cur);
-                else shadeKernel<false, 4, kTypesGlossy><<<shadeGrid, 128, 0, st>>>(R->rp, R->ds, R->paths, R->q, cur);
-            } else if (R->sort_materials) shadeKernel<true><<<shadeGrid, 128, 0, st>>>(R->rp, R->ds, R->paths, R->q, cur);
-            else shadeKernel<false><<<shadeGrid, 128, 0, st>>>(R->rp, R->ds, R->paths, R->q, cur);
-            // connect + MIS (skipped by their own zero counts when empty)
-            if ((rc = launchTrace<true>(ctx, R->q.shadow, n, R->q.count + 2, SinkShadow{R->q.shadow, R->q.shadowC, R->paths}, R->d_cursor + 4, st))) return rc;
-            if ((rc = launchTrace<false>(ctx, R->q.mis, n, R->q.count + 3, SinkMis{R->q.mis, R->q.misC, R->paths}, R->d_cursor + 8, st))) return rc;
-            bounceEndKernel<<<1, 1, 0, st>>>(R->q, cur, R->d_stats);
-            R->launches += 5;
-            cur ^= 1;
-        }
-        filmKernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(R->rp, R->paths, R->d_film, n);
-        R->launches++;
-        SPB_CUDA(ctx, cudaGetLastError());
-    }
-    SPB_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
-    SPB_CUDA(ctx, cudaStreamSynchronize(st));
-    float ms = 0.f;
-    SPB_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-    R->render_ms += ms;
-    R->paths_total += total;
+    RenderState* R = ctx->render;
+    if ((rc = workerDrain(ctx, R))) return rc;
+    return renderLoop(ctx, R, first, count, stride);
+}
+
+int spb_render_samples_async(spb_ctx* ctx, int32_t first, int32_t count, int32_t stride) {
+    int rc = renderArgs(ctx, first, count, stride, "spb_render_samples_async");
+    if (rc) return rc;
+    RenderState* R = ctx->render;
+    workerSubmit(ctx, R, [ctx, R, first, count, stride]() { return renderLoop(ctx, R, first, count, stride); });
+    return SPB_OK;
+}
+
+int spb_render_wait(spb_ctx* ctx) {
+    if (!ctx) return fail(nullptr, SPB_ERR_INVALID, "ctx is NULL");
+    return workerDrain(ctx, ctx->render);
+}
+
+static int filmReady(spb_ctx* ctx, const char* who, RenderState** out) {
+    RenderState* R = ctx->render;
+    if (!R || !R->d_film || R->film_pixels <= 0) return fail(ctx, SPB_ERR_INVALID, std::string(who) + ": no film (call spb_render_begin)");
+    const int rc = workerDrain(ctx, R);
+    if (rc) return rc;
+    cudaSetDevice(ctx->device);
+    *out = R;
     return SPB_OK;
 }
 
 int spb_film_read(spb_ctx* ctx, float* rgbw) {
     if (!ctx || !rgbw) return fail(ctx, SPB_ERR_INVALID, "spb_film_read: NULL argument");
-    RenderState* R = ctx->render;
-    if (!R || !R->begun) return fail(ctx, SPB_ERR_INVALID, "spb_film_read: no film (call spb_render_begin)");
-    cudaSetDevice(ctx->device);
+    RenderState* R; int rc;
+    if ((rc = filmReady(ctx, "spb_film_read", &R))) return rc;
     SPB_CUDA(ctx, cudaMemcpyAsync(rgbw, R->d_film, (size_t)R->film_pixels * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
     SPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return SPB_OK;
@@ -1063,35 +1344,29 @@ int spb_film_read(spb_ctx* ctx, float* rgbw) {
 
 int spb_film_resolve(spb_ctx* ctx, float* rgb) {
     if (!ctx || !rgb) return fail(ctx, SPB_ERR_INVALID, "spb_film_resolve: NULL argument");
-    RenderState* R = ctx->render;
-    if (!R || !R->begun) return fail(ctx, SPB_ERR_INVALID, "spb_film_resolve: no film (call spb_render_begin)");
-    cudaSetDevice(ctx->device);
-    float* d = nullptr;
-    SPB_CUDA(ctx, cudaMalloc(&d, (size_t)R->film_pixels * 3 * sizeof(float)));
-    resolveKernel<<<(unsigned)((R->film_pixels + 255) / 256), 256, 0, ctx->stream>>>(R->d_film, d, R->film_pixels);
+    RenderState* R; int rc;
+    if ((rc = filmReady(ctx, "spb_film_resolve", &R))) return rc;
+    void* d = nullptr;
+    if ((rc = scratch(ctx, R, (size_t)R->film_pixels * 3 * sizeof(float), &d))) return rc;
+    resolveKernel<<<(unsigned)((R->film_pixels + 255) / 256), 256, 0, ctx->stream>>>(R->d_film, (float*)d, R->film_pixels);
     R->launches++;
-    cudaError_t e = cudaMemcpyAsync(rgb, d, (size_t)R->film_pixels * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d);
-    SPB_CUDA(ctx, e);
+    SPB_CUDA(ctx, cudaMemcpyAsync(rgb, d, (size_t)R->film_pixels * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    SPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return SPB_OK;
 }
 
 static int filmEncode(spb_ctx* ctx, void* host, size_t bytesPerPixel, double invGamma, const char* what) {
     if (!ctx || !host) return fail(ctx, SPB_ERR_INVALID, std::string(what) + ": NULL argument");
-    RenderState* R = ctx->render;
-    if (!R || !R->begun) return fail(ctx, SPB_ERR_INVALID, std::string(what) + ": no film (call spb_render_begin)");
-    cudaSetDevice(ctx->device);
-    unsigned char* d = nullptr;
-    SPB_CUDA(ctx, cudaMalloc(&d, (size_t)R->film_pixels * bytesPerPixel));
+    RenderState* R; int rc;
+    if ((rc = filmReady(ctx, what, &R))) return rc;
+    void* d = nullptr;
+    if ((rc = scratch(ctx, R, (size_t)R->film_pixels * bytesPerPixel, &d))) return rc;
     const unsigned grid = (unsigned)((R->film_pixels + 255) / 256);
     if (bytesPerPixel == 4) encodeRgbeKernel<<<grid, 256, 0, ctx->stream>>>(R->d_film, (uchar4*)d, R->film_pixels);
-    else encodeLdrKernel<<<grid, 256, 0, ctx->stream>>>(R->d_film, d, invGamma, R->film_pixels);
+    else encodeLdrKernel<<<grid, 256, 0, ctx->stream>>>(R->d_film, (unsigned char*)d, invGamma, R->film_pixels);
     R->launches++;
-    cudaError_t e = cudaMemcpyAsync(host, d, (size_t)R->film_pixels * bytesPerPixel, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d);
-    SPB_CUDA(ctx, e);
+    SPB_CUDA(ctx, cudaMemcpyAsync(host, d, (size_t)R->film_pixels * bytesPerPixel, cudaMemcpyDeviceToHost, ctx->stream));
+    SPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return SPB_OK;
 }
 int spb_film_resolve_rgbe(spb_ctx* ctx, uint8_t* rgbe) { return filmEncode(ctx, rgbe, 4, 0.0, "spb_film_resolve_rgbe"); }
@@ -1102,19 +1377,14 @@ int spb_film_resolve_ldr(spb_ctx* ctx, double gamma, uint8_t* rgb8) {
 
 int spb_film_add(spb_ctx* ctx, const float* rgbw) {
     if (!ctx || !rgbw) return fail(ctx, SPB_ERR_INVALID, "spb_film_add: NULL argument");
-    RenderState* R = ctx->render;
-    if (!R || !R->begun) return fail(ctx, SPB_ERR_INVALID, "spb_film_add: no film (call spb_render_begin)");
-    cudaSetDevice(ctx->device);
-    float4* d = nullptr;
-    SPB_CUDA(ctx, cudaMalloc(&d, (size_t)R->film_pixels * sizeof(float4)));
-    cudaError_t e = cudaMemcpyAsync(d, rgbw, (size_t)R->film_pixels * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) {
-        filmAddKernel<<<(unsigned)((R->film_pixels + 255) / 256), 256, 0, ctx->stream>>>(R->d_film, d, R->film_pixels);
-        R->launches++;
-        e = cudaStreamSynchronize(ctx->stream);
-    }
-    cudaFree(d);
-    SPB_CUDA(ctx, e);
+    RenderState* R; int rc;
+    if ((rc = filmReady(ctx, "spb_film_add", &R))) return rc;
+    void* d = nullptr;
+    if ((rc = scratch(ctx, R, (size_t)R->film_pixels * sizeof(float4), &d))) return rc;
+    SPB_CUDA(ctx, cudaMemcpyAsync(d, rgbw, (size_t)R->film_pixels * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    filmAddKernel<<<(unsigned)((R->film_pixels + 255) / 256), 256, 0, ctx->stream>>>(R->d_film, (const float4*)d, R->film_pixels);
+    R->launches++;
+    SPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return SPB_OK;
 }
 
@@ -1122,13 +1392,16 @@ int spb_render_get_stats(spb_ctx* ctx, spb_render_stats* out) {
     if (!ctx || !out) return fail(ctx, SPB_ERR_INVALID, "spb_render_get_stats: NULL argument");
     RenderState* R = ctx->render;
     std::memset(out, 0, sizeof(*out));
-    if (!R || !R->begun) return SPB_OK;
+    if (!R || !R->d_ctl) return SPB_OK;
+    const int rc = workerDrain(ctx, R);
+    if (rc) return rc;
     cudaSetDevice(ctx->device);
-    unsigned long long h[8];
-    SPB_CUDA(ctx, cudaMemcpy(h, R->d_stats, sizeof(h), cudaMemcpyDeviceToHost));
-    out->paths = R->paths_total;
-    out->rays_closest = (int64_t)h[1]; out->rays_shadow = (int64_t)h[2]; out->rays_mis = (int64_t)h[3];
+    LoopCtl h;
+    SPB_CUDA(ctx, cudaMemcpy(&h, R->d_ctl, sizeof(h), cudaMemcpyDeviceToHost));
+    out->paths = (int64_t)h.stats[0];
+    out->rays_closest = (int64_t)h.stats[1]; out->rays_shadow = (int64_t)h.stats[2]; out->rays_mis = (int64_t)h.stats[3];
     out->kernel_launches = R->launches; out->render_ms = R->render_ms;
+    out->reduce_ms = R->reduce_ms; out->iterations = (int64_t)h.iterations;
     return SPB_OK;
 }
 
@@ -1137,6 +1410,9 @@ typedef struct { char internal[128]; } spbNcclUniqueId;
 typedef int (*ncclGetUniqueId_t)(spbNcclUniqueId*);
 typedef int (*ncclCommInitRank_t)(void**, int, spbNcclUniqueId, int);
 typedef int (*ncclAllReduce_t)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*ncclReduce_t)(const void*, void*, size_t, int, int, int, void*, cudaStream_t);
+typedef int (*ncclCommGetAsyncError_t)(void*, int*);
+typedef int (*ncclCommAbort_t)(void*);
 typedef int (*ncclCommDestroy_t)(void*);
 typedef const char* (*ncclGetErrorString_t)(int);
 
@@ -1192,28 +1468,89 @@ int spb_comm_init(spb_ctx* ctx, const char id[SPB_COMM_ID_BYTES], int32_t n_rank
     return SPB_OK;
 }
 
-int spb_film_allreduce(spb_ctx* ctx) {
-    if (!ctx) return fail(nullptr, SPB_ERR_INVALID, "ctx is NULL");
-    RenderState* R = ctx->render;
-    if (!R || !R->begun) return fail(ctx, SPB_ERR_INVALID, "spb_film_allreduce: no film");
-    if (!R->comm) return fail(ctx, SPB_ERR_INVALID, "spb_film_allreduce: call spb_comm_init first");
+// K7: one sum over the RGBW film per frame (ncclFloat32 = 7, ncclSum = 0), stream-ordered behind the last kernel of
+// the frame.  root < 0: ncclAllReduce (every rank ends up with the frame); root >= 0: ncclReduce (only `root` does --
+// half the traffic, and all a job that writes one image needs).  After the enqueue and again after the stream has
+// drained the communicator is asked for asynchronous errors (a peer that died, a transport fault): a film that was
+// not fully reduced must not be mistaken for a frame.
+static int ncclAsyncCheck(spb_ctx* ctx, RenderState* R, const char* where) {
+    ncclCommGetAsyncError_t ge = (ncclCommGetAsyncError_t)dlsym(R->nccl_lib, "ncclCommGetAsyncError");
+    if (!ge) return SPB_OK;
+    int async = 0;
+    const int rc = ge(R->comm, &async);
+    if (rc == 0 && (async == 0 || async == 7)) return SPB_OK;          // ncclSuccess, ncclInProgress
+    ncclGetErrorString_t es = (ncclGetErrorString_t)dlsym(R->nccl_lib, "ncclGetErrorString");
+    ncclCommAbort_t ab = (ncclCommAbort_t)dlsym(R->nccl_lib, "ncclCommAbort");
+    const int code = rc != 0 ? rc : async;
+    const std::string msg = std::string("NCCL asynchronous error ") + where + ": " + (es ? es(code) : "error");
+    if (ab) { ab(R->comm); R->comm = nullptr; }                         // the communicator is unusable from here on
+    return fail(ctx, SPB_ERR_CUDA, msg);
+}
+
+static int filmReduceNow(spb_ctx* ctx, RenderState* R, int32_t root) {
     cudaSetDevice(ctx->device);
-    ncclAllReduce_t f = (ncclAllReduce_t)dlsym(R->nccl_lib, "ncclAllReduce");
-    if (!f) return fail(ctx, SPB_ERR_UNSUPPORTED, "ncclAllReduce not found");
-    // K7: one sum over the RGBW film per frame (ncclFloat32 = 7, ncclSum = 0)
-    const int rc = f(R->d_film, R->d_film, (size_t)R->film_pixels * 4, 7, 0, R->comm, ctx->stream);
+    if (!R->comm) return fail(ctx, SPB_ERR_INVALID, "spb_film_reduce: call spb_comm_init first");
+    cudaStream_t st = ctx->stream;
+    SPB_CUDA(ctx, cudaEventRecord(R->ev_r0, st));
+    int rc;
+    if (root < 0) {
+        ncclAllReduce_t f = (ncclAllReduce_t)dlsym(R->nccl_lib, "ncclAllReduce");
+        if (!f) return fail(ctx, SPB_ERR_UNSUPPORTED, "ncclAllReduce not found");
+        rc = f(R->d_film, R->d_film, (size_t)R->film_pixels * 4, 7, 0, R->comm, st);
+    } else {
+        ncclReduce_t f = (ncclReduce_t)dlsym(R->nccl_lib, "ncclReduce");
+        if (!f) return fail(ctx, SPB_ERR_UNSUPPORTED, "ncclReduce not found");
+        rc = f(R->d_film, R->d_film, (size_t)R->film_pixels * 4, 7, 0, root, R->comm, st);
+    }
     if (rc != 0) {
         ncclGetErrorString_t es = (ncclGetErrorString_t)dlsym(R->nccl_lib, "ncclGetErrorString");
-        return fail(ctx, SPB_ERR_CUDA, std::string("ncclAllReduce: ") + (es ? es(rc) : "error"));
+        return fail(ctx, SPB_ERR_CUDA, std::string(root < 0 ? "ncclAllReduce: " : "ncclReduce: ") + (es ? es(rc) : "error"));
     }
-    SPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    SPB_CUDA(ctx, cudaEventRecord(R->ev_r1, st));
+    if ((rc = ncclAsyncCheck(ctx, R, "after the film reduce was enqueued"))) return rc;
+    // wait with a watchdog on the communicator instead of a blind synchronize: a dead peer would hang it for ever
+    for (;;) {
+        const cudaError_t q = cudaEventQuery(R->ev_r1);
+        if (q == cudaSuccess) break;
+        if (q != cudaErrorNotReady) { cudaOk(ctx, q, "cudaEventQuery(film reduce)"); return SPB_ERR_CUDA; }
+        if ((rc = ncclAsyncCheck(ctx, R, "while the film reduce was running"))) return rc;
+        std::this_thread::yield();
+    }
+    if ((rc = ncclAsyncCheck(ctx, R, "after the film reduce"))) return rc;
+    float ms = 0.f;
+    SPB_CUDA(ctx, cudaEventElapsedTime(&ms, R->ev_r0, R->ev_r1));
+    R->reduce_ms += ms;
     return SPB_OK;
 }
+
+static int reduceArgs(spb_ctx* ctx, const char* who) {
+    if (!ctx) return fail(nullptr, SPB_ERR_INVALID, "ctx is NULL");
+    RenderState* R = ctx->render;
+    if (!R || !R->d_film) return fail(ctx, SPB_ERR_INVALID, std::string(who) + ": no film");
+    if (!R->comm) return fail(ctx, SPB_ERR_INVALID, std::string(who) + ": call spb_comm_init first");
+    return SPB_OK;
+}
+
+int spb_film_reduce(spb_ctx* ctx, int32_t root) {
+    int rc = reduceArgs(ctx, "spb_film_reduce");
+    if (rc) return rc;
+    if ((rc = workerDrain(ctx, ctx->render))) return rc;
+    return filmReduceNow(ctx, ctx->render, root);
+}
+int spb_film_reduce_async(spb_ctx* ctx, int32_t root) {
+    const int rc = reduceArgs(ctx, "spb_film_reduce_async");
+    if (rc) return rc;
+    RenderState* R = ctx->render;
+    workerSubmit(ctx, R, [ctx, R, root]() { return filmReduceNow(ctx, R, root); });
+    return SPB_OK;
+}
+int spb_film_allreduce(spb_ctx* ctx) { return spb_film_reduce(ctx, -1); }
 
 int spb_comm_destroy(spb_ctx* ctx) {
     if (!ctx) return fail(nullptr, SPB_ERR_INVALID, "ctx is NULL");
     RenderState* R = ctx->render;
     if (!R || !R->comm) return SPB_OK;
+    workerDrain(ctx, R);
     ncclCommDestroy_t f = (ncclCommDestroy_t)dlsym(R->nccl_lib, "ncclCommDestroy");
     if (f) f(R->comm);
     R->comm = nullptr;

@@ -57,17 +57,25 @@ SPB_SHD uint32_t hash32(uint32_t x) {
     x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
     return x;
 }
-SPB_SHD uint32_t samplerKey(uint64_t seed, uint32_t pixel, uint32_t sample) {
-    uint32_t k = hash32((uint32_t)seed ^ 0x9e3779b9u);
-    k = hash32(k ^ (uint32_t)(seed >> 32)) + sample * 0x85ebca6bu;
-    k = hash32(k) ^ (pixel * 0xc2b2ae35u + 0x27d4eb2fu);
-    return hash32(k);
+// The key of a path is 64 bits -- one word from (seed, pixel), one from (seed, sample) -- so that a
+// 1024 x 1024 x 1024-spp image (2^30 paths) does not run into the birthday bound of a 32-bit key.
+struct Key2 { uint32_t x, y; };
+SPB_SHD Key2 samplerKey2(uint64_t seed, uint32_t pixel, uint32_t sample) {
+    const uint32_t s0 = hash32((uint32_t)seed ^ 0x9e3779b9u), s1 = hash32((uint32_t)(seed >> 32) ^ 0x85ebca6bu);
+    Key2 k;
+    k.x = hash32(hash32(pixel ^ s0) + s1);
+    k.y = hash32(hash32(sample + 0x27d4eb2fu + s1) ^ s0);
+    return k;
 }
 // uniform in [0,1) with a 24-bit mantissa (the reference draws genrand_int32 / 2^32, core/random.cc:161)
-SPB_SHD float sample1D(uint32_t key, uint32_t dim) {
-    const uint32_t h = hash32(key + dim * 0x9e3779b1u) ^ hash32(dim + 0x68bc21ebu);
+SPB_SHD float sample1D(uint32_t k0, uint32_t k1, uint32_t dim) {
+    const uint32_t h = hash32(k0 + dim * 0x9e3779b1u) ^ hash32(k1 ^ (dim * 0x68bc21ebu + 0x02e5be93u));
     return (float)(hash32(h) >> 8) * (1.0f / 16777216.0f);
 }
+#if defined(__CUDACC__)
+SPB_SHD uint2 samplerKey(uint64_t seed, uint32_t pixel, uint32_t sample) { const Key2 k = samplerKey2(seed, pixel, sample); return make_uint2(k.x, k.y); }
+SPB_SHD float sample1D(uint2 key, uint32_t dim) { return sample1D(key.x, key.y, dim); }
+#endif
 
 // sampler dimensions: 0,1 film, 2,3 lens, then kDimsPerBounce per path vertex
 enum { kDimFilm = 0, kDimLens = 2, kDimBounce0 = 4, kDimsPerBounce = 10,

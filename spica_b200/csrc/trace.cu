@@ -1,16 +1,13 @@
-// K1 trace_closest / K2 trace_any: sm_100a ray-cast kernels over the 8-wide compressed BVH.
-// Replace BVHAccel::intersectBVH x2 (reference accelerators/bvh.cc:331-387) + Triangle::intersect x2
-// (core/triangle.cc:98-178) for whole ray batches.
+// K1 trace_closest / K2 trace_any: the ray-cast entry points of the C ABI over the sm_100a kernels of
+// trace_kernels.cuh.  Replace BVHAccel::intersectBVH x2 (reference accelerators/bvh.cc:331-387) +
+// Triangle::intersect x2 (core/triangle.cc:98-178) for whole ray batches.
 //
-// Variant 1 (default) is a persistent-thread kernel: the grid is sized to the machine
-// (SMs x resident CTAs), every warp pulls rays from a global cursor with one warp-aggregated
-// atomic (ballot + popc + shuffle), and lanes whose ray has terminated are refilled while the
-// rest of the warp keeps traversing ("dynamic fetch"), so incoherent rays do not leave the warp
-// mostly idle while its longest ray finishes.  Variant 0 is the plain one-thread-per-ray kernel
-// kept as the measurement baseline.
+// The default kernel is variant 5 (traceCoopPairKernel: persistent CTAs, dynamic refill, shared-memory
+// stack, three node visits per warp-pooled float32 pre-test); variants 0-4 are the steps that led to it
+// and stay selectable for measurement (spb_set_option "trace_variant"); the 10+ measurement variants
+// are compiled only with `make EXP=1`.
 #include <algorithm>
 
-#define SPB_EXPERIMENTAL_VARIANTS 1
 #include "context.h"
 #include "trace_kernels.cuh"
 
@@ -69,25 +66,39 @@ static int traceHost(spb_ctx* ctx, const RayT* rays, int64_t n, OutT* out) {
     if (rc) return rc;
     SPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     const bool serial = ctx->opt_counters != 0;       // counters are read back per chunk
+    // On any error the pipeline is drained before returning: copies into and out of the caller's buffers must not
+    // be in flight when the caller sees the status.
+    auto drain = [&]() {
+        cudaStreamSynchronize(ctx->h2d);
+        for (int i = 0; i < spb_ctx::kPipe; i++) cudaStreamSynchronize(ctx->kstream[i]);
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamSynchronize(ctx->d2h);
+    };
+#define SPB_PIPE(call)                                                                                   \
+    do {                                                                                                 \
+        const cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) { drain(); cudaOk(ctx, e_, #call); return SPB_ERR_CUDA; }                 \
+    } while (0)
     int64_t off = 0;
     for (int c = 0; off < n; c++, off += chunk) {
         const int b = c % spb_ctx::kPipe;
         const int64_t m = std::min(chunk, n - off);
         cudaStream_t ks = serial ? ctx->stream : ctx->kstream[b];
         unsigned long long* cursor = serial ? ctx->d_work : ctx->d_work + 4 * (b + 1);
-        SPB_CUDA(ctx, cudaStreamWaitEvent(ctx->h2d, ctx->ev_k[b], 0));        // buffer b consumed
-        SPB_CUDA(ctx, cudaMemcpyAsync(ctx->d_in[b], rays + off, (size_t)m * sizeof(RayT), cudaMemcpyHostToDevice, ctx->h2d));
-        SPB_CUDA(ctx, cudaEventRecord(ctx->ev_in[b], ctx->h2d));
-        SPB_CUDA(ctx, cudaStreamWaitEvent(ks, ctx->ev_in[b], 0));
-        SPB_CUDA(ctx, cudaStreamWaitEvent(ks, ctx->ev_out[b], 0));            // previous results drained
+        SPB_PIPE(cudaStreamWaitEvent(ctx->h2d, ctx->ev_k[b], 0));        // buffer b consumed
+        SPB_PIPE(cudaMemcpyAsync(ctx->d_in[b], rays + off, (size_t)m * sizeof(RayT), cudaMemcpyHostToDevice, ctx->h2d));
+        SPB_PIPE(cudaEventRecord(ctx->ev_in[b], ctx->h2d));
+        SPB_PIPE(cudaStreamWaitEvent(ks, ctx->ev_in[b], 0));
+        SPB_PIPE(cudaStreamWaitEvent(ks, ctx->ev_out[b], 0));            // previous results drained
         rc = launchTrace<ANY>(ctx, (const RayT*)ctx->d_in[b], m, nullptr, Out{(OutT*)ctx->d_out[b]}, cursor, ks);
-        if (rc) return rc;
-        SPB_CUDA(ctx, cudaEventRecord(ctx->ev_k[b], ks));
-        SPB_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h, ctx->ev_k[b], 0));
-        SPB_CUDA(ctx, cudaMemcpyAsync(out + off, ctx->d_out[b], (size_t)m * sizeof(OutT), cudaMemcpyDeviceToHost, ctx->d2h));
-        SPB_CUDA(ctx, cudaEventRecord(ctx->ev_out[b], ctx->d2h));
-        if (serial) { SPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); rc = readCounters(ctx, m); if (rc) return rc; }
+        if (rc) { drain(); return rc; }
+        SPB_PIPE(cudaEventRecord(ctx->ev_k[b], ks));
+        SPB_PIPE(cudaStreamWaitEvent(ctx->d2h, ctx->ev_k[b], 0));
+        SPB_PIPE(cudaMemcpyAsync(out + off, ctx->d_out[b], (size_t)m * sizeof(OutT), cudaMemcpyDeviceToHost, ctx->d2h));
+        SPB_PIPE(cudaEventRecord(ctx->ev_out[b], ctx->d2h));
+        if (serial) { SPB_PIPE(cudaStreamSynchronize(ctx->stream)); rc = readCounters(ctx, m); if (rc) { drain(); return rc; } }
     }
+#undef SPB_PIPE
     SPB_CUDA(ctx, cudaStreamSynchronize(ctx->d2h));
     for (int i = 0; i < spb_ctx::kPipe; i++) SPB_CUDA(ctx, cudaStreamSynchronize(ctx->kstream[i]));
     SPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -16,6 +16,10 @@
 
 #include "bvh_layout.h"
 
+#ifndef SPB_NODE_I2F
+#define SPB_NODE_I2F 0     // 1: the r01 node test (integer-to-float conversions on the XU pipe), kept for A/B measurement builds
+#endif
+
 #if defined(__CUDACC__)
 #define SPB_HD __host__ __device__ __forceinline__
 #else
@@ -308,16 +312,54 @@ SPB_HD bool triTestRecord(const SceneParams& sp, const RayState& r, uint32_t ind
     return triTestExact(r, p0, p1, p2, t, u, v);
 }
 
+// byte j of `w` as a float32 WITHOUT an integer-to-float conversion: the byte is dropped into mantissa
+// bits 15..8 of 1.0f, which gives exactly 1 + q * 2^-15.  One PRMT on the ALU pipe instead of one I2F on
+// the XU pipe: ncu on the r01 kernel showed the XU pipe (16 lanes per clock and SM) as its busiest unit
+// (58 % over the whole kernel, saturated during node visits: 48 conversions = 384 XU cycles per
+// warp-visit against ~270 issue slots; profiles/r02a_trace_xu_pipe.md).
+// `one` = the bits of 1.0f, read from the kernel's parameter block (SceneParams::f32_one): PRMT takes ONE
+// immediate, and with a literal 0x3f800000 ptxas spends it on the constant and loads the four selectors into
+// registers with an extra IMAD.MOV each (+36 instructions per node visit); a constant-bank operand leaves
+// the immediate to the selector.
+#if defined(__CUDA_ARCH__)
+SPB_HD float byteMant(uint32_t w, int j, uint32_t one) { return __uint_as_float(__byte_perm(w, one, 0x7604u | ((uint32_t)j << 4))); }
+#else
+SPB_HD float byteMant(uint32_t w, int j, uint32_t one) { return asFloat(one | (byteOf(w, j) << 8)); }
+#endif
+
 // Tests the 8 quantised child boxes of one node; returns the hit mask in traversal layout:
 // bits 24..31 inner children at priority (slot ^ oct_inv), bits 0..23 triangles of hit leaves.
+//
+// Plane distance along the culling ray: t = q * ad + ao with ad = 2^e / d, ao = (p - o) / d.  With
+// f = 1 + q * 2^-15 (byteMant) the same value is f * AD + AO, AD = ad * 2^15 (exact: a power of two),
+// AO = ao - AD.  AO is rounded once (|error| <= |AO| * 2^-24); the near planes use AO - |AO| * 2^-23
+// and the far planes AO + |AO| * 2^-23, so the interval only ever grows: by at most 1/256 of a
+// quantisation step (plus 2^-23 of the distance to the node), which no traversal statistic notices.
 SPB_HD uint32_t nodeHitMask(const U4& n0, const U4& n1, const U4& n2, const U4& n3, const U4& n4,
-                            const RayState& r) {
+                            const RayState& r, uint32_t one) {
+#if SPB_NODE_I2F
     const float adx = r.idx * asFloat(byteOf(n0.w, 0) << 23);
     const float ady = r.idy * asFloat(byteOf(n0.w, 1) << 23);
     const float adz = r.idz * asFloat(byteOf(n0.w, 2) << 23);
     const float aox = (asFloat(n0.x) - r.cox) * r.idx;
     const float aoy = (asFloat(n0.y) - r.coy) * r.idy;
     const float aoz = (asFloat(n0.z) - r.coz) * r.idz;
+    const float anx = aox, any_ = aoy, anz = aoz, afx = aox, afy = aoy, afz = aoz;
+(void)one;
+#define SPB_Q(w, j) ((float)byteOf(w, j))
+#else
+    // 2^(e - 127 + 15); the builder keeps e - 127 <= 100, so the exponent field cannot overflow
+    const float adx = r.idx * asFloat((byteOf(n0.w, 0) + 15u) << 23);
+    const float ady = r.idy * asFloat((byteOf(n0.w, 1) + 15u) << 23);
+    const float adz = r.idz * asFloat((byteOf(n0.w, 2) + 15u) << 23);
+    const float aox = ffma(asFloat(n0.x) - r.cox, r.idx, -adx);
+    const float aoy = ffma(asFloat(n0.y) - r.coy, r.idy, -ady);
+    const float aoz = ffma(asFloat(n0.z) - r.coz, r.idz, -adz);
+    const float kUlp2 = 1.1920929e-07f;      // 2^-23
+    const float mx = fabsf(aox) * kUlp2, my = fabsf(aoy) * kUlp2, mz = fabsf(aoz) * kUlp2;
+    const float anx = aox - mx, any_ = aoy - my, anz = aoz - mz, afx = aox + mx, afy = aoy + my, afz = aoz + mz;
+#define SPB_Q(w, j) byteMant(w, j, one)
+#endif
     const bool nx = r.idx < 0.f, ny = r.idy < 0.f, nz = r.idz < 0.f;
     const uint32_t oct4 = r.oct_inv * 0x01010101u;
     uint32_t hitmask = 0;
@@ -338,18 +380,19 @@ SPB_HD uint32_t nodeHitMask(const U4& n0, const U4& n1, const U4& n2, const U4& 
 #pragma unroll
 #endif
         for (int j = 0; j < 4; j++) {
-            const float tnx = ffma((float)byteOf(nearx, j), adx, aox);
-            const float tny = ffma((float)byteOf(neary, j), ady, aoy);
-            const float tnz = ffma((float)byteOf(nearz, j), adz, aoz);
-            const float tfx = ffma((float)byteOf(farx, j), adx, aox);
-            const float tfy = ffma((float)byteOf(fary, j), ady, aoy);
-            const float tfz = ffma((float)byteOf(farz, j), adz, aoz);
+            const float tnx = ffma(SPB_Q(nearx, j), adx, anx);
+            const float tny = ffma(SPB_Q(neary, j), ady, any_);
+            const float tnz = ffma(SPB_Q(nearz, j), adz, anz);
+            const float tfx = ffma(SPB_Q(farx, j), adx, afx);
+            const float tfy = ffma(SPB_Q(fary, j), ady, afy);
+            const float tfz = ffma(SPB_Q(farz, j), adz, afz);
             const float tmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
             const float tmax = fminf(fminf(tfx, tfy), fminf(tfz, r.ctmax));
             // (unary count) << position; an empty slot has meta 0 and contributes nothing
             if (tmin <= tmax) hitmask |= shlWrap((meta4 >> (8 * j + 5)) & 7u, meta4 >> (8 * j));
         }
     }
+#undef SPB_Q
     return hitmask;
 }
 
@@ -380,7 +423,7 @@ struct Traverser {
         const WideNode* np = sp.nodes + (ngroup.x + rel);
         const U4 n0 = ldg4((const char*)np), n1 = ldg4((const char*)np + 16), n2 = ldg4((const char*)np + 32),
                  n3 = ldg4((const char*)np + 48), n4 = ldg4((const char*)np + 64);
-        const uint32_t hm = nodeHitMask(n0, n1, n2, n3, n4, r);
+        const uint32_t hm = nodeHitMask(n0, n1, n2, n3, n4, r, sp.f32_one);
         if (ctr) ctr->nodes++;
         ngroup.x = n1.x;
         ngroup.y = (hm & 0xff000000u) | (n0.w >> 24);
@@ -435,8 +478,8 @@ struct Traverser {
     SPB_HD void begin2(bool valid) { sp_ = 0; cur = 0u; finished = !valid; }
 
     SPB_HD U2 visitLoaded(const U4& n0, const U4& n1, const U4& n2, const U4& n3, const U4& n4, const RayState& r,
-                          U2* cgroup, TraceCounters* ctr) {
-        const uint32_t hm = nodeHitMask(n0, n1, n2, n3, n4, r);
+                          U2* cgroup, TraceCounters* ctr, uint32_t one) {
+        const uint32_t hm = nodeHitMask(n0, n1, n2, n3, n4, r, one);
         if (ctr) ctr->nodes++;
         cgroup->x = n1.x;
         cgroup->y = (hm & 0xff000000u) | (n0.w >> 24);
@@ -449,7 +492,7 @@ struct Traverser {
     SPB_HD U2 visitPhase(const SceneParams& sp, const RayState& r, U2* cgroup, TraceCounters* ctr) {
         const char* np = (const char*)(sp.nodes + cur);
         const U4 n0 = ldg4(np), n1 = ldg4(np + 16), n2 = ldg4(np + 32), n3 = ldg4(np + 48), n4 = ldg4(np + 64);
-        return visitLoaded(n0, n1, n2, n3, n4, r, cgroup, ctr);
+        return visitLoaded(n0, n1, n2, n3, n4, r, cgroup, ctr, sp.f32_one);
     }
 
     // g: the child group of the node just visited.  Takes the nearest pending inner child of g, or of

@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(128, MINB) traceCoopAheadKernel(SceneParams sp
                 cpAsyncWaitAll();
                 const uint4 a0 = myNode[0], a1 = myNode[128], a2 = myNode[256], a3 = myNode[384], a4 = myNode[512];
                 tg = tr.visitLoaded(U4{a0.x, a0.y, a0.z, a0.w}, U4{a1.x, a1.y, a1.z, a1.w}, U4{a2.x, a2.y, a2.z, a2.w},
-                                    U4{a3.x, a3.y, a3.z, a3.w}, U4{a4.x, a4.y, a4.z, a4.w}, r, &g, COUNT ? &c : nullptr);
+                                    U4{a3.x, a3.y, a3.z, a3.w}, U4{a4.x, a4.y, a4.z, a4.w}, r, &g, COUNT ? &c : nullptr, sp.f32_one);
             } else {
                 tg = tr.visitPhase(sp, r, &g, COUNT ? &c : nullptr);
             }
@@ -595,10 +595,10 @@ __global__ void __launch_bounds__(128, MINB) traceCoopPairKernel(SceneParams sp,
 // `cursor` points at 4 x u64: [0] the ray cursor (zeroed here), [1] node visits, [2] triangle tests.
 template <int FMT, bool ANY, bool COUNT, class RayT, class Out>
 static int launchTraceTyped(spb_ctx* ctx, const RayT* d_rays, int64_t n, const uint32_t* n_dev, Out out,
-                            unsigned long long* cursor, cudaStream_t st) {
+                            unsigned long long* cursor, cudaStream_t st, bool cursorIsClear) {
     if (n <= 0) return SPB_OK;     // n is the capacity bound when n_dev is given
     if (COUNT) { SPB_CUDA(ctx, cudaMemsetAsync(cursor, 0, 4 * sizeof(unsigned long long), st)); }
-    else { SPB_CUDA(ctx, cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), st)); }
+    else if (!cursorIsClear) { SPB_CUDA(ctx, cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), st)); }
     if (ctx->opt_variant == 0 && !n_dev) {
         const int block = std::min(ctx->opt_block, 256);
         const int64_t grid = (n + block - 1) / block;
@@ -641,12 +641,12 @@ static int launchTraceTyped(spb_ctx* ctx, const RayT* d_rays, int64_t n, const u
         const int block = 128;
         int perSm = ctx->opt_ctas_per_sm;
         if (perSm <= 0) {
-            static int cached[20] = {0};   // one per kernel instantiation; the query is slow enough to matter per chunk
-            if (cached[coop] <= 0) {
-                SPB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cached[coop], kern, block, 0));
-                if (cached[coop] < 1) cached[coop] = 1;
+            int& cached = ctx->occupancy[(const void*)kern];
+            if (cached <= 0) {
+                SPB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cached, kern, block, 0));
+                if (cached < 1) cached = 1;
             }
-            perSm = cached[coop];
+            perSm = cached;
         }
         int64_t grid = (int64_t)ctx->sm_count * perSm;
         const int64_t need = (n + block - 1) / block;
@@ -658,16 +658,18 @@ static int launchTraceTyped(spb_ctx* ctx, const RayT* d_rays, int64_t n, const u
     return SPB_OK;
 }
 
+// fromLoop: a launch of the integrator's streaming loop -- its control kernel has already cleared the cursor, and the
+// traversal counters (a ray-cast diagnostic) are never collected there.
 template <bool ANY, class RayT, class Out>
 static int launchTrace(spb_ctx* ctx, const RayT* d_rays, int64_t n, const uint32_t* n_dev, Out out,
-                       unsigned long long* cursor, cudaStream_t st) {
+                       unsigned long long* cursor, cudaStream_t st, bool fromLoop = false) {
     const int fmt = ctx->sp.tri_format;
-    if (ctx->opt_counters) {
-        return fmt == 0 ? launchTraceTyped<0, ANY, true>(ctx, d_rays, n, n_dev, out, cursor, st)
-                        : launchTraceTyped<1, ANY, true>(ctx, d_rays, n, n_dev, out, cursor, st);
+    if (ctx->opt_counters && !fromLoop) {
+        return fmt == 0 ? launchTraceTyped<0, ANY, true>(ctx, d_rays, n, n_dev, out, cursor, st, false)
+                        : launchTraceTyped<1, ANY, true>(ctx, d_rays, n, n_dev, out, cursor, st, false);
     }
-    return fmt == 0 ? launchTraceTyped<0, ANY, false>(ctx, d_rays, n, n_dev, out, cursor, st)
-                    : launchTraceTyped<1, ANY, false>(ctx, d_rays, n, n_dev, out, cursor, st);
+    return fmt == 0 ? launchTraceTyped<0, ANY, false>(ctx, d_rays, n, n_dev, out, cursor, st, fromLoop)
+                    : launchTraceTyped<1, ANY, false>(ctx, d_rays, n, n_dev, out, cursor, st, fromLoop);
 }
 
 }  // namespace spb

@@ -38,6 +38,7 @@ Emul* emul_create(const double* verts, int64_t n, int max_leaf, int bins, const 
     if (!ok) return e;
     SceneParams& sp = e->sp;
     std::memset(&sp, 0, sizeof(sp));
+    sp.f32_one = 0x3f800000u;
     sp.nodes = e->bvh.nodes.data();
     sp.tris = e->bvh.tris.data();
     sp.empty = (n == 0 || e->bvh.nodes.empty()) ? 1 : 0;

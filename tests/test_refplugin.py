@@ -88,6 +88,8 @@ def test_reference_host_textured_scene_resolves(tmp_path):
                 assert bind[slot] == -1
     assert len(s["textures"]) == 3                                   # one object per <texture> element: checker, poster, decal
 
+
+def test_reference_host_envmap_scene_resolves(tmp_path):
     """PLY mesh with vertex normals, rough dielectric, tent filter, rotated environment map: the shim's
     PODs equal what this repo's own C++ host resolves from the same file."""
     xml = os.path.join(SCENES, "envtorus.xml")
