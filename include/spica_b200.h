@@ -227,16 +227,23 @@ int spb_comm_destroy(spb_ctx* ctx);
 
 /* ---- acceleration structure ---------------------------------------------------------------- */
 
+enum {
+    SPB_BUILDER_DEVICE_SAH = 0,  /* default: top-down binned SAH (32 bins x 3 axes) + cost-optimal 8-wide collapse + quantisation, all on
+                                  * the device; nodes and triangles never leave HBM.  The same tree as the host builder (2), byte for byte. */
+    SPB_BUILDER_LBVH = 1,        /* Morton sort + Karras hierarchy + refit on the device, collapsed on the host: fastest binary build,
+                                  * worst trees; kept for measurement                                                                */
+    SPB_BUILDER_HOST_SAH = 2     /* the same binned SAH + collapse on the host cores (also used when sah_bins != 32 or SPICA_BVH_COLLAPSE=0) */
+};
 typedef struct spb_build_opts {
-    int32_t builder;        /* 0 = host binned-SAH (default; best trees), 1 = GPU LBVH (Morton sort +
-                             * Karras hierarchy + refit on the device; fastest build)            */
+    int32_t builder;        /* SPB_BUILDER_*                                                      */
     int32_t max_leaf_tris;  /* 1..3, 0 = default (3)                                             */
     int32_t sah_bins;       /* default 32                                                       */
     int32_t reserved_;
 } spb_build_opts;
 
 /* Replaces BVHAccel::construct / constructRec (accelerators/bvh.cc:139-237). opts may be NULL.
- * Builds a binary SAH tree, collapses it to the 8-wide compressed layout and uploads it. */
+ * Builds a binary SAH tree (1 primitive per leaf, like the reference), collapses it to the 8-wide compressed
+ * layout and leaves it in HBM. */
 int spb_bvh_build(spb_ctx* ctx, const spb_build_opts* opts);
 
 /* One node of a reference-built binary BVH (accelerators/bvh.h:28-52) with pointers replaced by
@@ -262,8 +269,21 @@ typedef struct spb_bvh_stats {
     int32_t tri_format;     /* 0: float32-exact vertices (48 B/tri), 1: float64 (80 B/tri)       */
     int32_t max_depth;
     double world_lo[3], world_hi[3]; /* Accelerator::worldBound (accelerators/bvh.cc:135-137)   */
+    double inflate;         /* conservative slack of the quantised boxes (scene size x 2^-19)    */
+    int32_t builder;        /* SPB_BUILDER_* that made this tree, -1: adopted (import_wide / clone) */
+    int32_t reserved_;
 } spb_bvh_stats;
 int spb_bvh_get_stats(const spb_ctx* ctx, spb_bvh_stats* out);
+
+/* One built tree for many contexts (replicas of a multi-GPU job must not each rebuild it).
+ *   spb_bvh_export      copies the 8-wide BVH out of HBM: `nodes` (spb_bvh_stats::node_bytes) and `tris` (tri_bytes).
+ *   spb_bvh_import_wide adopts an exported tree: `stats` is the exporter's spb_bvh_get_stats, unchanged; the context must have
+ *                       been given the same triangles (spb_scene_set_triangles) -- they are what the integrator shades.
+ *   spb_ctx_clone_scene same process: everything `src` holds -- triangles, attributes, the built tree, materials, lights,
+ *                       textures, environment -- is replicated on `dst`'s GPU; the tree goes device to device (NVLink peer copy). */
+int spb_bvh_export(spb_ctx* ctx, void* nodes, size_t node_capacity_bytes, void* tris, size_t tri_capacity_bytes);
+int spb_bvh_import_wide(spb_ctx* ctx, const spb_bvh_stats* stats, const void* nodes, const void* tris);
+int spb_ctx_clone_scene(spb_ctx* dst, spb_ctx* src);
 
 /* ---- ray casting ----------------------------------------------------------------------------- */
 
@@ -298,7 +318,7 @@ int spb_get_counters(spb_ctx* ctx, spb_counters* out);
  * "shade_minb" (4/5/6: occupancy the Lambertian-only shade instance is compiled for). Unknown names
  * return SPB_ERR_INVALID.
  * Environment read by spb_bvh_build / spb_bvh_import_binary: SPICA_BVH_COLLAPSE=0 selects the greedy
- * 8-wide collapse instead of the cost-optimal one. */
+ * 8-wide collapse instead of the cost-optimal one (host builder). */
 int spb_set_option(spb_ctx* ctx, const char* name, int64_t value);
 
 /* raw device memory helpers so that a host without the CUDA runtime (a plugin, ctypes) can keep

@@ -30,7 +30,8 @@ class BvhStats(C.Structure):
     _fields_ = [("n_tris", C.c_int64), ("n_wide_nodes", C.c_int64), ("n_binary_nodes", C.c_int64),
                 ("node_bytes", C.c_int64), ("tri_bytes", C.c_int64), ("sah_cost", C.c_double),
                 ("build_seconds", C.c_double), ("tri_format", C.c_int32), ("max_depth", C.c_int32),
-                ("world_lo", C.c_double * 3), ("world_hi", C.c_double * 3)]
+                ("world_lo", C.c_double * 3), ("world_hi", C.c_double * 3), ("inflate", C.c_double),
+                ("builder", C.c_int32), ("reserved_", C.c_int32)]
 
 
 class Counters(C.Structure):
@@ -84,6 +85,7 @@ _lib = None
 SYMBOLS = [
     "spb_version", "spb_last_error", "spb_ctx_create", "spb_ctx_destroy",
     "spb_scene_set_triangles", "spb_bvh_build", "spb_bvh_import_binary", "spb_bvh_get_stats",
+    "spb_bvh_export", "spb_bvh_import_wide", "spb_ctx_clone_scene",
     "spb_trace_closest", "spb_trace_closest_f64", "spb_trace_any", "spb_trace_any_f64",
     "spb_trace_closest_dev", "spb_trace_any_dev", "spb_get_counters", "spb_set_option",
     "spb_dev_alloc", "spb_dev_free", "spb_dev_upload", "spb_dev_download", "spb_dev_sync",
@@ -113,6 +115,9 @@ def load():
     L.spb_bvh_build.argtypes = [vp, C.POINTER(BuildOpts)]
     L.spb_bvh_import_binary.argtypes = [vp, vp, i64, i32]
     L.spb_bvh_get_stats.argtypes = [vp, C.POINTER(BvhStats)]
+    L.spb_bvh_export.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t]
+    L.spb_bvh_import_wide.argtypes = [vp, C.POINTER(BvhStats), vp, vp]
+    L.spb_ctx_clone_scene.argtypes = [vp, vp]
     for name in ("spb_trace_closest", "spb_trace_closest_f64", "spb_trace_any", "spb_trace_any_f64",
                  "spb_trace_closest_dev", "spb_trace_any_dev"):
         getattr(L, name).argtypes = [vp, vp, i64, vp]
@@ -210,6 +215,21 @@ class Context:
         s = BvhStats()
         self._check(self.L.spb_bvh_get_stats(self.h, C.byref(s)))
         return {k: (list(getattr(s, k)) if k.startswith("world") else getattr(s, k)) for k, _ in s._fields_}
+
+    def export_bvh(self):
+        """(stats struct, node bytes, triangle bytes) of the 8-wide BVH in HBM."""
+        s = BvhStats()
+        self._check(self.L.spb_bvh_get_stats(self.h, C.byref(s)))
+        nodes = np.empty(max(s.node_bytes, 1), dtype=np.uint8)
+        tris = np.empty(max(s.tri_bytes, 1), dtype=np.uint8)
+        self._check(self.L.spb_bvh_export(self.h, _ptr(nodes), nodes.nbytes, _ptr(tris), tris.nbytes))
+        return s, nodes[:s.node_bytes], tris[:s.tri_bytes]
+
+    def import_wide(self, stats, nodes, tris):
+        self._check(self.L.spb_bvh_import_wide(self.h, C.byref(stats), _ptr(np.ascontiguousarray(nodes)), _ptr(np.ascontiguousarray(tris))))
+
+    def clone_scene_from(self, src):
+        self._check(self.L.spb_ctx_clone_scene(self.h, src.h))
 
     def set_option(self, name, value):
         self._check(self.L.spb_set_option(self.h, name.encode(), int(value)))
@@ -435,5 +455,22 @@ def cornell_render(ctx, width, height, spp, max_depth=8, variant="diffuse", seed
         c2w, r2c = scenes.perspective_camera(scenes.look_at(cam["origin"], cam["target"], cam["up"]), cam["fov"], width, height)
         kw = dict(filter="gaussian", lens_radius=scenes.ZOO_LENS[0], focal_distance=scenes.ZOO_LENS[1]) if variant == "zoo" else {}
         ctx.render_begin(width, height, c2w, r2c, max_depth=max_depth, seed=seed, integrator=integrator, **kw)
+    ctx.render_samples(first, spp, stride)
+    return ctx.film_resolve()
+
+
+def envscene_render(ctx, width, height, spp, max_depth=8, nu=96, nv=48, seed=1, first=0, stride=1, begin=True, scene=None):
+    """Sets up spica_b200.scenes.envscene_arrays (torus + ground under an environment map) on `ctx` and renders `spp` samples."""
+    from . import scenes
+    if begin:
+        sc = scene or scenes.envscene_arrays(nu, nv)
+        ctx.set_triangles(sc["tris"], material_id=sc["material_id"], light_id=sc["light_id"])
+        ctx.set_materials(sc["materials"])
+        ctx.set_envmap(sc["env"], to_world=sc["env_to_world"], scale=sc["env_scale"], radius=sc["env_radius"])
+        ctx.set_lights([], envmap_at=0)
+        ctx.build()
+        cam = sc["camera"]
+        c2w, r2c = scenes.perspective_camera(scenes.look_at(cam["origin"], cam["target"], cam["up"]), cam["fov"], width, height)
+        ctx.render_begin(width, height, c2w, r2c, max_depth=max_depth, seed=seed, filter=sc["filter"])
     ctx.render_samples(first, spp, stride)
     return ctx.film_resolve()

@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -41,13 +42,13 @@ static void freeBvhDevice(spb_ctx* ctx) {
     renderSceneChanged(ctx);
 }
 
-static int uploadBvh(spb_ctx* ctx) {
-    freeBvhDevice(ctx);
+// fills the kernels' parameter block from ctx->bvh's statistics and the device arrays
+static void setSceneParams(spb_ctx* ctx) {
     const HostBVH& b = ctx->bvh;
     SceneParams& sp = ctx->sp;
     std::memset(&sp, 0, sizeof(sp));
     sp.f32_one = 0x3f800000u;
-    sp.empty = (b.n_tris == 0 || b.nodes.empty()) ? 1 : 0;
+    sp.empty = (b.n_tris == 0 || b.n_wide == 0) ? 1 : 0;
     sp.n_tris = (int32_t)b.n_tris;
     sp.tri_format = b.tri_format;
     sp.max_depth = b.max_depth;
@@ -56,21 +57,26 @@ static int uploadBvh(spb_ctx* ctx) {
         sp.wlo[k] = b.wlo[k] - 2.0 * b.inflate;
         sp.whi[k] = b.whi[k] + 2.0 * b.inflate;
     }
-    {
-        double m = 0.0;
-        for (int k = 0; k < 3; k++) m = std::max(m, std::max(std::abs(sp.wlo[k]), std::abs(sp.whi[k])));
-        sp.max_coord = (float)(m * 1.0000002);
-    }
-    if (!sp.empty) {
+    double m = 0.0;
+    for (int k = 0; k < 3; k++) m = std::max(m, std::max(std::abs(sp.wlo[k]), std::abs(sp.whi[k])));
+    sp.max_coord = (float)(m * 1.0000002);
+    sp.nodes = (const WideNode*)ctx->d_nodes;
+    sp.tris = ctx->d_tris;
+    ctx->bvh_ready = true;
+}
+
+// host-built tree -> device
+static int uploadBvh(spb_ctx* ctx) {
+    freeBvhDevice(ctx);
+    const HostBVH& b = ctx->bvh;
+    if (b.n_tris > 0 && !b.nodes.empty()) {
         SPB_CUDA(ctx, cudaMalloc(&ctx->d_nodes, b.nodes.size() * sizeof(WideNode)));
         SPB_CUDA(ctx, cudaMalloc(&ctx->d_tris, b.tris.size()));
         SPB_CUDA(ctx, cudaMemcpyAsync(ctx->d_nodes, b.nodes.data(), b.nodes.size() * sizeof(WideNode), cudaMemcpyHostToDevice, ctx->stream));
         SPB_CUDA(ctx, cudaMemcpyAsync(ctx->d_tris, b.tris.data(), b.tris.size(), cudaMemcpyHostToDevice, ctx->stream));
         SPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
-    sp.nodes = (const WideNode*)ctx->d_nodes;
-    sp.tris = ctx->d_tris;
-    ctx->bvh_ready = true;
+    setSceneParams(ctx);
     return SPB_OK;
 }
 
@@ -176,13 +182,28 @@ int spb_scene_set_triangle_attributes(spb_ctx* ctx, const int32_t* material_id, 
 int spb_bvh_build(spb_ctx* ctx, const spb_build_opts* opts) {
     if (!ctx) return fail(nullptr, SPB_ERR_INVALID, "ctx is NULL");
     cudaSetDevice(ctx->device);
-    spb_build_opts o = {0, 1, 32, 0};
+    spb_build_opts o = {SPB_BUILDER_DEVICE_SAH, 0, 32, 0};
     if (opts) o = *opts;
     if (o.max_leaf_tris <= 0) o.max_leaf_tris = 3;     // measured best with the cost-optimal collapse (profiles/r01g_kernel_experiments.md)
     if (o.sah_bins <= 0) o.sah_bins = 32;
-    if (o.builder != 0 && o.builder != 1) return fail(ctx, SPB_ERR_UNSUPPORTED, "spb_bvh_build: builder must be 0 (host binned SAH) or 1 (GPU LBVH)");
+    if (o.builder != SPB_BUILDER_DEVICE_SAH && o.builder != SPB_BUILDER_LBVH && o.builder != SPB_BUILDER_HOST_SAH)
+        return fail(ctx, SPB_ERR_UNSUPPORTED, "spb_bvh_build: builder must be 0 (device binned SAH), 1 (device LBVH) or 2 (host binned SAH)");
+    // the device builder sweeps 32 bins (one per lane) and always collapses cost-optimally; other settings are the host builder's
+    bool greedy = false;
+    if (const char* e = std::getenv("SPICA_BVH_COLLAPSE")) greedy = std::atoi(e) == 0;
+    if (o.builder == SPB_BUILDER_DEVICE_SAH && (o.sah_bins != 32 || greedy)) o.builder = SPB_BUILDER_HOST_SAH;
     const auto t0 = std::chrono::steady_clock::now();
-    if (o.builder == 1) {
+    if (o.builder == SPB_BUILDER_DEVICE_SAH) {
+        freeBvhDevice(ctx);
+        ctx->bin = BinaryBVH();
+        const int rc = buildSahDevice(ctx, o.max_leaf_tris);
+        if (rc) { freeBvhDevice(ctx); return rc; }
+        ctx->build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        ctx->builder_used = SPB_BUILDER_DEVICE_SAH;
+        setSceneParams(ctx);
+        return SPB_OK;
+    }
+    if (o.builder == SPB_BUILDER_LBVH) {
         const int rc = buildLbvhDevice(ctx, &ctx->bin);
         if (rc) return rc;
     } else {
@@ -192,6 +213,7 @@ int spb_bvh_build(spb_ctx* ctx, const spb_build_opts* opts) {
     if (!encode_wide(ctx->bin, ctx->verts.data(), ctx->n_tris, o.max_leaf_tris, &ctx->bvh, &err))
         return fail(ctx, SPB_ERR_UNSUPPORTED, "spb_bvh_build: " + err);
     ctx->build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    ctx->builder_used = o.builder;
     return uploadBvh(ctx);
 }
 
@@ -206,7 +228,85 @@ int spb_bvh_import_binary(spb_ctx* ctx, const spb_import_node* nodes, int64_t n_
     if (!encode_wide(ctx->bin, ctx->verts.data(), ctx->n_tris, 3, &ctx->bvh, &err))
         return fail(ctx, SPB_ERR_UNSUPPORTED, "spb_bvh_import_binary: " + err);
     ctx->build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    ctx->builder_used = SPB_BUILDER_HOST_SAH;
     return uploadBvh(ctx);
+}
+
+// ---- sharing one built tree: export / adopt (any process), clone (same process, device to device) ------------------------
+int spb_bvh_export(spb_ctx* ctx, void* nodes, size_t node_capacity, void* tris, size_t tri_capacity) {
+    if (!ctx) return fail(nullptr, SPB_ERR_INVALID, "ctx is NULL");
+    if (!ctx->bvh_ready) return fail(ctx, SPB_ERR_INVALID, "spb_bvh_export: no acceleration structure built");
+    const size_t nb = (size_t)ctx->bvh.n_wide * sizeof(WideNode), tb = (size_t)ctx->bvh.tri_bytes_device;
+    if ((nb && !nodes) || (tb && !tris) || node_capacity < nb || tri_capacity < tb)
+        return fail(ctx, SPB_ERR_INVALID, "spb_bvh_export: buffers smaller than spb_bvh_get_stats' node_bytes / tri_bytes");
+    cudaSetDevice(ctx->device);
+    if (nb) SPB_CUDA(ctx, cudaMemcpyAsync(nodes, ctx->d_nodes, nb, cudaMemcpyDeviceToHost, ctx->stream));
+    if (tb) SPB_CUDA(ctx, cudaMemcpyAsync(tris, ctx->d_tris, tb, cudaMemcpyDeviceToHost, ctx->stream));
+    SPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SPB_OK;
+}
+
+static void adoptStats(spb_ctx* ctx, const spb_bvh_stats& st) {
+    HostBVH& b = ctx->bvh;
+    b.nodes.clear(); b.tris.clear();
+    b.n_tris = st.n_tris; b.n_wide = st.n_wide_nodes; b.tri_bytes_device = st.tri_bytes; b.n_binary_nodes = st.n_binary_nodes;
+    b.tri_format = st.tri_format; b.max_depth = st.max_depth; b.sah_cost = st.sah_cost; b.inflate = st.inflate;
+    for (int k = 0; k < 3; k++) { b.wlo[k] = st.world_lo[k]; b.whi[k] = st.world_hi[k]; }
+}
+
+int spb_bvh_import_wide(spb_ctx* ctx, const spb_bvh_stats* st, const void* nodes, const void* tris) {
+    if (!ctx || !st) return fail(ctx, SPB_ERR_INVALID, "spb_bvh_import_wide: NULL argument");
+    if (st->n_tris != ctx->n_tris) return fail(ctx, SPB_ERR_INVALID, "spb_bvh_import_wide: the tree was built for a different number of triangles than spb_scene_set_triangles gave this context");
+    const size_t triSize = st->tri_format == 0 ? sizeof(TriF32) : sizeof(TriF64);
+    if (st->n_wide_nodes < 0 || st->node_bytes != st->n_wide_nodes * (int64_t)sizeof(WideNode) || st->tri_bytes != st->n_tris * (int64_t)triSize ||
+        (st->tri_format != 0 && st->tri_format != 1) || st->max_depth < 0 || st->max_depth > kStackCapacity - 2 || !(st->inflate > 0.0) ||
+        (st->n_tris > 0 && (!nodes || !tris || st->n_wide_nodes < 1)))
+        return fail(ctx, SPB_ERR_INVALID, "spb_bvh_import_wide: inconsistent description (pass the exporter's spb_bvh_get_stats unchanged)");
+    cudaSetDevice(ctx->device);
+    const auto t0 = std::chrono::steady_clock::now();
+    freeBvhDevice(ctx);
+    ctx->bin = BinaryBVH();
+    adoptStats(ctx, *st);
+    if (st->n_tris > 0) {
+        SPB_CUDA(ctx, cudaMalloc(&ctx->d_nodes, (size_t)st->node_bytes));
+        SPB_CUDA(ctx, cudaMalloc(&ctx->d_tris, (size_t)st->tri_bytes));
+        SPB_CUDA(ctx, cudaMemcpyAsync(ctx->d_nodes, nodes, (size_t)st->node_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        SPB_CUDA(ctx, cudaMemcpyAsync(ctx->d_tris, tris, (size_t)st->tri_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        SPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    ctx->builder_used = -1;
+    setSceneParams(ctx);
+    return SPB_OK;
+}
+
+int spb_ctx_clone_scene(spb_ctx* dst, spb_ctx* src) {
+    if (!dst || !src || dst == src) return fail(dst, SPB_ERR_INVALID, "spb_ctx_clone_scene: two different contexts are needed");
+    if (!src->bvh_ready) return fail(dst, SPB_ERR_INVALID, "spb_ctx_clone_scene: the source context has no acceleration structure");
+    const auto t0 = std::chrono::steady_clock::now();
+    cudaSetDevice(dst->device);
+    dst->n_tris = src->n_tris;
+    dst->verts = src->verts; dst->normals = src->normals; dst->uvs = src->uvs;
+    dst->material_id = src->material_id; dst->light_id = src->light_id;
+    freeBvhDevice(dst);
+    dst->bin = BinaryBVH();
+    spb_bvh_stats st;
+    int rc = spb_bvh_get_stats(src, &st);
+    if (rc) return fail(dst, rc, "spb_ctx_clone_scene: cannot describe the source tree");
+    adoptStats(dst, st);
+    if (st.n_tris > 0) {
+        SPB_CUDA(dst, cudaMalloc(&dst->d_nodes, (size_t)st.node_bytes));
+        SPB_CUDA(dst, cudaMalloc(&dst->d_tris, (size_t)st.tri_bytes));
+        // device to device: over NVLink when the GPUs are peers, through the host otherwise (the runtime picks)
+        SPB_CUDA(dst, cudaMemcpyPeerAsync(dst->d_nodes, dst->device, src->d_nodes, src->device, (size_t)st.node_bytes, dst->stream));
+        SPB_CUDA(dst, cudaMemcpyPeerAsync(dst->d_tris, dst->device, src->d_tris, src->device, (size_t)st.tri_bytes, dst->stream));
+        SPB_CUDA(dst, cudaStreamSynchronize(dst->stream));
+    }
+    dst->build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    dst->builder_used = -1;
+    setSceneParams(dst);
+    renderSceneClone(dst, src);
+    return SPB_OK;
 }
 
 int spb_bvh_get_stats(const spb_ctx* ctx, spb_bvh_stats* out) {
@@ -215,15 +315,17 @@ int spb_bvh_get_stats(const spb_ctx* ctx, spb_bvh_stats* out) {
     const HostBVH& b = ctx->bvh;
     std::memset(out, 0, sizeof(*out));
     out->n_tris = b.n_tris;
-    out->n_wide_nodes = (int64_t)b.nodes.size();
+    out->n_wide_nodes = b.n_wide;
     out->n_binary_nodes = b.n_binary_nodes;
-    out->node_bytes = (int64_t)(b.nodes.size() * sizeof(WideNode));
-    out->tri_bytes = (int64_t)b.tris.size();
+    out->node_bytes = b.n_wide * (int64_t)sizeof(WideNode);
+    out->tri_bytes = b.tri_bytes_device;
     out->sah_cost = b.sah_cost;
     out->build_seconds = ctx->build_seconds;
     out->tri_format = b.tri_format;
     out->max_depth = b.max_depth;
     for (int k = 0; k < 3; k++) { out->world_lo[k] = b.wlo[k]; out->world_hi[k] = b.whi[k]; }
+    out->inflate = b.inflate;
+    out->builder = ctx->builder_used;
     return SPB_OK;
 }
 

@@ -174,7 +174,10 @@ struct SahBuilder {
 
         int32_t mid;
         if (bestAxis < 0) {
-            mid = first + count / 2;  // all centroids coincide: split by index
+            // all centroids coincide (e.g. the two triangles of a quad whose diagonal spans its bounding box): split by
+            // index -- in ascending primitive order, so that the tree does not depend on the order earlier partitions left
+            std::sort(prims.begin() + first, prims.begin() + first + count, [](const PrimRef& a, const PrimRef& b) { return a.id < b.id; });
+            mid = first + count / 2;
         } else {
             const double cmin = cb.lo[bestAxis];
             const double scale = B / (cb.hi[bestAxis] - cmin);
@@ -286,6 +289,7 @@ bool encode_wide(const BinaryBVH& bin, const double* verts, int64_t n_tris, int 
                  std::string* err) {
     out->nodes.clear(); out->tris.clear();
     out->n_tris = n_tris; out->max_depth = 0; out->sah_cost = 0.0;
+    out->n_wide = 0; out->tri_bytes_device = 0;
     out->n_binary_nodes = (int64_t)bin.nodes.size();
     if (max_leaf < 1) max_leaf = 1;
     if (max_leaf > 3) max_leaf = 3;
@@ -534,7 +538,9 @@ bool encode_wide(const BinaryBVH& bin, const double* verts, int64_t n_tris, int 
         }
         int ex[3];
         for (int k = 0; k < 3; k++) {
-            int e = (int)std::ceil(std::log2(std::max(ext[k], 1e-300) / 255.0));
+            // smallest e with 2^e >= ext / 255, from the exponent of the quotient (exact; the device encoder uses the same rule)
+            int e;
+            { int x; const double m = std::frexp(std::max(ext[k], 1e-300) / 255.0, &x); e = (m == 0.5) ? x - 1 : x; }
             while (std::ldexp(255.0, e) < ext[k]) e++;
             if (e < -100) e = -100;
             if (e > 100) { *err = "quantisation exponent out of range"; return false; }
@@ -576,7 +582,13 @@ bool encode_wide(const BinaryBVH& bin, const double* verts, int64_t n_tris, int 
                 const int n = cn.count;     // 1..3
                 const uint8_t unary = (uint8_t)((1u << n) - 1u);
                 wn.meta[s] = (uint8_t)((unary << 5) | (uint8_t)triOff);
-                for (int i = 0; i < n; i++) emitTri(bin.order[cn.first + i]);
+                // Within a leaf the triangles go in ascending primitive index: the builders agree on the SET of a leaf, not on
+                // the order their partition passes leave it in, and the records should not depend on that.  (An imported
+                // tree keeps its leaf order: there the position is the tie-break rank.)
+                int32_t ids[3];
+                for (int i = 0; i < n; i++) ids[i] = bin.order[cn.first + i];
+                if (!bin.imported) std::sort(ids, ids + n);
+                for (int i = 0; i < n; i++) emitTri(ids[i]);
                 triOff += n;
                 out->sah_cost += relA * n;
             } else {
@@ -589,6 +601,8 @@ bool encode_wide(const BinaryBVH& bin, const double* verts, int64_t n_tris, int 
         out->nodes.push_back(wn);
     }
     if (triCursor != n_tris) { *err = "internal: collapse did not emit every triangle"; return false; }
+    out->n_wide = (int64_t)out->nodes.size();
+    out->tri_bytes_device = (int64_t)out->tris.size();
     if (out->max_depth > kStackCapacity - 2) {
         *err = "wide tree deeper than the traversal stack (" + std::to_string(out->max_depth) + ")";
         return false;

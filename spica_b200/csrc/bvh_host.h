@@ -35,6 +35,8 @@ struct HostBVH {
     int32_t max_depth = 0;
     double  sah_cost = 0.0;
     int64_t n_binary_nodes = 0;
+    int64_t n_wide = 0;              // wide nodes / triangle bytes on the device (the device builder leaves `nodes` and `tris` empty)
+    int64_t tri_bytes_device = 0;
 };
 
 // Top-down binned SAH over all three axes, 1 primitive per leaf (the collapse decides leaf sizes).

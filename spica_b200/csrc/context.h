@@ -33,6 +33,7 @@ struct spb_ctx {
     spb::HostBVH   bvh;
     bool bvh_ready = false;
     double build_seconds = 0.0;
+    int builder_used = 0;                // SPB_BUILDER_* of the current tree, -1: adopted (import / clone)
 
     void* d_nodes = nullptr;
     void* d_tris = nullptr;
@@ -75,8 +76,10 @@ int  fail(spb_ctx* ctx, int code, const std::string& msg);
 bool cudaOk(spb_ctx* ctx, cudaError_t e, const char* what);
 void setGlobalError(const std::string& msg);
 void renderStateDestroy(spb_ctx* ctx);   // integrator.cu
+void renderSceneClone(spb_ctx* dst, spb_ctx* src);   // integrator.cu: materials, lights, textures, environment of src -> dst (host side; uploaded by the next spb_render_begin)
 void renderSceneChanged(spb_ctx* ctx);   // integrator.cu: geometry / attributes changed, a new spb_render_begin is required
 int  buildLbvhDevice(spb_ctx* ctx, BinaryBVH* out);   // lbvh.cu
+int  buildSahDevice(spb_ctx* ctx, int maxLeaf);       // sah_build.cu: the default builder; leaves the 8-wide BVH in ctx->d_nodes / d_tris
 }  // namespace spb
 
 #define SPB_CUDA(ctx, call)                                                      \

@@ -74,7 +74,7 @@ void uploadGeometry(spb_ctx* ctx, const FlatScene& f) {
     check(ctx, spb_scene_set_triangles(ctx, f.verts.data(), f.anyNormals ? f.normals.data() : nullptr, f.anyUV ? f.uvs.data() : nullptr,
                                        f.material_id.data(), f.light_id.data(), n), "spb_scene_set_triangles");
     spb_build_opts opts; std::memset(&opts, 0, sizeof(opts));
-    if (const char* b = getenv("SPICA_BVH_BUILDER")) opts.builder = atoi(b);    // 0 host binned SAH (default), 1 GPU LBVH
+    if (const char* b = getenv("SPICA_BVH_BUILDER")) opts.builder = atoi(b);    // SPB_BUILDER_*: 0 device binned SAH (default), 1 device LBVH, 2 host binned SAH
     if (const char* b = getenv("SPICA_BVH_MAX_LEAF")) opts.max_leaf_tris = atoi(b);   // 1..3 triangles per leaf (default 3)
     check(ctx, spb_bvh_build(ctx, &opts), "spb_bvh_build");
 }
@@ -175,13 +175,14 @@ public:
         char commId[SPB_COMM_ID_BYTES];
         if (G > 1) check(nullptr, spb_comm_get_unique_id(commId), "spb_comm_get_unique_id");
 
+        // replicas: scene + BVH on every GPU; the tree is built ONCE (by the accelerator) and copied device to device
+        auto replicate = [&](int g) {
+            if (g == 0) return;
+            check(nullptr, spb_ctx_create(accel->device() + g, &ctxs[g]), "spb_ctx_create");
+            check(ctxs[g], spb_ctx_clone_scene(ctxs[g], ctxs[0]), "spb_ctx_clone_scene");
+        };
         auto setup = [&](int g) {
             spb_ctx* ctx = ctxs[g];
-            if (g > 0) {                                                    // replicas: scene + BVH on every GPU
-                check(nullptr, spb_ctx_create(accel->device() + g, &ctx), "spb_ctx_create");
-                ctxs[g] = ctx;
-                uploadGeometry(ctx, flat);
-            }
             check(ctx, spb_scene_set_triangle_attributes(ctx, flat.material_id.data(), flat.light_id.data(), (int64_t)flat.material_id.size()), "spb_scene_set_triangle_attributes");
             check(ctx, spb_scene_set_materials(ctx, flat.materials.data(), (int32_t)flat.materials.size()), "spb_scene_set_materials");
             if (!flat.textures.empty()) {
@@ -204,6 +205,7 @@ public:
             fn(0);
             for (auto& t : th) t.join();
         };
+        forEachGpu(replicate);
         forEachGpu(setup);
 
         std::vector<float> rgb((size_t)width * height * 3);
@@ -234,7 +236,7 @@ public:
                 const auto a = std::chrono::steady_clock::now();
                 check(ctxs[g], spb_render_samples(ctxs[g], g, std::max(count, 0), G), "spb_render_samples");
                 const auto b = std::chrono::steady_clock::now();
-                if (G > 1) check(ctxs[g], spb_film_allreduce(ctxs[g]), "spb_film_allreduce");
+                if (G > 1) check(ctxs[g], spb_film_reduce(ctxs[g], 0), "spb_film_reduce");      // only GPU 0 publishes the frame: ncclReduce, half the traffic of an all-reduce
                 tRender[g] = std::chrono::duration<double>(b - a).count();
                 tReduce[g] = std::chrono::duration<double>(std::chrono::steady_clock::now() - b).count();   // includes waiting for the slowest GPU
             });

@@ -186,7 +186,7 @@ inline void uploadGeometry(spb_ctx* ctx, const FlatScene& f) {
     check(ctx, spb_scene_set_triangles(ctx, f.verts.data(), f.anyNormals ? f.normals.data() : nullptr, f.anyUV ? f.uvs.data() : nullptr,
                                        f.material_id.data(), f.light_id.data(), n), "spb_scene_set_triangles");
     spb_build_opts opts; std::memset(&opts, 0, sizeof(opts));
-    if (const char* b = getenv("SPICA_BVH_BUILDER")) opts.builder = atoi(b);    // 0 host binned SAH (default), 1 GPU LBVH
+    if (const char* b = getenv("SPICA_BVH_BUILDER")) opts.builder = atoi(b);    // SPB_BUILDER_*: 0 device binned SAH (default), 1 device LBVH, 2 host binned SAH
     if (const char* b = getenv("SPICA_BVH_MAX_LEAF")) opts.max_leaf_tris = atoi(b);   // 1..3 triangles per leaf (default 3)
     check(ctx, spb_bvh_build(ctx, &opts), "spb_bvh_build");
 }

@@ -145,13 +145,14 @@ public:
         char commId[SPB_COMM_ID_BYTES];
         if (G > 1) check(nullptr, spb_comm_get_unique_id(commId), "spb_comm_get_unique_id");
 
+        // replicas: scene + BVH on every GPU; the tree is built ONCE (by the accelerator) and copied device to device
+        auto replicate = [&](int g) {
+            if (g == 0) return;
+            check(nullptr, spb_ctx_create(gs->device + g, &ctxs[g]), "spb_ctx_create");
+            check(ctxs[g], spb_ctx_clone_scene(ctxs[g], ctxs[0]), "spb_ctx_clone_scene");
+        };
         auto setup = [&](int g) {
             spb_ctx* ctx = ctxs[g];
-            if (g > 0) {                                                    // replicas: scene + BVH on every GPU
-                check(nullptr, spb_ctx_create(gs->device + g, &ctx), "spb_ctx_create");
-                ctxs[g] = ctx;
-                uploadGeometry(ctx, flat);
-            }
             check(ctx, spb_scene_set_triangle_attributes(ctx, flat.material_id.data(), flat.light_id.data(), (int64_t)flat.material_id.size()), "spb_scene_set_triangle_attributes");
             check(ctx, spb_scene_set_materials(ctx, flat.materials.data(), (int32_t)flat.materials.size()), "spb_scene_set_materials");
             if (!flat.textures.empty()) {
@@ -170,6 +171,7 @@ public:
             fn(0);
             for (auto& t : th) t.join();
         };
+        forEachGpu(replicate);
         forEachGpu(setup);
 
         std::vector<float> rgb((size_t)width * height * 3);
@@ -196,7 +198,7 @@ public:
             forEachGpu([&](int g) {
                 const int count = (numSamples - g + G - 1) / G;
                 check(ctxs[g], spb_render_samples(ctxs[g], g, std::max(count, 0), G), "spb_render_samples");
-                if (G > 1) check(ctxs[g], spb_film_allreduce(ctxs[g]), "spb_film_allreduce");
+                if (G > 1) check(ctxs[g], spb_film_reduce(ctxs[g], 0), "spb_film_reduce");      // only GPU 0 publishes the frame: ncclReduce, half the traffic of an all-reduce
             });
             const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
             spb_render_stats st;

@@ -459,6 +459,14 @@ def read_hdr(path):
     return rgb.astype(np.float32)
 
 
+def bin_image(img, b):
+    """Box average over b x b pixel blocks (the size is cropped to a multiple of b)."""
+    if b <= 1:
+        return img
+    h, w = (img.shape[0] // b) * b, (img.shape[1] // b) * b
+    return img[:h, :w].reshape(h // b, b, w // b, b, -1).mean(axis=(1, 3))
+
+
 def rel_mse(a, b, ref):
     """mean over pixels and channels of (a-b)^2 / (ref^2 + 1e-2)."""
     a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64); ref = np.asarray(ref, dtype=np.float64)
@@ -505,6 +513,40 @@ def synthetic_envmap(w=64, h=32):
     sun = np.exp(np.minimum(0.0, (d @ sun_dir - 1.0) * 60.0))[..., None] * np.array([30.0, 26.0, 20.0])
     img = np.where(theta[..., None] > np.pi * 0.62, np.array([0.25, 0.2, 0.15]) * (1 + 0 * sky), sky) + sun
     return np.ascontiguousarray(img, dtype=np.float32)
+
+
+ENV_CAMERA = dict(origin=(0.3, -2.6, 1.5), target=(0.0, 0.0, 0.0), up=(0.0, 0.0, 1.0), fov=40.0)
+
+
+def envscene_envmap():
+    """The texels the reference reads back from write_envscene's .hdr file: RGBE-quantised, decoded as core/image.cc:380-382
+    does (mantissa / 256 x 2^(e - 128), no half step)."""
+    img = np.asarray(synthetic_envmap(), dtype=np.float64)
+    d = img.max(-1)
+    m, e = np.frexp(d)
+    scale = np.where(d > 1e-32, m * 256.0 / np.maximum(d, 1e-300), 0.0)
+    mant = np.clip(img * scale[..., None], 0, 255).astype(np.uint8).astype(np.float64)
+    out = mant * np.where(d > 1e-32, np.exp2(e.astype(np.float64) - 8.0), 0.0)[..., None]
+    return np.ascontiguousarray(out, dtype=np.float32)
+
+
+def envscene_arrays(nu=96, nv=48):
+    """write_envscene's scene as the arrays the C ABI takes (what the hosts resolve that XML file into): the torus
+    (flat shaded: a PLY carries no normals, core/meshio.cc:76-166) + the ground quad, the two materials, the
+    environment map with its toWorld rotation (radians, spica/sceneparser.cc:147-148), the camera.
+    BASELINE configs[4] is envscene_arrays(2500, 2000): 10,000,000 + 2 triangles."""
+    v, f = torus_mesh(nu, nv, R=0.6, r=0.25, bump=0.0)
+    torus = mesh_triangles(v, f)
+    g = np.array([[-2, -2, -0.3], [2, -2, -0.3], [2, 2, -0.3], [-2, 2, -0.3]], dtype=np.float64)
+    ground = np.stack([np.concatenate([g[0], g[1], g[2]]), np.concatenate([g[0], g[2], g[3]])])
+    tris = np.concatenate([torus, ground])
+    mid = np.concatenate([np.zeros(len(torus), np.int32), np.ones(2, np.int32)])
+    mats = [dict(type="roughdielectric", specularReflectance=(1, 1, 1), specularTransmittance=(0.9, 0.95, 1.0), alpha=0.15, intIOR=1.5, distribution="ggx"),
+            dict(type="diffuse", reflectance=(0.6, 0.55, 0.5))]
+    c, s_ = np.cos(0.4), np.sin(0.4)
+    to_world = np.array([[c, -s_, 0, 0], [s_, c, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]], dtype=np.float64)      # core/transform.cc:136-165, axis z
+    return dict(tris=tris, material_id=mid, light_id=np.full(len(tris), -1, np.int32), materials=mats, env=envscene_envmap(), env_to_world=to_world,
+                env_scale=1.5, env_radius=6.0, camera=ENV_CAMERA, filter="tent")
 
 
 def write_envscene(dirpath, width=128, height=128, spp=64, max_depth=8, name="envtorus", nu=96, nv=48):

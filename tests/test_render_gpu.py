@@ -46,6 +46,53 @@ def test_cornell_relmse_against_reference(gpu_ctx, variant):
         np.save(os.path.join(out, "cornell_%s_gpu.npy" % variant), hi.astype(np.float32))
 
 
+@pytest.mark.parametrize("name,variant", [("baseline_c1_ref.npz", "diffuse"), ("baseline_c4_16spp_ref.npz", "glossy")])
+def test_baseline_configurations_against_reference(gpu_ctx, name, variant):
+    """Image parity AT the BASELINE configurations: C1 (512x512, 64 spp, depth 8) in full, C4 (glossy Cornell box, 1920x1080,
+    depth 16) at a reduced 16 spp.  The fixtures hold K = 4 runs of the unmodified reference, box-averaged over bin x bin
+    pixels (tests/golden/make_baseline_golden.py); the GPU image is binned the same way; tau = 1.5 x the largest pairwise
+    relMSE of the binned reference runs."""
+    path = os.path.join(GOLDEN, name)
+    if not os.path.exists(path):
+        pytest.skip("no fixture " + name)
+    g = np.load(path)
+    runs = g["runs"].astype(np.float64)
+    K, b = len(runs), int(g["bin"])
+    w, h, spp, depth = int(g["width"]), int(g["height"]), int(g["spp"]), int(g["max_depth"])
+    mean = runs.mean(0)
+    pair_max = float(g["pair_relmse"][0])
+    img = scenes.bin_image(capi.cornell_render(gpu_ctx, w, h, spp, max_depth=depth, variant=variant, seed=21).astype(np.float64), b)
+    r_equal = max(scenes.rel_mse(img, runs[k], mean) for k in range(K))
+    assert r_equal <= 1.5 * pair_max, (r_equal, pair_max)
+    # bias: 16x the samples against the mean of the reference runs (whose own noise is pairwise / (2K))
+    hi = scenes.bin_image(capi.cornell_render(gpu_ctx, w, h, 16 * spp, max_depth=depth, variant=variant, seed=22).astype(np.float64), b)
+    r_hi = scenes.rel_mse(hi, mean, mean)
+    assert r_hi <= 1.5 * pair_max / (2 * K) * (1.0 + K / 16.0), (r_hi, pair_max / (2 * K))
+    assert abs(hi.mean() / mean.mean() - 1.0) < 0.01, (hi.mean(), mean.mean())
+
+
+def test_baseline_c5_scene_in_miniature(gpu_ctx):
+    """BASELINE configs[4]'s scene (torus + ground under an environment map, rough dielectric, tent filter, depth 16) with 100 k
+    instead of 10 M triangles at 480x270: K = 4 runs of the unmodified reference (tests/golden/make_baseline_golden.py c5)
+    against the arrays bench.py feeds the C ABI for the full-size configuration (scenes.envscene_arrays)."""
+    path = os.path.join(GOLDEN, "baseline_c5_small_ref.npz")
+    if not os.path.exists(path):
+        pytest.skip("no fixture baseline_c5_small_ref.npz")
+    g = np.load(path)
+    runs = g["runs"].astype(np.float64)
+    K, b = len(runs), int(g["bin"])
+    w, h, spp, depth, nu, nv = (int(g[k]) for k in ("width", "height", "spp", "max_depth", "nu", "nv"))
+    mean = runs.mean(0)
+    pair_max = float(g["pair_relmse"][0])
+    img = scenes.bin_image(capi.envscene_render(gpu_ctx, w, h, spp, max_depth=depth, nu=nu, nv=nv, seed=41).astype(np.float64), b)
+    r_equal = max(scenes.rel_mse(img, runs[k], mean) for k in range(K))
+    assert r_equal <= 1.5 * pair_max, (r_equal, pair_max)
+    hi = scenes.bin_image(capi.envscene_render(gpu_ctx, w, h, 16 * spp, max_depth=depth, nu=nu, nv=nv, seed=42).astype(np.float64), b)
+    r_hi = scenes.rel_mse(hi, mean, mean)
+    assert r_hi <= 1.5 * pair_max / (2 * K) * (1.0 + K / 16.0), (r_hi, pair_max / (2 * K))
+    assert abs(hi.mean() / mean.mean() - 1.0) < 0.01, (hi.mean(), mean.mean())
+
+
 def test_directlighting_integrator_against_reference(gpu_ctx):
     """integrators/directlighting on the "zoo" scene (it has a mirror): emitted light at depth 0
     only, one light sample per vertex, continuation through specular reflection only.  The reference's own
@@ -126,3 +173,61 @@ def test_film_add_and_stats(gpu_ctx):
     assert st["paths"] == 32 * 32 * 2 and st["rays_closest"] >= st["paths"] and st["rays_shadow"] > 0
     gpu_ctx.film_add(f)
     assert np.allclose(gpu_ctx.film_read(), 2 * f)
+
+
+def test_async_render_graph_and_single_rank_reduce(gpu_ctx):
+    """spb_render_samples_async + spb_render_wait, the plain-launch loop and a (single-rank) NCCL film reduce all give the
+    film of the synchronous call (same sample set; float atomics only reorder the sums)."""
+    capi.cornell_render(gpu_ctx, 96, 80, 6, seed=8, variant="glossy")
+    ref = gpu_ctx.film_read()
+    # asynchronous, in two queued halves
+    capi.cornell_render(gpu_ctx, 96, 80, 0, seed=8, variant="glossy")
+    gpu_ctx.render_samples_async(0, 3, 1)
+    gpu_ctx.render_samples_async(3, 3, 1)
+    gpu_ctx.render_wait()
+    assert np.allclose(gpu_ctx.film_read(), ref, rtol=1e-4, atol=1e-5)
+    st = gpu_ctx.render_stats()
+    assert st["paths"] == 96 * 80 * 6 and st["iterations"] > 0 and st["rays_closest"] >= st["paths"]
+    # plain launches instead of the CUDA graph
+    gpu_ctx.set_option("render_graph", 0)
+    capi.cornell_render(gpu_ctx, 96, 80, 6, seed=8, variant="glossy")
+    gpu_ctx.set_option("render_graph", 1)
+    assert np.allclose(gpu_ctx.film_read(), ref, rtol=1e-4, atol=1e-5)
+    # a one-rank communicator: reduce to root 0 and all-reduce are the identity
+    try:
+        cid = capi.comm_unique_id()
+    except capi.SpbError:
+        pytest.skip("libnccl not loadable")
+    gpu_ctx.comm_init(cid, 1, 0)
+    gpu_ctx.film_reduce(0)
+    gpu_ctx.film_reduce_async(-1)
+    gpu_ctx.render_wait()
+    assert np.allclose(gpu_ctx.film_read(), ref, rtol=1e-4, atol=1e-5)
+    assert gpu_ctx.render_stats()["reduce_ms"] > 0
+    gpu_ctx.L.spb_comm_destroy(gpu_ctx.h)
+
+
+def test_scene_change_invalidates_a_begun_render(gpu_ctx):
+    """spb_scene_set_triangles after spb_render_begin used to leave the kernels' parameter block pointing at the
+    freed tree.  Now every scene change requires a new spb_render_begin."""
+    capi.cornell_render(gpu_ctx, 32, 32, 1, seed=2)
+    tris, mid, lid, mats, lights = scenes.cornell_arrays("diffuse")
+    gpu_ctx.set_triangles(tris, material_id=mid, light_id=lid)
+    with pytest.raises(capi.SpbError):
+        gpu_ctx.render_samples(1, 1, 1)            # no tree, stale shading records
+    gpu_ctx.build()
+    with pytest.raises(capi.SpbError):
+        gpu_ctx.render_samples(1, 1, 1)            # still no new spb_render_begin
+    capi.cornell_render(gpu_ctx, 32, 32, 1, seed=2)
+    gpu_ctx.set_materials(mats)
+    with pytest.raises(capi.SpbError):
+        gpu_ctx.render_samples(1, 1, 1)
+    # the bounce counter of a path has 12 bits
+    cam = scenes.CORNELL_CAMERA
+    c2w, r2c = scenes.perspective_camera(scenes.look_at(cam["origin"], cam["target"], cam["up"]), cam["fov"], 32, 32)
+    with pytest.raises(capi.SpbError):
+        gpu_ctx.render_begin(32, 32, c2w, r2c, max_depth=5000)
+    with pytest.raises(capi.SpbError):
+        gpu_ctx.set_option("trace_variant", 99)
+    img = capi.cornell_render(gpu_ctx, 32, 32, 2, seed=2)
+    assert np.isfinite(img).all() and img.mean() > 0

@@ -182,6 +182,108 @@ def test_full_size_properties_1m_triangles(gpu_ctx):
     assert np.array_equal(gpu_ctx.trace_any(rays[:200000]), (hits["prim"][:200000] >= 0).astype(np.uint8))
 
 
+def _wide_bytes(ctx):
+    st, nodes, tris = ctx.export_bvh()
+    return st, bytes(nodes), bytes(tris)
+
+
+@pytest.mark.parametrize("max_leaf", [1, 3])
+def test_device_sah_builder_is_the_host_builder_byte_for_byte(gpu_ctx, golden_torus, golden_f64verts, max_leaf):
+    """builder 0 (default): binned SAH, cost-optimal 8-wide collapse and quantisation on the device, in the host builder's
+    double arithmetic.  The 8-wide BVH in HBM must be the host builder's (builder 2), byte for byte -- nodes and
+    leaf-ordered triangle records -- on meshes without coincident centroids; and every answer is the reference's."""
+    meshes = [golden_torus["tris"], golden_f64verts["tris"]]      # (not the cube: the two triangles of a face have the same centroid)
+    v, f = scenes.torus_mesh(300, 150)                      # 90,000 triangles: large-node levels, chunked passes, small subtrees
+    meshes.append(scenes.mesh_triangles(v, f))
+    for tris in meshes:
+        gpu_ctx.set_triangles(tris)
+        gpu_ctx.build(max_leaf_tris=max_leaf, builder=2)
+        st_h, n_h, t_h = _wide_bytes(gpu_ctx)
+        gpu_ctx.build(max_leaf_tris=max_leaf, builder=0)
+        st_d, n_d, t_d = _wide_bytes(gpu_ctx)
+        assert st_d.builder == 0 and st_h.builder == 2
+        assert (st_d.n_wide_nodes, st_d.n_binary_nodes, st_d.tri_format, st_d.max_depth) == (st_h.n_wide_nodes, st_h.n_binary_nodes, st_h.tri_format, st_h.max_depth)
+        assert t_d == t_h, "triangle records differ"
+        assert n_d == n_h, "wide nodes differ"
+        assert abs(st_d.sah_cost / st_h.sah_cost - 1.0) < 1e-9 and st_d.inflate == st_h.inflate
+    g = golden_torus
+    gpu_ctx.set_triangles(g["tris"])
+    gpu_ctx.build(max_leaf_tris=max_leaf)
+    _check_closest(gpu_ctx, g["tris"], g["rays"], g["prim"], g["t"])
+    assert np.array_equal(gpu_ctx.trace_any(g["any_rays"]), g["occluded"])
+
+
+def test_device_builder_edge_cases(gpu_ctx):
+    r = np.array([[0.2, 0.2, 1, 0, 0, -1, 0, 1e32]], dtype=np.float32)
+    one = np.array([[0, 0, 0, 1, 0, 0, 0, 1, 0]], dtype=np.float64)
+    gpu_ctx.set_triangles(one)
+    gpu_ctx.build()
+    assert gpu_ctx.trace_closest(r)["prim"][0] == 0 and gpu_ctx.stats()["n_binary_nodes"] == 1
+    # coincident centroids (duplicated triangles): the index split; exact ties -> lowest index
+    for reps in (2, 9, 700, 3000):
+        gpu_ctx.set_triangles(np.repeat(one, reps, axis=0))
+        gpu_ctx.build()
+        assert gpu_ctx.trace_closest(r)["prim"][0] == 0
+        assert gpu_ctx.stats()["n_binary_nodes"] == 2 * reps - 1
+    # two far-apart clusters of duplicates, and a degenerate (flat) mesh: all centroids in one plane
+    two = np.concatenate([np.repeat(one, 600, axis=0), np.repeat(one + 10.0, 600, axis=0)])
+    gpu_ctx.set_triangles(two)
+    gpu_ctx.build()
+    assert gpu_ctx.trace_closest(r)["prim"][0] == 0
+    r2 = r.copy(); r2[0, :3] += 10.0
+    assert gpu_ctx.trace_closest(r2)["prim"][0] == 600
+    n = 40
+    xs, ys = np.meshgrid(np.arange(n, dtype=np.float64), np.arange(n, dtype=np.float64))
+    flat = np.stack([xs, ys, 0 * xs, xs + 1, ys, 0 * xs, xs, ys + 1, 0 * xs], -1).reshape(-1, 9)
+    gpu_ctx.set_triangles(flat)
+    gpu_ctx.build()
+    rays = np.zeros((n * n, 8), np.float32)
+    rays[:, 0] = xs.ravel() + 0.25; rays[:, 1] = ys.ravel() + 0.25; rays[:, 2] = 1; rays[:, 5] = -1; rays[:, 7] = 1e32
+    assert np.array_equal(gpu_ctx.trace_closest(rays)["prim"], np.arange(n * n))
+
+
+def test_export_import_and_clone_share_one_tree(gpu_ctx, golden_torus):
+    """spb_bvh_export -> spb_bvh_import_wide (another context, any process) and spb_ctx_clone_scene (same process, device to
+    device): the adopting context answers exactly like the builder's, without building."""
+    g = golden_torus
+    gpu_ctx.set_triangles(g["tris"])
+    gpu_ctx.build()
+    st, nodes, tris = gpu_ctx.export_bvh()
+    other = capi.Context(0)
+    try:
+        other.set_triangles(g["tris"])
+        with pytest.raises(capi.SpbError):
+            other.trace_closest(g["rays"])                 # nothing built or adopted yet
+        other.import_wide(st, nodes, tris)
+        assert other.stats()["builder"] == -1
+        _check_closest(other, g["tris"], g["rays"], g["prim"], g["t"])
+        bad = capi.BvhStats.from_buffer_copy(st); bad.node_bytes += 80
+        with pytest.raises(capi.SpbError):
+            other.import_wide(bad, nodes, tris)
+    finally:
+        other.close()
+    clone = capi.Context(0)
+    try:
+        clone.clone_scene_from(gpu_ctx)
+        _check_closest(clone, g["tris"], g["rays"], g["prim"], g["t"])
+        assert np.array_equal(clone.trace_any(g["any_rays"]), g["occluded"])
+        assert _wide_bytes(clone)[1:] == (bytes(nodes), bytes(tris))
+    finally:
+        clone.close()
+    # a cloned scene renders the same image (materials, lights and attributes travel with it)
+    img = capi.cornell_render(gpu_ctx, 48, 48, 4, seed=3, variant="glossy")
+    clone = capi.Context(0)
+    try:
+        clone.clone_scene_from(gpu_ctx)
+        cam = scenes.CORNELL_CAMERA
+        c2w, r2c = scenes.perspective_camera(scenes.look_at(cam["origin"], cam["target"], cam["up"]), cam["fov"], 48, 48)
+        clone.render_begin(48, 48, c2w, r2c, max_depth=8, seed=3)
+        clone.render_samples(0, 4, 1)
+        assert np.allclose(clone.film_resolve(), img, rtol=1e-4, atol=1e-5)
+    finally:
+        clone.close()
+
+
 def test_gpu_lbvh_builder_gives_identical_hits(gpu_ctx, golden_torus, golden_cube):
     """builder = 1: Morton sort + Karras hierarchy + refit on the device (replaces the reference's
     top-down BVHAccel::constructRec). Any valid tree must return the reference's (prim, t)."""
@@ -240,7 +342,7 @@ def test_greedy_and_cost_optimal_collapse_agree(gpu_ctx, monkeypatch):
     res = {}
     for col in ("1", "0"):
         monkeypatch.setenv("SPICA_BVH_COLLAPSE", col)
-        gpu_ctx.build()
+        gpu_ctx.build(builder=2)
         res[col] = (gpu_ctx.trace_closest(rays), gpu_ctx.stats()["n_wide_nodes"])
     assert np.array_equal(res["1"][0], res["0"][0])
     assert res["1"][1] < res["0"][1]
