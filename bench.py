@@ -320,7 +320,7 @@ def reference_arm(args):
                              "sample": "%d of %d incoherent rays (stride %d), BVHAccel::intersect on %d threads" % (len(rays), N_RAYS, stride, cores)},
             "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 def bind_to_gpu_numa(local):
@@ -348,7 +348,30 @@ def bind_to_gpu_numa(local):
         return "not bound (%s)" % type(e).__name__
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """bench.py's stdout carries exactly ONE line, the JSON record.  Libraries below us print there too (NCCL's version
+    banner, the C++ host's progress lines): from here on fd 1 is stderr, and emit() writes the record to the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -467,6 +490,27 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_val = world * n / float(t.item()) * 1e-6
+    e2e_s_max = float(t.item())
+
+    # ---- the ceiling of that call: the same bytes over PCIe with no kernel at all -- H2D of the rays and D2H of the hit
+    # records on two streams at once, on all ranks at once (with several GPUs the host-memory path is shared)
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    def pcie_pass():
+        with torch.cuda.stream(s_in):
+            d_rays.copy_(pin_rays, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            pin_hits.copy_(d_hits, non_blocking=True)
+        s_in.synchronize(); s_out.synchronize()
+    pcie_pass()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        pcie_pass()
+    pcie_s = (time.perf_counter() - t0) / 3
+    t = torch.tensor([pcie_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    pcie_s_max = float(t.item())
 
     # ---- BASELINE configs[2] and [3] on all ranks: the path tracer, 1920x1080, depth 16, the configuration's TOTAL sample
     # count partitioned over the GPUs (strong scaling), one NCCL reduce of the film per frame inside the timed region
@@ -599,11 +643,14 @@ def main():
                        "l2": "streamed inputs+outputs (%d MB/step) exceed the 126 MB L2; the BVH is meant to stay resident" % ((n * 48) >> 20),
                        "parallelism": "rays sharded over %d GPU(s), scene replicated, no collective" % world,
                        "host_numa": "rank 0: " + numa_note},
-            "e2e": {"value": e2e_val, "unit": "Mrays/s", "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": n * 16},
+            "e2e": {"value": e2e_val, "unit": "Mrays/s", "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": n * 16,
+                    "pcie_ceiling": {"value": world * n / pcie_s_max * 1e-6, "unit": "Mrays/s", "frac": pcie_s_max / e2e_s_max,
+                                     "what": "the same pinned buffers copied H2D (rays) and D2H (hit records) concurrently with no kernel, all ranks at once, max over ranks",
+                                     "h2d_gb_s_per_gpu": n * 32 / pcie_s_max * 1e-9, "d2h_gb_s_per_gpu": n * 16 / pcie_s_max * 1e-9}},
             "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roof, "cpu_baseline": cpu,
             "parity": parity, "extra": extra, "bvh_build_s": st["build_seconds"],
             "bvh_builder": {0: "device binned SAH + device 8-wide collapse", 1: "device LBVH", 2: "host binned SAH"}.get(st["builder"], "adopted")}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

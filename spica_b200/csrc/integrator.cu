@@ -387,7 +387,9 @@ __global__ void __launch_bounds__(128, MINB) shadeKernel(RenderParamsPOD rp, Dev
     float4* nextQ = q.ray[cur ^ 1];
     float4* nextS = q.state[cur ^ 1];
     uint32_t* nextCount = q.count + (cur ^ 1);
-    // whole CTAs iterate together: the queue pushes of a tile are aggregated over the CTA
+    // whole CTAs iterate together: the queue pushes of a tile are aggregated over the CTA.
+    // (Staging the five 16-byte pieces of an entry through shared memory with cp.async, one tile ahead, was measured in r02i:
+    // no gain -- 2134 -> 2115 Msamples/s on the diffuse Cornell box; the other resident warps already cover that latency.)
     __shared__ uint32_t s_cnt[2][4], s_base[4];
     if (threadIdx.x < 8) s_cnt[threadIdx.x >> 2][threadIdx.x & 3] = 0u;
     __syncthreads();
@@ -765,81 +767,120 @@ void renderSceneClone(spb_ctx* dst, spb_ctx* src) {
     D->scene_dirty = true; D->begun = false;
 }
 
-namespace {
+// The per-triangle shading records, the way the reference's Triangle constructors and Triangle::intersect build them
+// (core/triangle.cc:17-67, 119-137): in double, narrowed to float32 at the end; one thread per triangle.  Also the shading
+// bucket of the triangle (classifyKernel).
 struct D3 { double x, y, z; };
-inline D3 sub(D3 a, D3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
-inline D3 crossd(D3 a, D3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
-inline double normd(D3 a) { return std::sqrt(a.x * a.x + a.y * a.y + a.z * a.z); }
-inline D3 normalized(D3 a) { const double n = normd(a); return n > 0 ? D3{a.x / n, a.y / n, a.z / n} : a; }
-inline D3 scaled(D3 a, double s) { return {a.x * s, a.y * s, a.z * s}; }
-inline D3 addd(D3 a, D3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
-inline void coordSys(D3 w, D3* u, D3* v) {          // core/vect_math.h:115-123
-    if (std::abs(w.x) > std::abs(w.y)) *u = normalized({-w.z, 0, w.x}); else *u = normalized({0, w.z, -w.y});
-    *v = normalized(crossd(w, *u));
+__device__ __forceinline__ D3 d3sub(D3 a, D3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ D3 d3cross(D3 a, D3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+__device__ __forceinline__ double d3norm(D3 a) { return sqrt(a.x * a.x + a.y * a.y + a.z * a.z); }
+__device__ __forceinline__ D3 d3normalized(D3 a) { const double n = d3norm(a); return n > 0 ? D3{a.x / n, a.y / n, a.z / n} : a; }
+__device__ __forceinline__ D3 d3scaled(D3 a, double s) { return {a.x * s, a.y * s, a.z * s}; }
+__device__ __forceinline__ D3 d3add(D3 a, D3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ void d3coordSys(D3 w, D3* u, D3* v) {          // core/vect_math.h:115-123
+    if (fabs(w.x) > fabs(w.y)) *u = d3normalized({-w.z, 0, w.x}); else *u = d3normalized({0, w.z, -w.y});
+    *v = d3normalized(d3cross(w, *u));
 }
-inline void put3(float* d, D3 a) { d[0] = (float)a.x; d[1] = (float)a.y; d[2] = (float)a.z; }
-}  // namespace
 
-// Builds the per-triangle shading records the way the reference's Triangle constructors and
-// Triangle::intersect do (core/triangle.cc:17-67, 119-137), in double, then narrows to float32.
+__global__ void __launch_bounds__(256) shadeTriKernel(const double* __restrict__ verts, const float* __restrict__ normals, const float* __restrict__ uvs,
+                                                      const int32_t* __restrict__ material_id, const int32_t* __restrict__ light_id, int64_t n,
+                                                      const spb_material* __restrict__ mats, int n_mats, ShadeTri* __restrict__ out, uint8_t* __restrict__ bucket) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double* v = verts + i * 9;
+    const D3 p0{v[0], v[1], v[2]}, p1{v[3], v[4], v[5]}, p2{v[6], v[7], v[8]};
+    const D3 e1 = d3sub(p1, p0), e2 = d3sub(p2, p0);
+    D3 fn = d3cross(e1, e2);
+    bool triHasN = false;
+    if (normals) {
+        const float* nn = normals + i * 9;
+        triHasN = !(nn[0] == 0.f && nn[1] == 0.f && nn[2] == 0.f && nn[3] == 0.f && nn[4] == 0.f && nn[5] == 0.f && nn[6] == 0.f && nn[7] == 0.f && nn[8] == 0.f);
+        if (triHasN && d3norm(fn) < 1e-12) fn = d3scaled(D3{(double)nn[0] + nn[3] + nn[6], (double)nn[1] + nn[4] + nn[7], (double)nn[2] + nn[5] + nn[8]}, 1.0 / 3.0);
+    }
+    fn = d3normalized(fn);
+    D3 dpdu, dpdv;
+    double detUV = 0.0, duv01[2] = {0, 0}, duv02[2] = {0, 0};
+    if (uvs) {
+        const float* t = uvs + i * 6;
+        duv01[0] = (double)t[2] - t[0]; duv01[1] = (double)t[3] - t[1];
+        duv02[0] = (double)t[4] - t[0]; duv02[1] = (double)t[5] - t[1];
+        detUV = duv01[0] * duv02[1] - duv01[1] * duv02[0];
+    }
+    if (detUV == 0.0) d3coordSys(fn, &dpdu, &dpdv);
+    else {
+        const double inv = 1.0 / detUV;
+        dpdu = d3add(d3scaled(e1, duv02[1] * inv), d3scaled(e2, -duv01[1] * inv));
+        dpdv = d3add(d3scaled(e1, -duv02[0] * inv), d3scaled(e2, duv01[0] * inv));
+    }
+    const D3 ng = d3normalized(d3cross(dpdu, dpdv));
+    const D3 ss = d3normalized(dpdu), ts = d3normalized(dpdv);
+    ShadeTri s;
+    s.p0[0] = (float)p0.x; s.p0[1] = (float)p0.y; s.p0[2] = (float)p0.z;
+    s.e1x = (float)e1.x; s.e1y = (float)e1.y; s.e1z = (float)e1.z;
+    s.e2[0] = (float)e2.x; s.e2[1] = (float)e2.y; s.e2z = (float)e2.z;
+    s.ng[0] = (float)ng.x; s.ng[1] = (float)ng.y; s.ng[2] = (float)ng.z;
+    s.fn[0] = (float)fn.x; s.fn[1] = (float)fn.y; s.fn[2] = (float)fn.z;
+    s.area = (float)(0.5 * d3norm(d3cross(e1, e2)));
+    s.ss[0] = (float)ss.x; s.ss[1] = (float)ss.y; s.ss[2] = (float)ss.z;
+    s.ts[0] = (float)ts.x; s.ts[1] = (float)ts.y; s.ts[2] = (float)ts.z;
+    const int32_t m = material_id[i];
+    s.material = m; s.light = light_id[i];
+    s.has_normals = triHasN ? 1 : 0; s.pad0 = s.pad1 = s.pad2 = 0;
+    out[i] = s;
+    const int t = (m >= 0 && m < n_mats) ? mats[m].type : -1;
+    bucket[i] = (uint8_t)((t >= 0 && t <= 6) ? kBucketMat0 + t : kBucketNone);
+}
+
+__global__ void bucketMaskKernel(const uint8_t* __restrict__ bucket, int64_t n, uint32_t* mask) {
+    uint32_t m = 0u;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) m |= 1u << bucket[i];
+    for (int d = 16; d >= 1; d >>= 1) m |= __shfl_xor_sync(0xffffffffu, m, d);
+    if ((threadIdx.x & 31) == 0 && m) atomicOr(mask, m);
+}
+
 static int uploadScene(spb_ctx* ctx, RenderState* R) {
     freeScene(R);
     const int64_t n = ctx->n_tris;
     R->n_tris = n;
-    std::vector<ShadeTri> tris((size_t)n);
     const bool hasN = !ctx->normals.empty(), hasUV = !ctx->uvs.empty();
-    for (int64_t i = 0; i < n; i++) {
-        const double* v = ctx->verts.data() + i * 9;
-        const D3 p0{v[0], v[1], v[2]}, p1{v[3], v[4], v[5]}, p2{v[6], v[7], v[8]};
-        const D3 e1 = sub(p1, p0), e2 = sub(p2, p0);
-        D3 fn = crossd(e1, e2);
-        bool triHasN = false;
-        if (hasN) {
-            const float* nn = ctx->normals.data() + i * 9;
-            triHasN = !(nn[0] == 0.f && nn[1] == 0.f && nn[2] == 0.f && nn[3] == 0.f && nn[4] == 0.f && nn[5] == 0.f &&
-                        nn[6] == 0.f && nn[7] == 0.f && nn[8] == 0.f);
-            if (triHasN && normd(fn) < 1e-12) fn = scaled(D3{(double)nn[0] + nn[3] + nn[6], (double)nn[1] + nn[4] + nn[7], (double)nn[2] + nn[5] + nn[8]}, 1.0 / 3.0);
-        }
-        fn = normalized(fn);
-        D3 dpdu, dpdv;
-        double detUV = 0.0, duv01[2] = {0, 0}, duv02[2] = {0, 0};
-        if (hasUV) {
-            const float* t = ctx->uvs.data() + i * 6;
-            duv01[0] = (double)t[2] - t[0]; duv01[1] = (double)t[3] - t[1];
-            duv02[0] = (double)t[4] - t[0]; duv02[1] = (double)t[5] - t[1];
-            detUV = duv01[0] * duv02[1] - duv01[1] * duv02[0];
-        }
-        if (detUV == 0.0) coordSys(fn, &dpdu, &dpdv);
-        else {
-            const double inv = 1.0 / detUV;
-            dpdu = addd(scaled(e1, duv02[1] * inv), scaled(e2, -duv01[1] * inv));
-            dpdv = addd(scaled(e1, -duv02[0] * inv), scaled(e2, duv01[0] * inv));
-        }
-        const D3 ng = normalized(crossd(dpdu, dpdv));
-        ShadeTri& s = tris[(size_t)i];
-        std::memset(&s, 0, sizeof(s));
-        put3(s.p0, p0);
-        s.e1x = (float)e1.x; s.e1y = (float)e1.y; s.e1z = (float)e1.z;
-        s.e2[0] = (float)e2.x; s.e2[1] = (float)e2.y; s.e2z = (float)e2.z;
-        put3(s.ng, ng); put3(s.fn, fn);
-        s.area = (float)(0.5 * normd(crossd(e1, e2)));
-        put3(s.ss, normalized(dpdu)); put3(s.ts, normalized(dpdv));
-        s.material = ctx->material_id[(size_t)i];
-        s.light = ctx->light_id[(size_t)i];
-        s.has_normals = triHasN ? 1 : 0;
-    }
+    cudaStream_t st = ctx->stream;
+    const size_t nm0 = std::max<size_t>(R->mats.size(), 1);
+    SPB_CUDA(ctx, cudaMalloc(&R->d_mats, nm0 * sizeof(spb_material)));
+    if (!R->mats.empty()) SPB_CUDA(ctx, cudaMemcpyAsync(R->d_mats, R->mats.data(), R->mats.size() * sizeof(spb_material), cudaMemcpyHostToDevice, st));
+    R->bucket_mask = 1u << kBucketMiss;
     if (n > 0) {
-        SPB_CUDA(ctx, cudaMalloc(&R->d_tris, (size_t)n * sizeof(ShadeTri)));
-        SPB_CUDA(ctx, cudaMemcpy(R->d_tris, tris.data(), (size_t)n * sizeof(ShadeTri), cudaMemcpyHostToDevice));
+        double* d_v = nullptr; int32_t *d_m = nullptr, *d_l = nullptr; uint32_t* d_mask = nullptr; float* d_uv = nullptr;
+        auto freeTmp = [&]() { cudaFree(d_v); cudaFree(d_m); cudaFree(d_l); cudaFree(d_mask); cudaFree(d_uv); };
+#define US(call) do { const cudaError_t e_ = (call); if (e_ != cudaSuccess) { freeTmp(); cudaOk(ctx, e_, #call); return e_ == cudaErrorMemoryAllocation ? SPB_ERR_OOM : SPB_ERR_CUDA; } } while (0)
+        US(cudaMalloc(&R->d_tris, (size_t)n * sizeof(ShadeTri)));
+        US(cudaMalloc(&R->d_prim_bucket, (size_t)n));
+        US(cudaMalloc(&d_v, (size_t)n * 9 * sizeof(double)));
+        US(cudaMalloc(&d_m, (size_t)n * 4)); US(cudaMalloc(&d_l, (size_t)n * 4)); US(cudaMalloc(&d_mask, 4));
+        US(cudaMemcpyAsync(d_v, ctx->verts.data(), (size_t)n * 9 * sizeof(double), cudaMemcpyHostToDevice, st));
+        US(cudaMemcpyAsync(d_m, ctx->material_id.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        US(cudaMemcpyAsync(d_l, ctx->light_id.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        US(cudaMemsetAsync(d_mask, 0, 4, st));
         if (hasN) {
-            SPB_CUDA(ctx, cudaMalloc(&R->d_vnormals, (size_t)n * 9 * sizeof(float)));
-            SPB_CUDA(ctx, cudaMemcpy(R->d_vnormals, ctx->normals.data(), (size_t)n * 9 * sizeof(float), cudaMemcpyHostToDevice));
+            US(cudaMalloc(&R->d_vnormals, (size_t)n * 9 * sizeof(float)));
+            US(cudaMemcpyAsync(R->d_vnormals, ctx->normals.data(), (size_t)n * 9 * sizeof(float), cudaMemcpyHostToDevice, st));
         }
+        if (hasUV) {
+            US(cudaMalloc(&d_uv, (size_t)n * 6 * sizeof(float)));
+            US(cudaMemcpyAsync(d_uv, ctx->uvs.data(), (size_t)n * 6 * sizeof(float), cudaMemcpyHostToDevice, st));
+        }
+        shadeTriKernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_v, R->d_vnormals, d_uv, d_m, d_l, n, R->d_mats, (int)R->mats.size(), R->d_tris, R->d_prim_bucket);
+        bucketMaskKernel<<<ctx->sm_count * 4, 256, 0, st>>>(R->d_prim_bucket, n, d_mask);
+        uint32_t mask = 0u;
+        US(cudaMemcpyAsync(&mask, d_mask, 4, cudaMemcpyDeviceToHost, st));
+        US(cudaStreamSynchronize(st));
+        US(cudaGetLastError());
+#undef US
+        freeTmp();
+        R->bucket_mask |= mask;
+        R->launches += 2;
     }
-    const size_t nm = std::max<size_t>(R->mats.size(), 1), nl = std::max<size_t>(R->lights.size(), 1);
-    SPB_CUDA(ctx, cudaMalloc(&R->d_mats, nm * sizeof(spb_material)));
+    const size_t nl = std::max<size_t>(R->lights.size(), 1);
     SPB_CUDA(ctx, cudaMalloc(&R->d_lights, nl * sizeof(spb_light)));
-    if (!R->mats.empty()) SPB_CUDA(ctx, cudaMemcpy(R->d_mats, R->mats.data(), R->mats.size() * sizeof(spb_material), cudaMemcpyHostToDevice));
     if (!R->lights.empty()) SPB_CUDA(ctx, cudaMemcpy(R->d_lights, R->lights.data(), R->lights.size() * sizeof(spb_light), cudaMemcpyHostToDevice));
     R->ds.tris = R->d_tris; R->ds.vnormals = R->d_vnormals; R->ds.mats = R->d_mats; R->ds.lights = R->d_lights;
     R->ds.n_mats = (int)R->mats.size(); R->ds.n_lights = (int)R->lights.size();
@@ -870,18 +911,6 @@ static int uploadScene(spb_ctx* ctx, RenderState* R) {
     // every lobe type a material can turn into, and the shading bucket of every triangle
     R->type_mask = 0u;
     for (const spb_material& m : R->mats) if (m.type >= 0 && m.type <= 6) R->type_mask |= typeClosure(m.type);
-    R->bucket_mask = 1u << kBucketMiss;
-    if (n > 0) {
-        std::vector<uint8_t> pb((size_t)n);
-        for (int64_t i = 0; i < n; i++) {
-            const int32_t m = ctx->material_id[(size_t)i];
-            const int t = (m >= 0 && m < (int32_t)R->mats.size()) ? R->mats[(size_t)m].type : -1;
-            pb[(size_t)i] = (uint8_t)((t >= 0 && t <= 6) ? kBucketMat0 + t : kBucketNone);
-            R->bucket_mask |= 1u << pb[(size_t)i];
-        }
-        SPB_CUDA(ctx, cudaMalloc(&R->d_prim_bucket, (size_t)n));
-        SPB_CUDA(ctx, cudaMemcpy(R->d_prim_bucket, pb.data(), (size_t)n, cudaMemcpyHostToDevice));
-    }
     // a scene of Lambertian surfaces only (the diffuse Cornell boxes) is shaded in queue order by one instance
     R->sort_materials = (R->bucket_mask & ~((1u << kBucketMiss) | (1u << (kBucketMat0 + SPB_MAT_DIFFUSE)))) != 0u;
     R->scene_dirty = false;

@@ -28,6 +28,8 @@
 #include <cfloat>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "context.h"
@@ -829,6 +831,16 @@ int buildSahDevice(spb_ctx* ctx, int maxLeaf) {
     if (n64 <= 0) return SPB_OK;
     const int n = (int)n64;
     cudaStream_t st = ctx->stream;
+    // SPICA_BUILD_TIMING=1: phase times on stderr (allocation + upload, binary tree, collapse + emission, hand-over)
+    const bool timing = std::getenv("SPICA_BUILD_TIMING") != nullptr;
+    auto tPrev = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        cudaStreamSynchronize(st);
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[spb build] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - tPrev).count());
+        tPrev = now;
+    };
 
     double* d_verts = nullptr; DBox* d_prims = nullptr; int32_t *d_idx[2] = {nullptr, nullptr}, *d_order = nullptr, *d_parent = nullptr;
     DNode* d_nodes = nullptr; DBox* d_cbs = nullptr; BuildGlobals* d_g = nullptr; LargeTask* d_large[2] = {nullptr, nullptr};
@@ -862,7 +874,9 @@ int buildSahDevice(spb_ctx* ctx, int maxLeaf) {
     SB(cub::DeviceScan::ExclusiveSum(nullptr, scanBytes, d_chunks, d_chunkStart, std::max(maxLarge + 1, n / 2 + 2), st));
     SB(cudaMalloc(&d_scan, scanBytes));
 
+    lap("allocations");
     SB(cudaMemcpyAsync(d_verts, ctx->verts.data(), (size_t)n * 9 * sizeof(double), cudaMemcpyHostToDevice, st));
+    lap("vertex upload");
     initGlobalsKernel<<<1, 1, 0, st>>>(d_g);
     primBoxKernel<<<(n + 255) / 256, 256, 0, st>>>(d_verts, n, d_prims, d_idx[0], d_g);
     rootKernel<<<1, 1, 0, st>>>(d_g, d_nodes, d_cbs, d_parent, n);
@@ -917,6 +931,7 @@ int buildSahDevice(spb_ctx* ctx, int maxLeaf) {
     SB(cudaMemcpyAsync(&hg, d_g, sizeof(hg), cudaMemcpyDeviceToHost, st));
     SB(cudaStreamSynchronize(st));
     SB(cudaGetLastError());
+    lap("binary tree");
     const int nNodes = (int)hg.nodeCounter;
     if (nNodes != nNodesMax) { freeAll(); return fail(ctx, SPB_ERR_CUDA, "internal: the device builder produced " + std::to_string(nNodes) + " nodes for " + std::to_string(n) + " triangles"); }
     // the large-node scratch is dead
@@ -989,6 +1004,7 @@ int buildSahDevice(spb_ctx* ctx, int maxLeaf) {
         nLevel = (int)tot[0];
         lv ^= 1;
     }
+    lap("collapse + emission");
     if ((int64_t)triBase != n64) { freeAll(); return fail(ctx, SPB_ERR_CUDA, "internal: the device collapse emitted " + std::to_string(triBase) + " of " + std::to_string(n) + " triangles"); }
     if (depth > kStackCapacity - 2) { freeAll(); return fail(ctx, SPB_ERR_UNSUPPORTED, "spb_bvh_build: wide tree deeper than the traversal stack (" + std::to_string(depth) + ")"); }
     SB(cudaMemcpyAsync(&hg, d_g, sizeof(hg), cudaMemcpyDeviceToHost, st));
@@ -1008,6 +1024,7 @@ int buildSahDevice(spb_ctx* ctx, int maxLeaf) {
     keepWide = true;
     d_wide = nullptr;
     freeAll();
+    lap("hand-over + frees");
     return SPB_OK;
 }
 #undef SB
