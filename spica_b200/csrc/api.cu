@@ -130,6 +130,7 @@ int spb_ctx_create(int device, spb_ctx** out) {
     cudaMemset(ctx->d_work, 0, 4 * (spb_ctx::kPipe + 1) * sizeof(unsigned long long));
     std::memset(&ctx->sp, 0, sizeof(ctx->sp));
     ctx->sp.empty = 1; ctx->sp.f32_one = 0x3f800000u;
+    renderStateEnsure(ctx);
     *out = ctx;
     return SPB_OK;
 }
@@ -159,9 +160,11 @@ int spb_scene_set_triangles(spb_ctx* ctx, const double* verts, const float* norm
     if (n > 0x7fffffff / 2) return fail(ctx, SPB_ERR_UNSUPPORTED, "more than 2^30 triangles");
     cudaSetDevice(ctx->device);
     ctx->n_tris = n;
-    ctx->verts.assign(verts, verts + n * 9);
-    if (normals) ctx->normals.assign(normals, normals + n * 9); else ctx->normals.clear();
-    if (uvs) ctx->uvs.assign(uvs, uvs + n * 6); else ctx->uvs.clear();
+    auto geo = std::make_shared<spb_ctx::Geometry>();
+    geo->verts.assign(verts, verts + n * 9);
+    if (normals) geo->normals.assign(normals, normals + n * 9);
+    if (uvs) geo->uvs.assign(uvs, uvs + n * 6);
+    ctx->geo = geo;
     if (material_id) ctx->material_id.assign(material_id, material_id + n); else ctx->material_id.assign((size_t)n, 0);
     if (light_id) ctx->light_id.assign(light_id, light_id + n); else ctx->light_id.assign((size_t)n, -1);
     freeBvhDevice(ctx);
@@ -207,10 +210,10 @@ int spb_bvh_build(spb_ctx* ctx, const spb_build_opts* opts) {
         const int rc = buildLbvhDevice(ctx, &ctx->bin);
         if (rc) return rc;
     } else {
-        build_binary_sah(ctx->verts.data(), ctx->n_tris, o.sah_bins, &ctx->bin);
+        build_binary_sah(ctx->geo->verts.data(), ctx->n_tris, o.sah_bins, &ctx->bin);
     }
     std::string err;
-    if (!encode_wide(ctx->bin, ctx->verts.data(), ctx->n_tris, o.max_leaf_tris, &ctx->bvh, &err))
+    if (!encode_wide(ctx->bin, ctx->geo->verts.data(), ctx->n_tris, o.max_leaf_tris, &ctx->bvh, &err))
         return fail(ctx, SPB_ERR_UNSUPPORTED, "spb_bvh_build: " + err);
     ctx->build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     ctx->builder_used = o.builder;
@@ -223,9 +226,9 @@ int spb_bvh_import_binary(spb_ctx* ctx, const spb_import_node* nodes, int64_t n_
     cudaSetDevice(ctx->device);
     const auto t0 = std::chrono::steady_clock::now();
     std::string err;
-    if (!import_binary(nodes, n_nodes, root, ctx->verts.data(), ctx->n_tris, &ctx->bin, &err))
+    if (!import_binary(nodes, n_nodes, root, ctx->geo->verts.data(), ctx->n_tris, &ctx->bin, &err))
         return fail(ctx, SPB_ERR_INVALID, "spb_bvh_import_binary: " + err);
-    if (!encode_wide(ctx->bin, ctx->verts.data(), ctx->n_tris, 3, &ctx->bvh, &err))
+    if (!encode_wide(ctx->bin, ctx->geo->verts.data(), ctx->n_tris, 3, &ctx->bvh, &err))
         return fail(ctx, SPB_ERR_UNSUPPORTED, "spb_bvh_import_binary: " + err);
     ctx->build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     ctx->builder_used = SPB_BUILDER_HOST_SAH;
@@ -286,7 +289,7 @@ int spb_ctx_clone_scene(spb_ctx* dst, spb_ctx* src) {
     const auto t0 = std::chrono::steady_clock::now();
     cudaSetDevice(dst->device);
     dst->n_tris = src->n_tris;
-    dst->verts = src->verts; dst->normals = src->normals; dst->uvs = src->uvs;
+    dst->geo = src->geo;                 // shared, not copied: 72 B per triangle stay where they are
     dst->material_id = src->material_id; dst->light_id = src->light_id;
     freeBvhDevice(dst);
     dst->bin = BinaryBVH();

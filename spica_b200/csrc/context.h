@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <memory>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -22,11 +23,15 @@ struct spb_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string err;
 
-    // host copies of the scene (the builder runs on the host; also the source for re-builds)
-    std::vector<double>  verts;          // 9 per triangle
-    std::vector<float>   normals;        // 9 per triangle or empty
-    std::vector<float>   uvs;            // 6 per triangle or empty
-    std::vector<int32_t> material_id, light_id;
+    // host copy of the geometry: what the builders and the shading-record kernel are fed from.  Shared (not copied) between
+    // a context and its clones (spb_ctx_clone_scene); replaced, never modified, by spb_scene_set_triangles.
+    struct Geometry {
+        std::vector<double>  verts;      // 9 per triangle
+        std::vector<float>   normals;    // 9 per triangle or empty
+        std::vector<float>   uvs;        // 6 per triangle or empty
+    };
+    std::shared_ptr<const Geometry> geo = std::make_shared<Geometry>();
+    std::vector<int32_t> material_id, light_id;      // per context: the attributes may be re-set without touching the tree
     int64_t n_tris = 0;
 
     spb::BinaryBVH bin;
@@ -75,6 +80,7 @@ namespace spb {
 int  fail(spb_ctx* ctx, int code, const std::string& msg);
 bool cudaOk(spb_ctx* ctx, cudaError_t e, const char* what);
 void setGlobalError(const std::string& msg);
+void renderStateEnsure(spb_ctx* ctx);    // integrator.cu: the render state exists from spb_ctx_create on (so that calls from two host threads never race to create it)
 void renderStateDestroy(spb_ctx* ctx);   // integrator.cu
 void renderSceneClone(spb_ctx* dst, spb_ctx* src);   // integrator.cu: materials, lights, textures, environment of src -> dst (host side; uploaded by the next spb_render_begin)
 void renderSceneChanged(spb_ctx* ctx);   // integrator.cu: geometry / attributes changed, a new spb_render_begin is required

@@ -753,6 +753,8 @@ void renderSceneChanged(spb_ctx* ctx) {
     R->begun = false;
 }
 
+void renderStateEnsure(spb_ctx* ctx) { rs(ctx); }
+
 void renderSceneClone(spb_ctx* dst, spb_ctx* src) {
     RenderState* S = src->render;
     renderSceneChanged(dst);
@@ -842,7 +844,7 @@ static int uploadScene(spb_ctx* ctx, RenderState* R) {
     freeScene(R);
     const int64_t n = ctx->n_tris;
     R->n_tris = n;
-    const bool hasN = !ctx->normals.empty(), hasUV = !ctx->uvs.empty();
+    const bool hasN = !ctx->geo->normals.empty(), hasUV = !ctx->geo->uvs.empty();
     cudaStream_t st = ctx->stream;
     const size_t nm0 = std::max<size_t>(R->mats.size(), 1);
     SPB_CUDA(ctx, cudaMalloc(&R->d_mats, nm0 * sizeof(spb_material)));
@@ -856,17 +858,17 @@ static int uploadScene(spb_ctx* ctx, RenderState* R) {
         US(cudaMalloc(&R->d_prim_bucket, (size_t)n));
         US(cudaMalloc(&d_v, (size_t)n * 9 * sizeof(double)));
         US(cudaMalloc(&d_m, (size_t)n * 4)); US(cudaMalloc(&d_l, (size_t)n * 4)); US(cudaMalloc(&d_mask, 4));
-        US(cudaMemcpyAsync(d_v, ctx->verts.data(), (size_t)n * 9 * sizeof(double), cudaMemcpyHostToDevice, st));
+        US(cudaMemcpyAsync(d_v, ctx->geo->verts.data(), (size_t)n * 9 * sizeof(double), cudaMemcpyHostToDevice, st));
         US(cudaMemcpyAsync(d_m, ctx->material_id.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
         US(cudaMemcpyAsync(d_l, ctx->light_id.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
         US(cudaMemsetAsync(d_mask, 0, 4, st));
         if (hasN) {
             US(cudaMalloc(&R->d_vnormals, (size_t)n * 9 * sizeof(float)));
-            US(cudaMemcpyAsync(R->d_vnormals, ctx->normals.data(), (size_t)n * 9 * sizeof(float), cudaMemcpyHostToDevice, st));
+            US(cudaMemcpyAsync(R->d_vnormals, ctx->geo->normals.data(), (size_t)n * 9 * sizeof(float), cudaMemcpyHostToDevice, st));
         }
         if (hasUV) {
             US(cudaMalloc(&d_uv, (size_t)n * 6 * sizeof(float)));
-            US(cudaMemcpyAsync(d_uv, ctx->uvs.data(), (size_t)n * 6 * sizeof(float), cudaMemcpyHostToDevice, st));
+            US(cudaMemcpyAsync(d_uv, ctx->geo->uvs.data(), (size_t)n * 6 * sizeof(float), cudaMemcpyHostToDevice, st));
         }
         shadeTriKernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_v, R->d_vnormals, d_uv, d_m, d_l, n, R->d_mats, (int)R->mats.size(), R->d_tris, R->d_prim_bucket);
         bucketMaskKernel<<<ctx->sm_count * 4, 256, 0, st>>>(R->d_prim_bucket, n, d_mask);
@@ -895,7 +897,7 @@ static int uploadScene(spb_ctx* ctx, RenderState* R) {
                                              (size_t)(t.texel_offset + (int64_t)t.width * t.height) * 3 > R->texels.size()))
                 return fail(ctx, SPB_ERR_INVALID, "bitmap texture outside the texel array");
         std::vector<float> uv((size_t)n * 6, 0.f);
-        if (!ctx->uvs.empty()) uv = ctx->uvs;
+        if (!ctx->geo->uvs.empty()) uv = ctx->geo->uvs;
         std::vector<float4> tx(std::max<size_t>(R->texels.size() / 3, 1));
         for (size_t i = 0; i < R->texels.size() / 3; i++) tx[i] = make_float4(R->texels[i * 3], R->texels[i * 3 + 1], R->texels[i * 3 + 2], 0.f);
         SPB_CUDA(ctx, cudaMalloc(&R->d_mat_tex, R->mat_tex.size() * sizeof(int32_t)));
@@ -1525,14 +1527,19 @@ int spb_comm_init(spb_ctx* ctx, const char id[SPB_COMM_ID_BYTES], int32_t n_rank
     }
     // NCCL connects its channels lazily inside the first collective (tens of ms over 8 GPUs): do that here, as
     // part of communicator set-up, so that the one all-reduce of a frame costs what the transfer costs
+    // (on a stream of its own: a host may bring the communicator up on one thread while another thread of the same context is
+    // inside spb_render_begin, whose stream is being captured into the loop's graph)
     ncclAllReduce_t ar = (ncclAllReduce_t)dlsym(lib, "ncclAllReduce");
     if (ar) {
+        cudaStream_t ws = nullptr;
         float* d_warm = nullptr;
+        SPB_CUDA(ctx, cudaStreamCreateWithFlags(&ws, cudaStreamNonBlocking));
         SPB_CUDA(ctx, cudaMalloc(&d_warm, 1024 * sizeof(float)));
-        SPB_CUDA(ctx, cudaMemsetAsync(d_warm, 0, 1024 * sizeof(float), ctx->stream));
-        const int wrc = ar(d_warm, d_warm, 1024, 7, 0, R->comm, ctx->stream);
-        SPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        SPB_CUDA(ctx, cudaMemsetAsync(d_warm, 0, 1024 * sizeof(float), ws));
+        const int wrc = ar(d_warm, d_warm, 1024, 7, 0, R->comm, ws);
+        SPB_CUDA(ctx, cudaStreamSynchronize(ws));
         cudaFree(d_warm);
+        cudaStreamDestroy(ws);
         if (wrc != 0) return fail(ctx, SPB_ERR_CUDA, "ncclAllReduce (communicator warm-up) failed");
     }
     return SPB_OK;
@@ -1578,12 +1585,19 @@ static int filmReduceNow(spb_ctx* ctx, RenderState* R, int32_t root) {
     }
     SPB_CUDA(ctx, cudaEventRecord(R->ev_r1, st));
     if ((rc = ncclAsyncCheck(ctx, R, "after the film reduce was enqueued"))) return rc;
-    // wait with a watchdog on the communicator instead of a blind synchronize: a dead peer would hang it for ever
+    // wait with a watchdog on the communicator instead of a blind synchronize: a dead peer would hang it for ever.  The
+    // communicator is only asked every 5 ms: ncclCommGetAsyncError in a tight loop competes with NCCL's own proxy thread
+    // (r02j: 8.9 ms for the 33 MB reduce of C3 on 8 GPUs with a check per spin).
+    auto lastCheck = std::chrono::steady_clock::now();
     for (;;) {
         const cudaError_t q = cudaEventQuery(R->ev_r1);
         if (q == cudaSuccess) break;
         if (q != cudaErrorNotReady) { cudaOk(ctx, q, "cudaEventQuery(film reduce)"); return SPB_ERR_CUDA; }
-        if ((rc = ncclAsyncCheck(ctx, R, "while the film reduce was running"))) return rc;
+        const auto now = std::chrono::steady_clock::now();
+        if (now - lastCheck > std::chrono::milliseconds(5)) {
+            lastCheck = now;
+            if ((rc = ncclAsyncCheck(ctx, R, "while the film reduce was running"))) return rc;
+        }
         std::this_thread::yield();
     }
     if ((rc = ncclAsyncCheck(ctx, R, "after the film reduce"))) return rc;

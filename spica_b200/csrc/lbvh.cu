@@ -123,7 +123,7 @@ int buildLbvhDevice(spb_ctx* ctx, BinaryBVH* out) {
     if (n64 <= 0) return SPB_OK;
     if (n64 == 1) {
         BinNode nd;
-        const double* v = ctx->verts.data();
+        const double* v = ctx->geo->verts.data();
         for (int a = 0; a < 3; a++) { nd.lo[a] = std::min(v[a], std::min(v[3 + a], v[6 + a])); nd.hi[a] = std::max(v[a], std::max(v[3 + a], v[6 + a])); }
         nd.left = nd.right = -1; nd.first = 0; nd.count = 1;
         out->nodes.push_back(nd); out->order.push_back(0); out->root = 0;
@@ -133,7 +133,7 @@ int buildLbvhDevice(spb_ctx* ctx, BinaryBVH* out) {
     // centroid bounds on the host (one pass over data that is already host-resident)
     double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
     for (int64_t i = 0; i < n64; i++) {
-        const double* v = ctx->verts.data() + i * 9;
+        const double* v = ctx->geo->verts.data() + i * 9;
         for (int a = 0; a < 3; a++) {
             const double c = 0.5 * (std::min(v[a], std::min(v[3 + a], v[6 + a])) + std::max(v[a], std::max(v[3 + a], v[6 + a])));
             lo[a] = std::min(lo[a], c); hi[a] = std::max(hi[a], c);
@@ -156,7 +156,7 @@ int buildLbvhDevice(spb_ctx* ctx, BinaryBVH* out) {
     LB(cudaMalloc(&d_parent, (size_t)(2 * n - 1) * 4));
     LB(cudaMalloc(&d_nodes, (size_t)(2 * n - 1) * sizeof(DevBinNode)));
     LB(cudaMalloc(&d_flags, (size_t)n * 4));
-    LB(cudaMemcpyAsync(d_verts, ctx->verts.data(), (size_t)n * 9 * sizeof(double), cudaMemcpyHostToDevice, st));
+    LB(cudaMemcpyAsync(d_verts, ctx->geo->verts.data(), (size_t)n * 9 * sizeof(double), cudaMemcpyHostToDevice, st));
     const int B = 256;
     mortonKernel<<<(n + B - 1) / B, B, 0, st>>>(d_verts, n, dlo, inv, d_k0, d_v0);
     size_t tmpBytes = 0;

@@ -875,7 +875,7 @@ int buildSahDevice(spb_ctx* ctx, int maxLeaf) {
     SB(cudaMalloc(&d_scan, scanBytes));
 
     lap("allocations");
-    SB(cudaMemcpyAsync(d_verts, ctx->verts.data(), (size_t)n * 9 * sizeof(double), cudaMemcpyHostToDevice, st));
+    SB(cudaMemcpyAsync(d_verts, ctx->geo->verts.data(), (size_t)n * 9 * sizeof(double), cudaMemcpyHostToDevice, st));
     lap("vertex upload");
     initGlobalsKernel<<<1, 1, 0, st>>>(d_g);
     primBoxKernel<<<(n + 255) / 256, 256, 0, st>>>(d_verts, n, d_prims, d_idx[0], d_g);

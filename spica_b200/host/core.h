@@ -313,5 +313,8 @@ struct HostOptions {
     std::function<void(const Image&)> onImage;   // receives the final normalised image
 };
 HostOptions& hostOptions();
+void hostGpuPrewarm(int gpus);           // start CUDA, one context per GPU and the NCCL communicator on background threads (call before parsing)
+void hostGpuFinish();                    // join them (after the render)
+void hostPhaseLap(const char* what);     // SPICA_TIMING=1: "[TIME] what  seconds since the first lap" on stdout
 
 }  // namespace spica

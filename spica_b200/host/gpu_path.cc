@@ -5,6 +5,7 @@
 //                                                      through Film::setImage + Film::save (core/film.cc:23-63)
 // Nothing is computed on the CPU here; a missing device is a FatalError (no fallback).
 #include <chrono>
+#include <condition_variable>
 #include <cstring>
 #include <ctime>
 #include <map>
@@ -17,8 +18,90 @@
 namespace spica {
 
 namespace {
+// SPICA_TIMING=1: wall-clock phases of the GPU plugins on stdout ([TIME] lines), measured from process start
+struct PhaseClock {
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now(), last = t0;
+    bool on = getenv("SPICA_TIMING") != nullptr;
+    void lap(const char* what) {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        printf("[TIME] %-34s %8.3f s  (+%.3f)\n", what, std::chrono::duration<double>(now - t0).count(), std::chrono::duration<double>(now - last).count());
+        last = now;
+    }
+};
+PhaseClock& phaseClock() { static PhaseClock c; return c; }
+
 void check(spb_ctx* ctx, int rc, const char* what) {
     if (rc != SPB_OK) FatalError("%s failed (%d): %s", what, rc, spb_last_error(ctx));
+}
+
+// Everything about the GPUs that does not depend on the scene -- CUDA start-up (1.6 s and more on a box without the
+// persistence daemon), one context per GPU, the NCCL communicator -- is started on background threads the moment the number
+// of GPUs is known (hostGpuPrewarm, called from main() before the scene file is even opened) and picked up when needed.
+struct GpuPool {
+    int first = 0, G = 0;
+    bool started = false;
+    char commId[SPB_COMM_ID_BYTES];
+    std::vector<std::thread> th;
+    std::vector<spb_ctx*> ctx;
+    std::vector<int> ctxDone, commDone;         // guarded by mu
+    std::mutex mu;
+    std::condition_variable cv;
+    ~GpuPool() { for (auto& t : th) if (t.joinable()) t.join(); }
+};
+GpuPool& gpuPool() { static GpuPool p; return p; }
+
+void gpuPoolStart(int firstDevice, int G) {
+    GpuPool& p = gpuPool();
+    if (p.started) return;
+    p.started = true; p.first = firstDevice; p.G = G;
+    p.ctx.assign(G, nullptr); p.ctxDone.assign(G, 0); p.commDone.assign(G, 0);
+    for (int g = 0; g < G; g++) {
+        p.th.emplace_back([&p, g]() {
+            spb_ctx* c = nullptr;
+            check(nullptr, spb_ctx_create(p.first + g, &c), "spb_ctx_create");
+            { std::lock_guard<std::mutex> lk(p.mu); p.ctx[g] = c; p.ctxDone[g] = 1; }
+            p.cv.notify_all();
+            if (p.G > 1) {
+                if (g == 0) {
+                    check(nullptr, spb_comm_get_unique_id(p.commId), "spb_comm_get_unique_id");
+                    { std::lock_guard<std::mutex> lk(p.mu); p.commDone[0] = -1; }       // the id exists
+                    p.cv.notify_all();
+                } else {
+                    std::unique_lock<std::mutex> lk(p.mu);
+                    p.cv.wait(lk, [&] { return p.commDone[0] != 0; });
+                }
+                check(c, spb_comm_init(c, p.commId, p.G, g), "spb_comm_init");
+                { std::lock_guard<std::mutex> lk(p.mu); p.commDone[g] = 1; }
+                p.cv.notify_all();
+            }
+        });
+    }
+}
+// the context of GPU `first + g` (created here when nothing was pre-warmed, e.g. a plain library user)
+spb_ctx* gpuPoolContext(int device, int g) {
+    GpuPool& p = gpuPool();
+    if (!p.started || device != p.first || g >= p.G) {
+        spb_ctx* c = nullptr;
+        check(nullptr, spb_ctx_create(device + g, &c), "spb_ctx_create");
+        return c;
+    }
+    std::unique_lock<std::mutex> lk(p.mu);
+    p.cv.wait(lk, [&] { return p.ctxDone[g] != 0; });
+    return p.ctx[g];
+}
+// true when the pool brought (or is bringing) the communicator up for this job; waits for rank g's part of it
+bool gpuPoolCommReady(int device, int G, int g) {
+    GpuPool& p = gpuPool();
+    if (!p.started || device != p.first || G != p.G || G < 2) return false;
+    std::unique_lock<std::mutex> lk(p.mu);
+    p.cv.wait(lk, [&] { return p.commDone[g] == 1; });
+    return true;
+}
+void gpuPoolFinish() {
+    GpuPool& p = gpuPool();
+    for (auto& t : p.th) if (t.joinable()) t.join();
+    p.th.clear(); p.started = false;
 }
 
 struct FlatScene {              // the primitives as the C ABI takes them
@@ -86,9 +169,12 @@ public:
         params.getBool("useSIMD", false, true);                         // accelerators/bvh.cc:127-131 (no meaning on the GPU)
         const char* dev = getenv("SPICA_DEVICE");
         device_ = dev ? atoi(dev) : 0;
-        check(nullptr, spb_ctx_create(device_, &ctx_), "spb_ctx_create");
+        phaseClock().lap("scene parsed, accelerator ctor");
+        ctx_ = gpuPoolContext(device_, 0);
+        phaseClock().lap("context of GPU 0 ready");
         flatten(prims, &flat_);
         uploadGeometry(ctx_, flat_);
+        phaseClock().lap("flatten + set_triangles + build");
         spb_bvh_stats st;
         check(ctx_, spb_bvh_get_stats(ctx_, &st), "spb_bvh_get_stats");
         for (int k = 0; k < 3; k++) { lo_[k] = st.world_lo[k]; hi_[k] = st.world_hi[k]; }
@@ -172,13 +258,14 @@ public:
         const int G = std::max(1, opt.gpus);
         std::vector<spb_ctx*> ctxs(G, nullptr);
         ctxs[0] = accel->ctx();
+        const bool pooledComm = G > 1 && gpuPool().started && gpuPool().first == accel->device() && gpuPool().G == G;
         char commId[SPB_COMM_ID_BYTES];
-        if (G > 1) check(nullptr, spb_comm_get_unique_id(commId), "spb_comm_get_unique_id");
+        if (G > 1 && !pooledComm) check(nullptr, spb_comm_get_unique_id(commId), "spb_comm_get_unique_id");
 
         // replicas: scene + BVH on every GPU; the tree is built ONCE (by the accelerator) and copied device to device
         auto replicate = [&](int g) {
             if (g == 0) return;
-            check(nullptr, spb_ctx_create(accel->device() + g, &ctxs[g]), "spb_ctx_create");
+            ctxs[g] = gpuPoolContext(accel->device(), g);
             check(ctxs[g], spb_ctx_clone_scene(ctxs[g], ctxs[0]), "spb_ctx_clone_scene");
         };
         auto setup = [&](int g) {
@@ -195,7 +282,6 @@ public:
                 const double c[3] = {env->worldCenter.x, env->worldCenter.y, env->worldCenter.z};
                 check(ctx, spb_scene_set_envmap(ctx, rgb.data(), env->image.width, env->image.height, &env->toWorld.getMat().m[0][0], env->scale, c, env->worldRadius), "spb_scene_set_envmap");
             }
-            if (G > 1) check(ctx, spb_comm_init(ctx, commId, G, g), "spb_comm_init");
             if (const char* ws = getenv("SPICA_WAVE_SLOTS")) check(ctx, spb_set_option(ctx, "wave_slots", atoll(ws)), "spb_set_option(wave_slots)");
             check(ctx, spb_render_begin(ctx, &desc), "spb_render_begin");
         };
@@ -205,8 +291,16 @@ public:
             fn(0);
             for (auto& t : th) t.join();
         };
+        phaseClock().lap("integrator: lights resolved");
         forEachGpu(replicate);
+        phaseClock().lap("replicas: ctx_create + clone");
+        // the NCCL communicator takes a second or two to come up: it does so on its own threads while the scene is uploaded
+        std::vector<std::thread> commThreads;
+        if (G > 1 && !pooledComm) for (int g = 0; g < G; g++) commThreads.emplace_back([&, g]() { check(ctxs[g], spb_comm_init(ctxs[g], commId, G, g), "spb_comm_init"); });
         forEachGpu(setup);
+        for (auto& t : commThreads) t.join();
+        if (pooledComm) for (int g = 0; g < G; g++) gpuPoolCommReady(accel->device(), G, g);
+        phaseClock().lap("scene upload, comm_init, begin");
 
         std::vector<float> rgb((size_t)width * height * 3);
         auto publish = [&](int id) {
@@ -251,16 +345,25 @@ public:
             MsgInfo("rendered %d spp at %dx%d on %d GPU(s) in %.3f s: %.2f Msamples/s; GPU0: %.1f Mrays/s", numSamples, width, height, G, sec,
                     1e-6 * width * height * (double)numSamples / sec,
                     st.render_ms > 0 ? 1e-3 * (double)(st.rays_closest + st.rays_shadow + st.rays_mis) / st.render_ms : 0.0);
+            phaseClock().lap("render + reduce");
             publish(numSamples);
+            phaseClock().lap("publish (resolve, encode, save)");
         }
-        for (int g = 1; g < G; g++) { spb_comm_destroy(ctxs[g]); spb_ctx_destroy(ctxs[g]); }
-        if (G > 1) spb_comm_destroy(ctxs[0]);
+        forEachGpu([&](int g) { if (G > 1) spb_comm_destroy(ctxs[g]); if (g > 0) spb_ctx_destroy(ctxs[g]); });
+        phaseClock().lap("replicas destroyed");
         printf("Finish!!\n");
     }
 private:
     std::shared_ptr<Sampler> sampler_;
     int mode_;
 };
+
+void hostPhaseLap(const char* what) { phaseClock().lap(what); }
+void hostGpuPrewarm(int gpus) {
+    const char* dev = getenv("SPICA_DEVICE");
+    gpuPoolStart(dev ? atoi(dev) : 0, std::max(1, gpus));
+}
+void hostGpuFinish() { gpuPoolFinish(); }
 
 void registerGpuPlugins() {
     PluginManager& pm = PluginManager::getInstance();

@@ -12,6 +12,7 @@ namespace fs = std::filesystem;
 using namespace spica;
 
 int main(int argc, char** argv) {
+    hostPhaseLap("main entered");
     std::string input, output;
     int threads = 4;
     HostOptions& opt = hostOptions();
@@ -34,10 +35,13 @@ int main(int argc, char** argv) {
         if (ec) FatalError("Failed to open file:%s\n", input.c_str());
         output = full.substr(0, full.find_last_of('.'));
     }
+    hostGpuPrewarm(opt.gpus);                                           // CUDA start-up and the communicator run behind the scene loading
     RenderParams& params = RenderParams::getInstance();
     params.add("numUserThreads", threads);
     params.add("outputFile", output);
     SceneParser parser(input);
     parser.parse();
+    hostGpuFinish();
+    hostPhaseLap("parse() returned");
     return 0;
 }

@@ -161,7 +161,6 @@ public:
             }
             check(ctx, spb_scene_set_lights(ctx, lights.data(), (int32_t)lights.size()), "spb_scene_set_lights");
             if (env) check(ctx, spb_scene_set_envmap(ctx, envRgb.data(), envW, envH, envL2W, 1.0, envCenter, env->worldRadius_), "spb_scene_set_envmap");
-            if (G > 1) check(ctx, spb_comm_init(ctx, commId, G, g), "spb_comm_init");
             if (const char* ws = getenv("SPICA_WAVE_SLOTS")) check(ctx, spb_set_option(ctx, "wave_slots", atoll(ws)), "spb_set_option(wave_slots)");
             check(ctx, spb_render_begin(ctx, &desc), "spb_render_begin");
         };
@@ -172,7 +171,11 @@ public:
             for (auto& t : th) t.join();
         };
         forEachGpu(replicate);
+        // the NCCL communicator takes a second or two to come up: it does so on its own threads while the scene is uploaded
+        std::vector<std::thread> commThreads;
+        if (G > 1) for (int g = 0; g < G; g++) commThreads.emplace_back([&, g]() { check(ctxs[g], spb_comm_init(ctxs[g], commId, G, g), "spb_comm_init"); });
         forEachGpu(setup);
+        for (auto& t : commThreads) t.join();
 
         std::vector<float> rgb((size_t)width * height * 3);
         auto publish = [&](int id) {
@@ -208,8 +211,7 @@ public:
                     st.render_ms > 0 ? 1e-3 * (double)(st.rays_closest + st.rays_shadow + st.rays_mis) / st.render_ms : 0.0);
             publish(numSamples);
         }
-        for (int g = 1; g < G; g++) { spb_comm_destroy(ctxs[g]); spb_ctx_destroy(ctxs[g]); }
-        if (G > 1) spb_comm_destroy(ctxs[0]);
+        forEachGpu([&](int g) { if (G > 1) spb_comm_destroy(ctxs[g]); if (g > 0) spb_ctx_destroy(ctxs[g]); });
         printf("Finish!!\n");
     }
 

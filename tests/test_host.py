@@ -134,3 +134,21 @@ def test_envmap_roughdielectric_ply_scene_matches_reference(tmp_path):
     out = os.environ.get("SPB_TEST_OUT")
     if out:
         np.save(os.path.join(out, "envtorus_gpu.npy"), hi.astype(np.float32))
+
+
+@pytest.mark.gpu
+def test_two_gpus_render_the_single_gpu_image(tmp_path):
+    """`--gpus 2`: the replica's scene and BVH are cloned device to device (spb_ctx_clone_scene), the sample indices are
+    interleaved, the films are summed with one NCCL reduce to GPU 0 -- and the image is the one-GPU image up to float
+    summation order.  (Skipped on a one-GPU box.)"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    xml = os.path.join(SCENES, "cornell_glossy.xml")
+    one = host.render_scene(xml, str(tmp_path / "g1"), gpus=1, seed=13)
+    two = host.render_scene(xml, str(tmp_path / "g2"), gpus=2, seed=13)
+    assert np.allclose(one, two, rtol=1e-4, atol=1e-5)
+    xml = os.path.join(SCENES, "envtorus.xml")
+    one = host.render_scene(xml, str(tmp_path / "e1"), gpus=1, seed=14)
+    two = host.render_scene(xml, str(tmp_path / "e2"), gpus=2, seed=14)
+    assert np.allclose(one, two, rtol=1e-4, atol=1e-5)
