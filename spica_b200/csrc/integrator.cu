@@ -27,6 +27,7 @@
 // reports an empty pipeline through mapped host memory (polled one launch behind, so the stream never drains).
 #include <chrono>
 #include <condition_variable>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <functional>
@@ -1491,6 +1492,12 @@ typedef const char* (*ncclGetErrorString_t)(int);
 static void* ncclLib() {
     static void* lib = nullptr;
     if (lib) return lib;
+    // A communicator that carries one 33-133 MB reduce per frame needs neither NVLS multicast groups nor 32 channels, and
+    // setting them up is most of its bring-up time: 8 GPUs in one process, 2.3-2.5 s with NCCL's defaults, 1.3-1.6 s with
+    // these (profiles/r02q_cli_phases_g8.txt; the reduce itself takes 0.2 ms either way).  Only defaults: variables the user
+    // exported win, and a process whose NCCL is already initialised (bench.py under torchrun) is not affected.
+    setenv("NCCL_NVLS_ENABLE", "0", 0);
+    setenv("NCCL_MAX_NCHANNELS", "8", 0);
     const char* names[] = {"libnccl.so.2", "libnccl.so"};
     for (const char* nme : names) { lib = dlopen(nme, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
     return lib;

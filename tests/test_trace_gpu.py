@@ -3,6 +3,8 @@ against the oracle and the committed golden vectors of the real reference.
 
 Bar: primitive ids bit-exact; t bit-exact in double (and <= 1e-5 relative through the float32 hit
 record, the tolerance BASELINE.json states); any-hit flags equal."""
+import os
+
 import numpy as np
 import pytest
 
@@ -282,6 +284,24 @@ def test_export_import_and_clone_share_one_tree(gpu_ctx, golden_torus):
         assert np.allclose(clone.film_resolve(), img, rtol=1e-4, atol=1e-5)
     finally:
         clone.close()
+
+
+def test_full_size_c2_against_the_compiled_reference(gpu_ctx):
+    """BASELINE configs[1] at full size: the 1,000,000-triangle torus, 131,072 rays of each C2 ray set, answered by the
+    unmodified reference's BVHAccel::intersect (tests/golden/make_golden_c2.py -> raycast_c2_ref.npz).  Ids bit-exact (rays whose
+    two candidates are hit at exactly the same double t may name the other triangle: own-built tree), t within 1e-5."""
+    from tests.golden.make_golden_c2 import c2_rays
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "raycast_c2_ref.npz"))
+    v, f = scenes.torus_mesh(1000, 500)
+    tris = scenes.mesh_triangles(v, f)
+    inc, pri, anyr = c2_rays(v)
+    assert len(inc) == int(g["n"])
+    gpu_ctx.set_triangles(tris)
+    gpu_ctx.build()
+    assert gpu_ctx.stats()["builder"] == 0 and gpu_ctx.stats()["max_depth"] <= 14
+    _check_closest(gpu_ctx, tris, inc, g["prim_incoherent"], g["t_incoherent"], max_ties=0)
+    _check_closest(gpu_ctx, tris, pri, g["prim_primary"], g["t_primary"], max_ties=8)       # the pinhole grid's diagonal: genuine ties
+    assert np.array_equal(gpu_ctx.trace_any(anyr), g["occluded"])
 
 
 def test_gpu_lbvh_builder_gives_identical_hits(gpu_ctx, golden_torus, golden_cube):
