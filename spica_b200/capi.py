@@ -355,6 +355,9 @@ class Context:
         self._check(self.L.spb_scene_set_lights(self.h, arr, n))
 
     def set_envmap(self, rgb, to_world=None, scale=1.0, center=(0.0, 0.0, 0.0), radius=2.0):
+        if rgb is None:                  # removes the environment map
+            self._check(self.L.spb_scene_set_envmap(self.h, None, 0, 0, None, 1.0, None, 2.0))
+            return
         rgb = np.ascontiguousarray(rgb, dtype=np.float32)
         h, w = rgb.shape[:2]
         m = np.ascontiguousarray(np.eye(4) if to_world is None else to_world, dtype=np.float64)

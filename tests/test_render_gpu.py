@@ -231,3 +231,37 @@ def test_scene_change_invalidates_a_begun_render(gpu_ctx):
         gpu_ctx.set_option("trace_variant", 99)
     img = capi.cornell_render(gpu_ctx, 32, 32, 2, seed=2)
     assert np.isfinite(img).all() and img.mean() > 0
+
+
+def test_unusual_scenes_render(gpu_ctx):
+    """Paths the fixtures do not reach: vertices that are not float32-exact (80-byte triangle records: the traversal falls back to
+    the float64-triangle kernels inside the render loop), and a scene with no triangles at all under an environment map."""
+    ref = capi.cornell_render(gpu_ctx, 64, 64, 32, seed=6)
+    tris, mid, lid, mats, lights = scenes.cornell_arrays("diffuse")
+    gpu_ctx.set_triangles(tris * (1.0 + 1e-10), material_id=mid, light_id=lid)
+    gpu_ctx.set_materials(mats)
+    gpu_ctx.set_lights(lights)
+    gpu_ctx.build()
+    assert gpu_ctx.stats()["tri_format"] == 1
+    cam = scenes.CORNELL_CAMERA
+    c2w, r2c = scenes.perspective_camera(scenes.look_at(cam["origin"], cam["target"], cam["up"]), cam["fov"], 64, 64)
+    gpu_ctx.render_begin(64, 64, c2w, r2c, max_depth=8, seed=6)
+    gpu_ctx.render_samples(0, 32, 1)
+    img = gpu_ctx.film_resolve()
+    assert np.isfinite(img).all() and abs(img.mean() / ref.mean() - 1.0) < 0.02, (img.mean(), ref.mean())
+    # nothing but the sky: every camera ray escapes and is answered by Envmap::Le (lights/envmap.cc:130-134)
+    sc = scenes.envscene_arrays(8, 4)
+    gpu_ctx.set_triangles(np.zeros((0, 9)))
+    gpu_ctx.set_materials([])
+    gpu_ctx.set_envmap(sc["env"], to_world=sc["env_to_world"], scale=sc["env_scale"], radius=sc["env_radius"])
+    gpu_ctx.set_lights([], envmap_at=0)
+    gpu_ctx.build()
+    cam = sc["camera"]
+    c2w, r2c = scenes.perspective_camera(scenes.look_at(cam["origin"], cam["target"], cam["up"]), cam["fov"], 48, 32)
+    gpu_ctx.render_begin(48, 32, c2w, r2c, max_depth=4, seed=1)
+    gpu_ctx.render_samples(0, 4, 1)
+    sky = gpu_ctx.film_resolve()
+    st = gpu_ctx.render_stats()
+    assert np.isfinite(sky).all() and sky.min() > 0 and st["paths"] == 48 * 32 * 4 and st["rays_shadow"] == 0
+    assert np.array_equal(gpu_ctx.film_read()[..., 3], np.full((32, 48), 4.0, dtype=np.float32))
+    gpu_ctx.set_envmap(None)
