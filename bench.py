@@ -164,7 +164,8 @@ def cornell_c1_side_by_side():
     xml = scenes.write_cornell(d, 512, 512, 64, 8)
     secs = []
     with quiet_stdout():
-        host.render_scene(xml, os.path.join(d, "warm"), seed=1, spp=1)        # first use of the host library in this process
+        for w in range(2):                                                    # first use of the host library in this process, and the
+            host.render_scene(xml, os.path.join(d, "warm"), seed=1)           # GPU back at its clocks after the CPU-only minutes before
         for rep in range(3):
             t0 = time.perf_counter()
             img = host.render_scene(xml, os.path.join(d, "gpu"), seed=1 + rep)
