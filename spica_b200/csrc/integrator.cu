@@ -2,20 +2,22 @@
 //
 // Replaces SamplerIntegrator::render (reference core/integrator.cc:46-110) and PathIntegrator::Li
 // (integrators/path/path.cc:42-125) with uniformSampleOneLight / estimateDirectLight
-// (core/mis.cc:21-136) for whole waves of paths:
+// (core/mis.cc:21-136) for queues of paths:
 //
-//   K3 generate   camera rays for a wave of (pixel, sample) pairs          integrator.cc:80-86, perspective.cc:53-74
-//   K1 extend     closest hit for the ray queue (trace_kernels.cuh)        scene.cc:37 -> bvh.cc:331-360
-//   K4 shade      emission, NEE light sample + MIS BSDF sample, BSDF       path.cc:58-94, mis.cc:35-136
-//                 sample for the next segment, Russian roulette, queue compaction
-//   K2 connect    any-hit for the shadow queue; the unoccluded             visibility_tester.cc:21-24 -> bvh.cc:362-387
-//                 contribution is added inside the traversal kernel
-//   K1' mis       closest hit for the (rare) MIS rays; the emission is     mis.cc:113-130
-//                 added inside the traversal kernel when the expected light is hit
-//   K5 film       adds every finished path into the RGBW film              film.cc:65-74, integrator.cc:88-90
-//
-//   K5 film       every radiance term (emission, unoccluded light sample, MIS hit) goes straight   film.cc:65-74, integrator.cc:88-90
-//                 into the RGBW film with one 128-bit reduction (RED.ADD.F32x4)
+//   control       one thread: statistics, queue counters, this iteration's regeneration plan
+//   K3 generate   camera rays for the next (pixel, sample) pairs, appended   integrator.cc:80-86, perspective.cc:53-74
+//                 to the extend queue behind the surviving paths
+//   K1 extend     closest hit for the ray queue (trace_kernels.cuh)          scene.cc:37 -> bvh.cc:331-360
+//   K4 classify   (scenes with several BSDF types) queue positions sorted into one index list per material bucket
+//      shade      one kernel instance per bucket: emission, NEE light        path.cc:58-94, mis.cc:35-136
+//                 sample + MIS BSDF sample, BSDF sample for the next segment, Russian roulette; survivors are pushed
+//                 (ray + state) to the other extend queue, shadow and MIS rays to theirs
+//   K2 connect    any-hit for the shadow queue; the unoccluded               visibility_tester.cc:21-24 -> bvh.cc:362-387
+//                 contribution is added to the film inside the traversal kernel
+//   K1' mis       closest hit for the (rare) MIS rays; the emission is       mis.cc:113-130
+//                 added to the film inside the traversal kernel when the expected light is hit
+//   K5 film       every radiance term (emission, unoccluded light sample,    film.cc:65-74, integrator.cc:88-90
+//                 MIS hit) and each path's filter weight go straight into the RGBW film: one 128-bit reduction each
 //
 // STREAMING, not waves: the extend queue is topped up with new camera paths at the start of every
 // iteration (path regeneration), so every launch works on a full queue until the samples of the call
@@ -219,18 +221,6 @@ __global__ void loopBeginKernel(LoopCtl* ctl, Queues q, int first, int stride, u
     q.count[0] = 0u; q.count[1] = 0u; q.count[2] = 0u; q.count[3] = 0u;
     status[0] = 0u;
     __threadfence_system();
-}
-
-// warp-aggregated queue push: one atomic per warp per queue
-__device__ __forceinline__ uint32_t queuePush(uint32_t* counter, bool want) {
-    const unsigned mask = __ballot_sync(__activemask(), want);
-    if (!want) return 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const int leader = __ffs(mask) - 1;
-    uint32_t base = 0;
-    if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
-    base = __shfl_sync(mask, base, leader);
-    return base + __popc(mask & ((1u << lane) - 1u));
 }
 
 __device__ __forceinline__ void writeRay(float4* q, uint32_t idx, V3 o, V3 d, uint32_t tag, float tmax) {
