@@ -141,6 +141,23 @@ def test_reference_host_renders_on_the_gpu(tmp_path, variant):
 
 
 @pytest.mark.gpu
+def test_reference_host_on_two_gpus(tmp_path):
+    """SPICA_GPUS=2 under the unmodified reference host: the replica is cloned from the accelerator's context, the communicator
+    comes up on its own threads, the films meet on GPU 0 -- and the file is the one-GPU file.  (Skipped on a one-GPU box.)"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    xml = os.path.join(SCENES, "cornell_zoo.xml")
+    imgs = []
+    for g in (1, 2):
+        out = str(tmp_path / ("out%d" % g))
+        r = refhost.run(xml, out, str(tmp_path / ("run%d" % g)), REF, env={"SPICA_SEED": 5, "SPICA_GPUS": g})
+        assert r.returncode == 0, r.stderr
+        imgs.append(scenes.read_hdr(out + ".hdr"))
+    assert (np.abs(imgs[0] - imgs[1]) <= imgs[0].max(-1, keepdims=True) / 64 + 1e-6).all()      # RGBE quantisation of two float summation orders
+
+
+@pytest.mark.gpu
 def test_reference_host_directlighting_plugin(tmp_path):
     """plugins/directlighting.so: `<integrator type="directlighting">` of the unmodified reference host on the GPU."""
     g = np.load(os.path.join(GOLDEN, "cornell_direct_ref.npz"))
