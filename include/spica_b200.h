@@ -313,7 +313,7 @@ int spb_get_counters(spb_ctx* ctx, spb_counters* out);
  * 2 = 1 + warp-pooled float32 pre-test, 3 = 2 in visit / select / triangles order, 4 = 3 with the
  * stack in shared memory, 5 = 4 with three node visits per pooled triangle phase (default); every
  * variant returns the same records), "chunk_rays" (rays per pipelined chunk of the host-buffer calls,
- * default 524288), "wave_slots" (capacity of the integrator's queues = paths in flight, default 8 Mi, takes effect at
+ * default 524288), "wave_slots" (capacity of the integrator's queues = paths in flight, 240 B each, default 32 Mi but never more than 64 samples of the image, takes effect at
  * the next spb_render_begin), "render_graph" (0 = plain launches instead of the CUDA graph),
  * "shade_minb" (4/5/6: occupancy the Lambertian-only shade instance is compiled for). Unknown names
  * return SPB_ERR_INVALID.

@@ -62,7 +62,7 @@ struct spb_ctx {
                                          // 4 = 3 with the stack in shared memory, 5 = 4 with three node visits per pooled triangle phase (default;
                                          // falls back to 3 on trees deeper than the shared stack and to 2 on float64 triangles)
     int64_t opt_chunk = 1 << 19;         // rays per pipelined chunk on the host-buffer path (measured: 256K 1412, 512K 1574, 1M 1403, 2M 1364 Mrays/s; PCIe floor 1574)
-    int64_t opt_wave_slots = 1 << 23;    // capacity of the integrator's queues = paths in flight (240 B each); the streaming loop keeps them full, so the size only has to amortise the ~6 launches of an iteration
+    int64_t opt_wave_slots = 1 << 25;    // capacity of the integrator's queues = paths in flight (240 B each); the streaming loop keeps them full, so the size only has to amortise the launches and kernel tails of an iteration: 8 Mi -> 2134, 16 Mi -> 2195, 32 Mi -> 2223 Msamples/s on the diffuse Cornell box (7.7 GB of the 180 GB)
 
     // resident CTAs per SM of each traversal kernel instantiation on THIS device (the occupancy query is slow enough to matter per chunk)
     std::unordered_map<const void*, int> occupancy;

@@ -163,6 +163,8 @@ struct RenderState {
     cudaGraphExec_t graph_exec = nullptr;    // two iterations (queue 0, queue 1)
     cudaEvent_t poll[4] = {};                // the host polls h_status one graph launch behind
     cudaEvent_t ev_r0 = nullptr, ev_r1 = nullptr;
+    cudaStream_t side = nullptr;             // the MIS launch of an iteration runs here, beside the connect launch
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int64_t launches = 0; int launches_per_iteration = 6; double render_ms = 0.0, reduce_ms = 0.0;
     void* d_scratch = nullptr; size_t scratch_bytes = 0;    // grow-only staging of spb_film_resolve* / spb_film_add
     RenderWorker* worker = nullptr;
@@ -725,6 +727,9 @@ void renderStateDestroy(spb_ctx* ctx) {
     for (cudaEvent_t e : R->poll) if (e) cudaEventDestroy(e);
     if (R->ev_r0) cudaEventDestroy(R->ev_r0);
     if (R->ev_r1) cudaEventDestroy(R->ev_r1);
+    if (R->ev_fork) cudaEventDestroy(R->ev_fork);
+    if (R->ev_join) cudaEventDestroy(R->ev_join);
+    if (R->side) cudaStreamDestroy(R->side);
     if (R->comm && R->nccl_lib) {
         typedef int (*destroy_t)(void*);
         destroy_t f = (destroy_t)dlsym(R->nccl_lib, "ncclCommDestroy");
@@ -1110,9 +1115,15 @@ static int enqueueIteration(spb_ctx* ctx, RenderState* R, int cur, cudaStream_t 
     int shadeLaunches = 0;
     if ((rc = launchShade(ctx, R, cur, st, &shadeLaunches))) return rc;
     R->launches_per_iteration = 5 + shadeLaunches;
-    // connect + MIS (skipped by their own zero counts when empty)
+    // connect + MIS (skipped by their own zero counts when empty).  They are independent of each other: the MIS launch (a
+    // handful of rays, ~20 us of launch and tail) runs on a side stream next to the connect launch -- a fork and a join in
+    // the captured graph.
+    SPB_CUDA(ctx, cudaEventRecord(R->ev_fork, st));
+    SPB_CUDA(ctx, cudaStreamWaitEvent(R->side, R->ev_fork, 0));
+    if ((rc = launchTrace<false>(ctx, (const spb_ray_f32*)R->q.mis, cap, R->q.count + 3, SinkMis{R->q.mis, R->q.misC, R->d_film}, R->d_cursor + 8, R->side, true))) return rc;
+    SPB_CUDA(ctx, cudaEventRecord(R->ev_join, R->side));
     if ((rc = launchTrace<true>(ctx, (const spb_ray_f32*)R->q.shadow, cap, R->q.count + 2, SinkShadow{R->q.shadow, R->q.shadowC, R->d_film}, R->d_cursor + 4, st, true))) return rc;
-    if ((rc = launchTrace<false>(ctx, (const spb_ray_f32*)R->q.mis, cap, R->q.count + 3, SinkMis{R->q.mis, R->q.misC, R->d_film}, R->d_cursor + 8, st, true))) return rc;
+    SPB_CUDA(ctx, cudaStreamWaitEvent(st, R->ev_join, 0));
     return SPB_OK;
 }
 
@@ -1321,6 +1332,8 @@ int spb_render_begin(spb_ctx* ctx, const spb_render_desc* desc) {
         SPB_CUDA(ctx, cudaHostGetDevicePointer(&R->d_status, R->h_status, 0));
         for (cudaEvent_t& e : R->poll) SPB_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         SPB_CUDA(ctx, cudaEventCreate(&R->ev_r0)); SPB_CUDA(ctx, cudaEventCreate(&R->ev_r1));
+        SPB_CUDA(ctx, cudaStreamCreateWithFlags(&R->side, cudaStreamNonBlocking));
+        SPB_CUDA(ctx, cudaEventCreateWithFlags(&R->ev_fork, cudaEventDisableTiming)); SPB_CUDA(ctx, cudaEventCreateWithFlags(&R->ev_join, cudaEventDisableTiming));
     }
     R->h_status[0] = 0u; R->h_status[1] = 0u;
     SPB_CUDA(ctx, cudaMemsetAsync(R->d_ctl, 0, sizeof(LoopCtl), st));
@@ -1489,7 +1502,7 @@ static void* ncclLib() {
     setenv("NCCL_NVLS_ENABLE", "0", 0);
     setenv("NCCL_MAX_NCHANNELS", "8", 0);
     const char* names[] = {"libnccl.so.2", "libnccl.so"};
-    for (const char* nme : names) { lib = dlopen(nme, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+    for (const char* nme : names) { lib = dlopen(nme, RTLD_NOW | RTLD_LOCAL); if (lib) break; }
     return lib;
 }
 

@@ -15,6 +15,17 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (runs on the B200 box)")
 
 
+def has_cuda_device():
+    """True when a context can be created.  (Through the C ABI, not torch: importing torch AFTER this repo's CUDA libraries
+    were loaded into the process fails, and tests may run in any subset and order.)"""
+    from spica_b200 import capi
+    try:
+        capi.Context(0).close()
+        return True
+    except capi.SpbError:
+        return False
+
+
 def load_golden(name):
     return dict(np.load(os.path.join(GOLDEN, name)))
 

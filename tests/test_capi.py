@@ -33,8 +33,8 @@ def test_record_sizes_match_header():
 
 
 def test_no_device_means_no_context():
-    import torch
-    if torch.cuda.is_available():
+    from tests.conftest import has_cuda_device
+    if has_cuda_device():
         pytest.skip("a device is present")
     with pytest.raises(capi.SpbError) as ei:
         capi.Context(0)

@@ -67,10 +67,10 @@ def test_ply_shape_transform_and_defaults(tmp_path):
 
 
 def test_cli_fails_loudly_without_device_or_scene(tmp_path):
-    import torch
+    from tests.conftest import has_cuda_device
     r = subprocess.run([host.CLI_PATH, "-i", str(tmp_path / "missing.xml")], capture_output=True, text=True)
     assert r.returncode != 0 and "Failed to open" in r.stderr
-    if not torch.cuda.is_available():
+    if not has_cuda_device():
         r = host.run_cli(os.path.join(SCENES, "cornell_diffuse.xml"), str(tmp_path / "o"))
         assert r.returncode != 0 and "no CUDA device" in r.stderr             # no CPU fallback
 
@@ -141,8 +141,10 @@ def test_two_gpus_render_the_single_gpu_image(tmp_path):
     """`--gpus 2`: the replica's scene and BVH are cloned device to device (spb_ctx_clone_scene), the sample indices are
     interleaved, the films are summed with one NCCL reduce to GPU 0 -- and the image is the one-GPU image up to float
     summation order.  (Skipped on a one-GPU box.)"""
-    import torch
-    if torch.cuda.device_count() < 2:
+    from spica_b200 import capi
+    try:
+        capi.Context(1).close()          # (not torch.cuda.device_count(): importing torch after the CUDA libraries of this repo fails)
+    except capi.SpbError:
         pytest.skip("needs two GPUs")
     xml = os.path.join(SCENES, "cornell_glossy.xml")
     one = host.render_scene(xml, str(tmp_path / "g1"), gpus=1, seed=13)

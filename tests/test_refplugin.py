@@ -111,8 +111,8 @@ def test_reference_host_envmap_scene_resolves(tmp_path):
 
 
 def test_reference_host_has_no_cpu_fallback(tmp_path):
-    import torch
-    if torch.cuda.is_available():
+    from tests.conftest import has_cuda_device
+    if has_cuda_device():
         pytest.skip("a device is present")
     r = refhost.run(os.path.join(SCENES, "cornell_diffuse.xml"), str(tmp_path / "o"), str(tmp_path / "run"), REF)
     assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)
@@ -144,8 +144,10 @@ def test_reference_host_renders_on_the_gpu(tmp_path, variant):
 def test_reference_host_on_two_gpus(tmp_path):
     """SPICA_GPUS=2 under the unmodified reference host: the replica is cloned from the accelerator's context, the communicator
     comes up on its own threads, the films meet on GPU 0 -- and the file is the one-GPU file.  (Skipped on a one-GPU box.)"""
-    import torch
-    if torch.cuda.device_count() < 2:
+    from spica_b200 import capi
+    try:
+        capi.Context(1).close()          # (not torch.cuda.device_count(): importing torch after the CUDA libraries of this repo fails)
+    except capi.SpbError:
         pytest.skip("needs two GPUs")
     xml = os.path.join(SCENES, "cornell_zoo.xml")
     imgs = []
