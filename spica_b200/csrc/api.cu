@@ -33,7 +33,8 @@ bool cudaOk(spb_ctx* ctx, cudaError_t e, const char* what) {
 static void freeBvhDevice(spb_ctx* ctx) {
     if (ctx->d_nodes) cudaFree(ctx->d_nodes);
     if (ctx->d_tris) cudaFree(ctx->d_tris);
-    ctx->d_nodes = ctx->d_tris = nullptr;
+    if (ctx->d_pre_tris) cudaFree(ctx->d_pre_tris);
+    ctx->d_nodes = ctx->d_tris = ctx->d_pre_tris = nullptr;
     ctx->bvh_ready = false;
     // nothing may keep pointing at the freed tree: the kernels' parameter block goes back to "no geometry" and a
     // render that was begun on the old tree needs a new spb_render_begin
@@ -42,8 +43,19 @@ static void freeBvhDevice(spb_ctx* ctx) {
     renderSceneChanged(ctx);
 }
 
+// TriF64 records -> the float32 records the pre-test reads (vertices rounded to nearest, same id and tie rank)
+__global__ void roundTrisKernel(const TriF64* __restrict__ in, TriF32* __restrict__ out, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const TriF64 t = in[i];
+    TriF32 o;
+    for (int k = 0; k < 3; k++) { o.v0[k] = (float)t.v[k]; o.v1[k] = (float)t.v[3 + k]; o.v2[k] = (float)t.v[6 + k]; }
+    o.id = t.id; o.rank = t.rank; o.pad = 0;
+    out[i] = o;
+}
+
 // fills the kernels' parameter block from ctx->bvh's statistics and the device arrays
-static void setSceneParams(spb_ctx* ctx) {
+static int setSceneParams(spb_ctx* ctx) {
     const HostBVH& b = ctx->bvh;
     SceneParams& sp = ctx->sp;
     std::memset(&sp, 0, sizeof(sp));
@@ -62,7 +74,19 @@ static void setSceneParams(spb_ctx* ctx) {
     sp.max_coord = (float)(m * 1.0000002);
     sp.nodes = (const WideNode*)ctx->d_nodes;
     sp.tris = ctx->d_tris;
+    sp.pre_tris = (const TriF32*)ctx->d_tris;
+    sp.pre_round = 0.f;
+    if (!sp.empty && b.tri_format == 1) {
+        if (ctx->d_pre_tris) { cudaFree(ctx->d_pre_tris); ctx->d_pre_tris = nullptr; }
+        SPB_CUDA(ctx, cudaMalloc(&ctx->d_pre_tris, (size_t)b.n_tris * sizeof(TriF32)));
+        roundTrisKernel<<<(unsigned)((b.n_tris + 255) / 256), 256, 0, ctx->stream>>>((const TriF64*)ctx->d_tris, (TriF32*)ctx->d_pre_tris, (int64_t)b.n_tris);
+        SPB_CUDA(ctx, cudaGetLastError());
+        SPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        sp.pre_tris = (const TriF32*)ctx->d_pre_tris;
+        sp.pre_round = sp.max_coord * 1.1920929e-07f;     // 2^-23 max_coord
+    }
     ctx->bvh_ready = true;
+    return SPB_OK;
 }
 
 // host-built tree -> device
@@ -76,8 +100,7 @@ static int uploadBvh(spb_ctx* ctx) {
         SPB_CUDA(ctx, cudaMemcpyAsync(ctx->d_tris, b.tris.data(), b.tris.size(), cudaMemcpyHostToDevice, ctx->stream));
         SPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
-    setSceneParams(ctx);
-    return SPB_OK;
+    return setSceneParams(ctx);
 }
 
 }  // namespace spb
@@ -203,8 +226,7 @@ int spb_bvh_build(spb_ctx* ctx, const spb_build_opts* opts) {
         if (rc) { freeBvhDevice(ctx); return rc; }
         ctx->build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         ctx->builder_used = SPB_BUILDER_DEVICE_SAH;
-        setSceneParams(ctx);
-        return SPB_OK;
+        return setSceneParams(ctx);
     }
     if (o.builder == SPB_BUILDER_LBVH) {
         const int rc = buildLbvhDevice(ctx, &ctx->bin);
@@ -279,8 +301,7 @@ int spb_bvh_import_wide(spb_ctx* ctx, const spb_bvh_stats* st, const void* nodes
     }
     ctx->build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     ctx->builder_used = -1;
-    setSceneParams(ctx);
-    return SPB_OK;
+    return setSceneParams(ctx);
 }
 
 int spb_ctx_clone_scene(spb_ctx* dst, spb_ctx* src) {
@@ -307,7 +328,7 @@ int spb_ctx_clone_scene(spb_ctx* dst, spb_ctx* src) {
     }
     dst->build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     dst->builder_used = -1;
-    setSceneParams(dst);
+    { const int rc = setSceneParams(dst); if (rc) return rc; }
     renderSceneClone(dst, src);
     return SPB_OK;
 }

@@ -49,6 +49,11 @@ struct SceneParams {                    // small POD passed to kernels by value
     int32_t empty;                      // 1: no geometry
     int32_t max_depth;                  // depth of the wide tree = the most stack entries a ray can hold
     uint32_t f32_one;                   // 0x3f800000, as a parameter-block operand of the node test's PRMT (trace_core.h, byteMant)
+    // What the float32 pre-test reads (trace_core.h, triPretestMayHit): for TriF32 scenes the records themselves and
+    // pre_round = 0; for TriF64 scenes a TriF32 copy whose vertices are the doubles rounded to nearest float32, and
+    // pre_round = 2^-23 * max_coord >= twice the largest rounding step, which the pre-test adds to its error bounds.
+    const TriF32* pre_tris;
+    float    pre_round;
 };
 
 }  // namespace spb

@@ -42,6 +42,7 @@ struct spb_ctx {
 
     void* d_nodes = nullptr;
     void* d_tris = nullptr;
+    void* d_pre_tris = nullptr;          // TriF64 scenes: float32-rounded copy for the pre-test (SceneParams::pre_tris)
     spb::SceneParams sp{};
 
     // grow-only scratch for the host-buffer entry points (kPipe-deep ring)

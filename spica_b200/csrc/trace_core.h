@@ -191,7 +191,15 @@ SPB_HD bool triTestExact(const RayState& r, const double p0[3], const double p1[
 // written so that NaN / Inf fall through to the exact test.
 struct CullRay { float cox, coy, coz, fdx, fdy, fdz, ctmax; };   // what the pre-test reads of a ray (7 floats: cheap to hand to another lane)
 
-SPB_HD bool triPretestMayHit(const CullRay& r, float maxCoord, const U4& a, const U4& b, const U4& c) {
+//
+// Rounded triangles (TriF64 scenes): a, b, c are the double vertices rounded to float32, each coordinate off by at
+// most u M.  With rnd = 2^-23 M (twice that, which also swallows the second-order terms), exact arithmetic on the
+// rounded triangle differs from exact arithmetic on the true one by at most (|d_k| <= 1, first-order perturbation
+// of each triple product: edges move by <= rnd, tv by <= rnd / 2)
+//   |d det| <= 6 rnd (E1 + E2)            |d U| <= rnd (3 E2 + 6 TV)
+//   |d V|   <= rnd (3 E1 + 6 TV)          |d T| <= rnd (6 TV E1 + 3 E1 E2 + 6 E2 TV)
+// and the pre-test adds twice these to the bounds above.  rnd = 0 (a literal at the TriF32 call sites) folds them away.
+SPB_HD bool triPretestMayHit(const CullRay& r, float maxCoord, const U4& a, const U4& b, const U4& c, const float rnd = 0.f) {
     const float p0x = asFloat(a.x), p0y = asFloat(a.y), p0z = asFloat(a.z);
     const float e1x = asFloat(b.x) - p0x, e1y = asFloat(b.y) - p0y, e1z = asFloat(b.z) - p0z;
     const float e2x = asFloat(c.x) - p0x, e2y = asFloat(c.y) - p0y, e2z = asFloat(c.z) - p0z;
@@ -207,7 +215,14 @@ SPB_HD bool triPretestMayHit(const CullRay& r, float maxCoord, const U4& a, cons
     const float TV = fmaxf(fmaxf(fabsf(tx), fabsf(ty)), fabsf(tz));
     const float k = 7.62939453125e-06f;              // 2^-17
     const float mt = k * (maxCoord + TV);
-    const float eDet = k * E1 * E2, eU = mt * E2, eV = mt * E1, eT = mt * E1 * E2;
+    float eDet = k * E1 * E2, eU = mt * E2, eV = mt * E1, eT = mt * E1 * E2;
+    if (rnd != 0.f) {
+        const float rt = 12.f * rnd * TV;
+        eDet += 12.f * rnd * (E1 + E2);
+        eU += 6.f * rnd * E2 + rt;
+        eV += 6.f * rnd * E1 + rt;
+        eT += rt * (E1 + E2) + 6.f * rnd * E1 * E2;
+    }
     const float D = fabsf(det);
     if (!(D > eDet)) return true;                    // sign of det uncertain (or NaN): exact test decides
     const float sgn = det < 0.f ? -1.f : 1.f;
@@ -271,9 +286,9 @@ SPB_HD int triPretestClassify(const CullRay& r, float maxCoord, const U4& a, con
     return 2;
 }
 
-SPB_HD bool triPretestMayHit(const RayState& r, float maxCoord, const U4& a, const U4& b, const U4& c) {
+SPB_HD bool triPretestMayHit(const RayState& r, float maxCoord, const U4& a, const U4& b, const U4& c, const float rnd = 0.f) {
     const CullRay cr = {r.cox, r.coy, r.coz, r.fdx, r.fdy, r.fdz, r.ctmax};
-    return triPretestMayHit(cr, maxCoord, a, b, c);
+    return triPretestMayHit(cr, maxCoord, a, b, c, rnd);
 }
 
 // PRETEST = false: the candidate already passed the pre-test (cooperative kernel), go straight to the exact test
@@ -290,6 +305,11 @@ SPB_HD bool triTestRecord(const SceneParams& sp, const RayState& r, uint32_t ind
         p2[0] = (double)asFloat(c.x); p2[1] = (double)asFloat(c.y); p2[2] = (double)asFloat(c.z);
         *id = (int32_t)a.w; *rank = (int32_t)b.w;
     } else {
+        if (PRETEST) {
+            const TriF32* pp = sp.pre_tris + index;
+            const U4 pa = ldg4(&pp->v0[0]), pb = ldg4(&pp->v1[0]), pc = ldg4(&pp->v2[0]);
+            if (!triPretestMayHit(r, sp.max_coord, pa, pb, pc, sp.pre_round)) return false;
+        }
         const TriF64* tp = (const TriF64*)sp.tris + index;
         const U4 a = ldg4(&tp->v[0]), b = ldg4(&tp->v[2]), c = ldg4(&tp->v[4]), d = ldg4(&tp->v[6]),
                  e = ldg4(&tp->v[8]);

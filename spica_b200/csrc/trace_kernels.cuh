@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(128, 7) traceCoopKernel(SceneParams sp, const 
         U2 tg; tg.x = 0u; tg.y = 0u;
         if (active) tg = tr.nodePhase(sp, r, COUNT ? &c : nullptr);
         if (__any_sync(full, tg.y != 0u)) {
-            if (FMT == 0) {
+            {
                 const int cnt = __popc(tg.y);
                 if (COUNT) c.tris += (unsigned long long)cnt;
                 int incl = cnt;
@@ -236,16 +236,14 @@ __global__ void __launch_bounds__(128, 7) traceCoopKernel(SceneParams sp, const 
                         uint32_t m = maskL;
                         for (; k > 0; k--) m &= m - 1u;
                         const int bit = __ffs((int)m) - 1;
-                        const TriF32* tp = (const TriF32*)sp.tris + (baseL + (uint32_t)bit);
+                        const TriF32* tp = sp.pre_tris + (baseL + (uint32_t)bit);
                         const U4 a = ldg4(&tp->v0[0]), b = ldg4(&tp->v1[0]), cc = ldg4(&tp->v2[0]);
-                        if (triPretestMayHit(cr, sp.max_coord, a, b, cc)) atomicOr(&filt[L], 1u << bit);
+                        if (triPretestMayHit(cr, sp.max_coord, a, b, cc, FMT ? sp.pre_round : 0.f)) atomicOr(&filt[L], 1u << bit);
                     }
                 }
                 __syncwarp();
                 tg.y = filt[lane];
                 if (tg.y) tr.template triPhase<false>(sp, r, tg, COUNT ? &c : nullptr);
-            } else {
-                if (tg.y) tr.template triPhase<true>(sp, r, tg, COUNT ? &c : nullptr);
             }
         }
         if (active) {
@@ -288,11 +286,12 @@ struct SharedStack {
     __device__ __forceinline__ void set(int i, U2 v) const { s[i * 128] = make_uint2(v.x, v.y); }
 };
 
-template <int ANY_, bool COUNT, class RayT, class Out, int REFILL_MIN, int PF, bool DEFER, int MINB, int SS>
+template <int FMT, int ANY_, bool COUNT, class RayT, class Out, int REFILL_MIN, int PF, bool DEFER_, int MINB, int SS>
 __global__ void __launch_bounds__(128, MINB) traceCoopAheadKernel(SceneParams sp, const RayT* __restrict__ rays, int64_t n,
                                                                const uint32_t* __restrict__ n_dev, Out out,
                                                                unsigned long long* ctr) {
     constexpr bool ANY = ANY_ != 0;
+    constexpr bool DEFER = DEFER_ && FMT == 0;   // the postponed exact test reads float32-exact records
     constexpr uint32_t NONE = 0xffffffffu;
     __shared__ uint32_t s_filt[4][32];
     __shared__ uint32_t s_cert[DEFER ? 4 : 1][32], s_cmin[DEFER ? 4 : 1][32];
@@ -310,7 +309,7 @@ __global__ void __launch_bounds__(128, MINB) traceCoopAheadKernel(SceneParams sp
     const uint4* myNode = s_node + (PF == 2 ? threadIdx.x : 0);
     const uint32_t smemSlot = (uint32_t)__cvta_generic_to_shared(myNode);
     if (n_dev) n = (int64_t)__ldg(n_dev);
-    Traverser<0, ANY> tr;
+    Traverser<FMT, ANY> tr;
     tr.pend = NONE; tr.pend_lo = 0.f;
     RayState r;
     r.cox = r.coy = r.coz = r.fdx = r.fdy = r.fdz = r.ctmax = 0.f;
@@ -403,13 +402,13 @@ __global__ void __launch_bounds__(128, MINB) traceCoopAheadKernel(SceneParams sp
                     uint32_t m = maskL;
                     for (; k > 0; k--) m &= m - 1u;
                     bit = __ffs((int)m) - 1;
-                    const TriF32* tp = (const TriF32*)sp.tris + (baseL + (uint32_t)bit);
+                    const TriF32* tp = sp.pre_tris + (baseL + (uint32_t)bit);
                     const U4 a = ldg4(&tp->v0[0]), b = ldg4(&tp->v1[0]), cc = ldg4(&tp->v2[0]);
                     if (DEFER) {
                         cls = triPretestClassify(cr, sp.max_coord, a, b, cc, &tlo, &thi);
                         if (cls == 1) atomicOr(&filt[L], 1u << bit);
                         if (cls == 2) atomicMin(&cmin[L], __float_as_uint(thi));
-                    } else if (triPretestMayHit(cr, sp.max_coord, a, b, cc)) {
+                    } else if (triPretestMayHit(cr, sp.max_coord, a, b, cc, FMT ? sp.pre_round : 0.f)) {
                         atomicOr(&filt[L], 1u << bit);
                     }
                 }
@@ -453,7 +452,7 @@ __global__ void __launch_bounds__(128, MINB) traceCoopAheadKernel(SceneParams sp
 // K = 3 2306, K = 4 2310 Mrays/s on C2; K = 3 is also the best of the three on the Cornell renders.
 // What the pooled pre-test needs of a lane (its candidate groups and its culling ray) is parked
 // in shared memory, where any lane can read it; the owner keeps neither in registers.
-template <int ANY_, bool COUNT, class RayT, class Out, int REFILL_MIN, int MINB, int SS, int K>
+template <int FMT, int ANY_, bool COUNT, class RayT, class Out, int REFILL_MIN, int MINB, int SS, int K>
 __global__ void __launch_bounds__(128, MINB) traceCoopPairKernel(SceneParams sp, const RayT* __restrict__ rays, int64_t n,
                                                                const uint32_t* __restrict__ n_dev, Out out,
                                                                unsigned long long* ctr) {
@@ -471,7 +470,7 @@ __global__ void __launch_bounds__(128, MINB) traceCoopPairKernel(SceneParams sp,
     float4* cullA = s_cull[0][wid];
     float4* cullB = s_cull[1][wid];
     if (n_dev) n = (int64_t)__ldg(n_dev);
-    Traverser<0, ANY> tr;
+    Traverser<FMT, ANY> tr;
     RayState r;
     r.ctmax = 0.f;
     TraceCounters c = {0ull, 0ull, 0ull};
@@ -555,9 +554,9 @@ __global__ void __launch_bounds__(128, MINB) traceCoopPairKernel(SceneParams sp,
                     const int bit = __ffs((int)m) - 1;
                     const float4 c0 = cullA[L], c1 = cullB[L];
                     const CullRay cr = {c0.x, c0.y, c0.z, c1.x, c1.y, c1.z, c0.w};
-                    const TriF32* tp = (const TriF32*)sp.tris + (g.x + (uint32_t)bit);
+                    const TriF32* tp = sp.pre_tris + (g.x + (uint32_t)bit);
                     const U4 ta = ldg4(&tp->v0[0]), tb = ldg4(&tp->v1[0]), tc = ldg4(&tp->v2[0]);
-                    if (triPretestMayHit(cr, sp.max_coord, ta, tb, tc)) atomicOr(&filt[which * 128 + L], 1u << bit);
+                    if (triPretestMayHit(cr, sp.max_coord, ta, tb, tc, FMT ? sp.pre_round : 0.f)) atomicOr(&filt[which * 128 + L], 1u << bit);
                 }
             }
             __syncwarp();
@@ -607,35 +606,35 @@ static int launchTraceTyped(spb_ctx* ctx, const RayT* d_rays, int64_t n, const u
         int coop = ctx->opt_variant >= 2 ? 1 : 0;
         void (*kern)(SceneParams, const RayT*, int64_t, const uint32_t*, Out, unsigned long long*) =
             coop ? traceCoopKernel<FMT, ANY, COUNT, RayT, Out, 8> : tracePersistentKernel<FMT, ANY, COUNT, RayT, Out, 8, 2>;
-        if constexpr (FMT == 0) {     // the early-select kernels exist for float32-exact triangles only
+        {
             const int v = ctx->opt_variant;
-            if (v == 3) { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 8, 0, false, 7, 0>; coop = 2; }
+            if (v == 3) { kern = traceCoopAheadKernel<FMT, ANY, COUNT, RayT, Out, 8, 0, false, 7, 0>; coop = 2; }
             // 4: the stack in shared memory, when the tree is shallow enough for its 16 entries
             if (v == 4) {
-                if (ctx->sp.max_depth <= 14) { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 8, 0, false, 7, 16>; coop = 11; }
-                else { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 8, 0, false, 7, 0>; coop = 2; }
+                if (ctx->sp.max_depth <= 14) { kern = traceCoopAheadKernel<FMT, ANY, COUNT, RayT, Out, 8, 0, false, 7, 16>; coop = 11; }
+                else { kern = traceCoopAheadKernel<FMT, ANY, COUNT, RayT, Out, 8, 0, false, 7, 0>; coop = 2; }
             }
             // 5: three node visits per pooled triangle phase, 6 CTAs per SM (80 registers); same fallbacks as 4
             if (v == 5) {
-                if (ctx->sp.max_depth <= 14) { kern = traceCoopPairKernel<ANY, COUNT, RayT, Out, 8, 6, 16, 3>; coop = 15; }
-                else { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 8, 0, false, 7, 0>; coop = 2; }
+                if (ctx->sp.max_depth <= 14) { kern = traceCoopPairKernel<FMT, ANY, COUNT, RayT, Out, 8, 6, 16, 3>; coop = 15; }
+                else { kern = traceCoopAheadKernel<FMT, ANY, COUNT, RayT, Out, 8, 0, false, 7, 0>; coop = 2; }
             }
 #ifdef SPB_EXPERIMENTAL_VARIANTS      // measurement variants (trace.cu only; profiles/r01g_kernel_experiments.md)
-            if (v == 10) { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 8, 1, false, 7, 0>; coop = 3; }
-            if (v == 11) { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 8, 2, false, 7, 0>; coop = 4; }
-            if (v == 12) { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 8, 0, true, 7, 0>; coop = 5; }
-            if (v == 13) { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 8, 0, false, 8, 0>; coop = 6; }
-            if (v == 14) { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 8, 0, false, 6, 0>; coop = 7; }
-            if (v == 15 && ctx->sp.max_depth <= 14) { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 4, 0, false, 7, 16>; coop = 8; }
-            if (v == 16 && ctx->sp.max_depth <= 14) { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 6, 0, false, 7, 16>; coop = 9; }
-            if (v == 17 && ctx->sp.max_depth <= 14) { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 12, 0, false, 7, 16>; coop = 10; }
-            if (v == 25 && ctx->sp.max_depth <= 14) { kern = traceCoopPairKernel<ANY, COUNT, RayT, Out, 8, 5, 16, 3>; coop = 16; }
-            if (v == 21 && ctx->sp.max_depth <= 14) { kern = traceCoopPairKernel<ANY, COUNT, RayT, Out, 8, 7, 16, 3>; coop = 19; }
-            if (v == 22 && ctx->sp.max_depth <= 14) { kern = traceCoopPairKernel<ANY, COUNT, RayT, Out, 8, 6, 16, 2>; coop = 17; }
-            if (v == 23 && ctx->sp.max_depth <= 14) { kern = traceCoopPairKernel<ANY, COUNT, RayT, Out, 8, 6, 16, 4>; coop = 18; }
-            if (v == 18 && ctx->sp.max_depth <= 10) { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 8, 0, false, 7, 12>; coop = 12; }
-            if (v == 19 && ctx->sp.max_depth <= 14) { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 8, 0, false, 8, 16>; coop = 13; }
-            if (v == 20 && ctx->sp.max_depth <= 14) { kern = traceCoopAheadKernel<ANY, COUNT, RayT, Out, 8, 0, false, 6, 16>; coop = 14; }
+            if (v == 10) { kern = traceCoopAheadKernel<FMT, ANY, COUNT, RayT, Out, 8, 1, false, 7, 0>; coop = 3; }
+            if (v == 11) { kern = traceCoopAheadKernel<FMT, ANY, COUNT, RayT, Out, 8, 2, false, 7, 0>; coop = 4; }
+            if (v == 12) { kern = traceCoopAheadKernel<FMT, ANY, COUNT, RayT, Out, 8, 0, true, 7, 0>; coop = 5; }
+            if (v == 13) { kern = traceCoopAheadKernel<FMT, ANY, COUNT, RayT, Out, 8, 0, false, 8, 0>; coop = 6; }
+            if (v == 14) { kern = traceCoopAheadKernel<FMT, ANY, COUNT, RayT, Out, 8, 0, false, 6, 0>; coop = 7; }
+            if (v == 15 && ctx->sp.max_depth <= 14) { kern = traceCoopAheadKernel<FMT, ANY, COUNT, RayT, Out, 4, 0, false, 7, 16>; coop = 8; }
+            if (v == 16 && ctx->sp.max_depth <= 14) { kern = traceCoopAheadKernel<FMT, ANY, COUNT, RayT, Out, 6, 0, false, 7, 16>; coop = 9; }
+            if (v == 17 && ctx->sp.max_depth <= 14) { kern = traceCoopAheadKernel<FMT, ANY, COUNT, RayT, Out, 12, 0, false, 7, 16>; coop = 10; }
+            if (v == 25 && ctx->sp.max_depth <= 14) { kern = traceCoopPairKernel<FMT, ANY, COUNT, RayT, Out, 8, 5, 16, 3>; coop = 16; }
+            if (v == 21 && ctx->sp.max_depth <= 14) { kern = traceCoopPairKernel<FMT, ANY, COUNT, RayT, Out, 8, 7, 16, 3>; coop = 19; }
+            if (v == 22 && ctx->sp.max_depth <= 14) { kern = traceCoopPairKernel<FMT, ANY, COUNT, RayT, Out, 8, 6, 16, 2>; coop = 17; }
+            if (v == 23 && ctx->sp.max_depth <= 14) { kern = traceCoopPairKernel<FMT, ANY, COUNT, RayT, Out, 8, 6, 16, 4>; coop = 18; }
+            if (v == 18 && ctx->sp.max_depth <= 10) { kern = traceCoopAheadKernel<FMT, ANY, COUNT, RayT, Out, 8, 0, false, 7, 12>; coop = 12; }
+            if (v == 19 && ctx->sp.max_depth <= 14) { kern = traceCoopAheadKernel<FMT, ANY, COUNT, RayT, Out, 8, 0, false, 8, 16>; coop = 13; }
+            if (v == 20 && ctx->sp.max_depth <= 14) { kern = traceCoopAheadKernel<FMT, ANY, COUNT, RayT, Out, 8, 0, false, 6, 16>; coop = 14; }
 #endif
         }
         const int block = 128;

@@ -56,3 +56,27 @@ def gpu_ctx():
     ctx = capi.Context(0)
     yield ctx
     ctx.close()
+
+
+def transformed_torus_case(offset, n_incoherent=40000, n_aimed=20000):
+    """A torus under a double-precision toWorld transform (vertices are not float32 numbers; `offset` moves it away from the
+    origin so that the float32 rounding step is large against the triangles) + rays: incoherent ones and ones aimed at
+    mesh vertices and edge midpoints.  Returns (tris float64 [n, 9], rays float32 [m, 8], lo, hi)."""
+    import numpy as np
+    from spica_b200 import scenes
+    v, f = scenes.torus_mesh(160, 80)
+    c, s_ = np.cos(0.7), np.sin(0.7)
+    rot = np.array([[c, -s_, 0], [s_, c * np.cos(0.3), -np.sin(0.3)], [0, np.sin(0.3), np.cos(0.3)]])
+    vd = v.astype(np.float64) @ rot.T * 1.37 + np.array([offset, -0.5 * offset, 0.1])
+    tris = np.ascontiguousarray(vd[f].reshape(len(f), 9))
+    lo, hi = vd.min(0), vd.max(0)
+    rng = np.random.default_rng(12)
+    pick = rng.integers(0, len(f), n_aimed)
+    h = n_aimed // 2
+    tgt = np.concatenate([vd[f[pick[:h], 0]], 0.5 * (vd[f[pick[h:], 0]] + vd[f[pick[h:], 1]])])
+    aimed = np.zeros((n_aimed, 8), np.float32)
+    aimed[:, :3] = lo + (hi - lo) * rng.uniform(-0.2, 1.2, (n_aimed, 3))
+    aimed[:, 3:6] = tgt - aimed[:, :3].astype(np.float64)
+    aimed[:, 7] = 1e32
+    rays = np.concatenate([scenes.incoherent_rays(n_incoherent, lo, hi, seed=11), aimed])
+    return tris, rays, lo, hi

@@ -21,6 +21,7 @@ struct Emul {
     BinaryBVH bin;
     HostBVH bvh;
     SceneParams sp{};
+    std::vector<TriF32> pre;            // TriF64 trees: the rounded records of the pre-test (api.cu: roundTrisKernel)
     std::string err;
 };
 
@@ -48,6 +49,19 @@ Emul* emul_create(const double* verts, int64_t n, int max_leaf, int bins, const 
     sp.inflate = (float)e->bvh.inflate;
     for (int k = 0; k < 3; k++) { sp.wlo[k] = e->bvh.wlo[k] - 2 * e->bvh.inflate; sp.whi[k] = e->bvh.whi[k] + 2 * e->bvh.inflate; }
     { double m = 0.0; for (int k = 0; k < 3; k++) m = std::max(m, std::max(std::abs(sp.wlo[k]), std::abs(sp.whi[k]))); sp.max_coord = (float)(m * 1.0000002); }
+    sp.pre_tris = (const TriF32*)e->bvh.tris.data();
+    sp.pre_round = 0.f;
+    if (!sp.empty && e->bvh.tri_format == 1) {
+        const TriF64* t64 = (const TriF64*)e->bvh.tris.data();
+        e->pre.resize((size_t)n);
+        for (int64_t i = 0; i < n; i++) {
+            TriF32& o = e->pre[(size_t)i];
+            for (int k = 0; k < 3; k++) { o.v0[k] = (float)t64[i].v[k]; o.v1[k] = (float)t64[i].v[3 + k]; o.v2[k] = (float)t64[i].v[6 + k]; }
+            o.id = t64[i].id; o.rank = t64[i].rank; o.pad = 0;
+        }
+        sp.pre_tris = e->pre.data();
+        sp.pre_round = sp.max_coord * 1.1920929e-07f;
+    }
     return e;
 }
 const char* emul_error(Emul* e) { return e->err.c_str(); }

@@ -78,6 +78,30 @@ def test_golden_f64_vertices(gpu_ctx, golden_f64verts):
     _check_closest(gpu_ctx, g["tris"], g["rays"], g["prim"], g["t"])
 
 
+@pytest.mark.parametrize("variant", [2, 3, 4, 5])
+@pytest.mark.parametrize("offset", [0.0, 250.0])
+def test_transformed_mesh_double_vertices_on_the_pooled_kernels(gpu_ctx, variant, offset):
+    """A shape with a toWorld transform has vertices that are not float32 numbers (the hosts transform in double, as
+    core/triangle.cc does): 80-byte double records for the exact test, and a float32-rounded copy for the pooled
+    pre-test whose error bounds carry the rounding (trace_core.h: triPretestMayHit, rnd).  Rays aimed at mesh vertices
+    and edge midpoints sit inside that band; the far offset makes the rounding step large against the triangles."""
+    from tests.conftest import transformed_torus_case
+    tris, rays, lo, hi = transformed_torus_case(offset)
+    nodes = ob.bvh_build(tris)
+    p0, t0, _, _ = ob.trace_closest(nodes, tris, rays)
+    assert (p0 >= 0).sum() > 20000
+    gpu_ctx.set_option("trace_variant", variant)
+    gpu_ctx.set_triangles(tris)
+    gpu_ctx.build()
+    assert gpu_ctx.stats()["tri_format"] == 1
+    _check_closest(gpu_ctx, tris, rays, p0, t0, max_ties=64)        # aimed at shared vertices / edges: genuine ties
+    gpu_ctx.import_binary(nodes.view(capi.IMPORT_NODE))
+    _check_closest(gpu_ctx, tris, rays, p0, t0, max_ties=0)
+    anyr = scenes.incoherent_rays(30000, lo, hi, seed=13, anyhit=True)
+    assert np.array_equal(gpu_ctx.trace_any(anyr), ob.trace_any(nodes, tris, anyr))
+    gpu_ctx.set_option("trace_variant", DEFAULT_VARIANT)
+
+
 def test_medium_torus_vs_oracle_with_import(gpu_ctx):
     v, f = scenes.torus_mesh(200, 100)
     tris = scenes.mesh_triangles(v, f)

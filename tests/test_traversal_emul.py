@@ -306,3 +306,27 @@ def test_cost_optimal_collapse_against_greedy(monkeypatch):
     for ml in (1, 3):
         assert out[("1", ml)][1] < 0.85 * out[("0", ml)][1]          # wide nodes
         assert out[("1", ml)][2] < out[("0", ml)][2] * 1.01          # node visits per ray
+
+
+@pytest.mark.parametrize("offset", [0.0, 250.0])
+def test_transformed_mesh_rounded_pretest(offset):
+    """Double-precision vertices (a shape under a toWorld transform): the pre-test runs on float32-rounded copies with the
+    rounding in its error bounds (trace_core.h: triPretestMayHit, rnd) and must never reject what the exact test accepts --
+    including rays aimed at vertices and edge midpoints, which sit inside the rounding band -- while still rejecting
+    most candidates."""
+    from tests.conftest import transformed_torus_case
+    tris, rays, lo, hi = transformed_torus_case(offset)
+    nodes = ob.bvh_build(tris)
+    for e in (Emul(tris, max_leaf=4), Emul(tris, import_nodes=nodes)):
+        assert e.tri_format == 1
+        for mode in (0, 1, 3):
+            p0, t0, _, _ = ob.trace_closest(nodes, tris, rays)
+            p, t, _, _ = e.trace(rays, mode=mode)
+            assert np.array_equal(t, t0)
+            assert verify_ties(tris, rays, p, p0, t0) <= 64
+            # at the origin the rounded pre-test rejects what the float32-exact one rejects (0.49 exact tests per incoherent ray on
+            # either); 250 units away the rounding step is 1/1000 of a triangle edge and it lets more through, still correctly
+            assert e.exact_tests < (0.5 if offset == 0.0 else 0.8) * e.tri_tests, (e.exact_tests, e.tri_tests)
+        anyr = scenes.incoherent_rays(30000, lo, hi, seed=13, anyhit=True)
+        occ, _, _, _ = e.trace(anyr, any_hit=True)
+        assert np.array_equal((occ >= 0).astype(np.uint8), ob.trace_any(nodes, tris, anyr))

@@ -16,6 +16,11 @@ variants = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [2
 render = len(sys.argv) > 3 and sys.argv[3] == "render"
 v, f = scenes.torus_mesh(1000, 500)
 tris = scenes.mesh_triangles(v, f)
+if os.environ.get("SPB_TRANSFORM"):     # the mesh under a double-precision toWorld rotation: vertices are no longer float32 numbers
+    c, s_ = np.cos(0.7), np.sin(0.7)
+    rot = np.array([[c, -s_, 0], [s_, c * np.cos(0.3), -np.sin(0.3)], [0, np.sin(0.3), np.cos(0.3)]])
+    v = v.astype(np.float64) @ rot.T
+    tris = np.ascontiguousarray(v[f].reshape(len(f), 9))
 lo, hi = v.min(0), v.max(0)
 rays = scenes.incoherent_rays(n, lo, hi, seed=2)
 anyr = scenes.incoherent_rays(n, lo, hi, seed=2, anyhit=True)
@@ -23,6 +28,7 @@ pri = scenes.primary_rays(4096, 4096)[:n]
 ctx = capi.Context(0)
 ctx.set_triangles(tris)
 ctx.build(max_leaf_tris=int(os.environ.get("SPB_MAX_LEAF", "0")))
+print("tri_format", ctx.stats()["tri_format"], "lib", os.environ.get("SPICA_B200_LIB", "default"), flush=True)
 d_rays = ctx.dev_alloc(n * 32); d_any = ctx.dev_alloc(n * 32); d_pri = ctx.dev_alloc(len(pri) * 32)
 d_hits = ctx.dev_alloc(n * 16); d_occ = ctx.dev_alloc(n)
 ctx.dev_upload(d_rays, rays); ctx.dev_upload(d_pri, pri); ctx.dev_upload(d_any, anyr)
