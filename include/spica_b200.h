@@ -223,6 +223,13 @@ int spb_comm_init(spb_ctx* ctx, const char id[SPB_COMM_ID_BYTES], int32_t n_rank
 int spb_film_reduce(spb_ctx* ctx, int32_t root);
 int spb_film_reduce_async(spb_ctx* ctx, int32_t root);
 int spb_film_allreduce(spb_ctx* ctx);   /* = spb_film_reduce(ctx, -1)                                  */
+/* ONE process driving several GPUs needs no communicator: sums the films of `others` into `root`'s film with one kernel
+ * on the root's GPU that reads the other films through peer memory (NVLink / NVSwitch; a staging copy between GPUs that
+ * are not peers; plain loads for a context on the same GPU).  Waits for everything queued on all the contexts first;
+ * the other films are left as they were; every film must have the root's size.  spb_render_stats.reduce_ms of the root
+ * counts the kernel.  (Replaces, like spb_film_reduce, the tile merge into the one Film of SamplerIntegrator::render,
+ * core/integrator.cc:64-105, when the samples are spread over GPUs.) */
+int spb_film_reduce_peers(spb_ctx* root, spb_ctx* const* others, int32_t n_others);
 int spb_comm_destroy(spb_ctx* ctx);
 
 /* ---- acceleration structure ---------------------------------------------------------------- */

@@ -92,7 +92,7 @@ SYMBOLS = [
     "spb_ctx_stream",
     "spb_scene_set_triangle_attributes", "spb_scene_set_materials", "spb_scene_set_lights", "spb_scene_set_envmap",
     "spb_scene_set_textures", "spb_scene_set_material_textures",
-    "spb_render_begin", "spb_render_samples", "spb_render_samples_async", "spb_render_wait", "spb_film_reduce", "spb_film_reduce_async", "spb_film_read", "spb_film_resolve", "spb_film_resolve_rgbe", "spb_film_resolve_ldr",
+    "spb_render_begin", "spb_render_samples", "spb_render_samples_async", "spb_render_wait", "spb_film_reduce", "spb_film_reduce_async", "spb_film_reduce_peers", "spb_film_read", "spb_film_resolve", "spb_film_resolve_rgbe", "spb_film_resolve_ldr",
     "spb_film_add",
     "spb_render_get_stats", "spb_comm_get_unique_id", "spb_comm_init", "spb_film_allreduce", "spb_comm_destroy",
 ]
@@ -141,6 +141,7 @@ def load():
     L.spb_render_wait.argtypes = [vp]
     L.spb_film_reduce.argtypes = [vp, i32]
     L.spb_film_reduce_async.argtypes = [vp, i32]
+    L.spb_film_reduce_peers.argtypes = [vp, C.POINTER(vp), i32]
     L.spb_film_read.argtypes = [vp, vp]
     L.spb_film_resolve.argtypes = [vp, vp]
     L.spb_film_add.argtypes = [vp, vp]
@@ -420,6 +421,11 @@ class Context:
 
     def film_reduce(self, root=0):
         self._check(self.L.spb_film_reduce(self.h, root))
+
+    def film_reduce_peers(self, others):
+        """One process, several GPUs: sums the films of the `others` contexts into this one over peer memory (no communicator)."""
+        arr = (C.c_void_p * max(len(others), 1))(*[o.h for o in others])
+        self._check(self.L.spb_film_reduce_peers(self.h, arr, len(others)))
 
     def render_samples_async(self, first, count, stride=1):
         self._check(self.L.spb_render_samples_async(self.h, first, count, stride))

@@ -308,6 +308,18 @@ int spb_ctx_clone_scene(spb_ctx* dst, spb_ctx* src) {
     if (!dst || !src || dst == src) return fail(dst, SPB_ERR_INVALID, "spb_ctx_clone_scene: two different contexts are needed");
     if (!src->bvh_ready) return fail(dst, SPB_ERR_INVALID, "spb_ctx_clone_scene: the source context has no acceleration structure");
     const auto t0 = std::chrono::steady_clock::now();
+    // the two GPUs into each other's address space when they are peers (NVLink / NVSwitch): the copies below then go device
+    // to device instead of through the host, and spb_film_reduce_peers finds the mapping in place (enabling it costs
+    // milliseconds, which do not belong into a frame)
+    if (dst->device != src->device) {
+        const int pair[2][2] = {{src->device, dst->device}, {dst->device, src->device}};
+        for (const auto& pr : pair) {
+            int can = 0;
+            cudaSetDevice(pr[0]);
+            if (cudaDeviceCanAccessPeer(&can, pr[0], pr[1]) == cudaSuccess && can) cudaDeviceEnablePeerAccess(pr[1], 0);
+            cudaGetLastError();          // "already enabled" is fine
+        }
+    }
     cudaSetDevice(dst->device);
     dst->n_tris = src->n_tris;
     dst->geo = src->geo;                 // shared, not copied: 72 B per triangle stay where they are
@@ -321,7 +333,7 @@ int spb_ctx_clone_scene(spb_ctx* dst, spb_ctx* src) {
     if (st.n_tris > 0) {
         SPB_CUDA(dst, cudaMalloc(&dst->d_nodes, (size_t)st.node_bytes));
         SPB_CUDA(dst, cudaMalloc(&dst->d_tris, (size_t)st.tri_bytes));
-        // device to device: over NVLink when the GPUs are peers, through the host otherwise (the runtime picks)
+        // device to device: over NVLink when the GPUs are peers (mapped above), through the host otherwise (the runtime picks)
         SPB_CUDA(dst, cudaMemcpyPeerAsync(dst->d_nodes, dst->device, src->d_nodes, src->device, (size_t)st.node_bytes, dst->stream));
         SPB_CUDA(dst, cudaMemcpyPeerAsync(dst->d_tris, dst->device, src->d_tris, src->device, (size_t)st.tri_bytes, dst->stream));
         SPB_CUDA(dst, cudaStreamSynchronize(dst->stream));

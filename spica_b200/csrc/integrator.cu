@@ -1640,6 +1640,88 @@ int spb_film_reduce_async(spb_ctx* ctx, int32_t root) {
 }
 int spb_film_allreduce(spb_ctx* ctx) { return spb_film_reduce(ctx, -1); }
 
+// ---- K7b: the film sum of one process driving several GPUs, over peer memory -----------------------------------
+// One kernel on the root's GPU: every thread keeps one RGBW texel of every other film in flight (loads through NVLink /
+// NVSwitch peer mappings; plain loads when the other context sits on the same GPU) and adds them to its own.  33 MB x 7
+// peers at 1080p = 0.23 GB into one GPU's NVLink ingress; no communicator to bring up or tear down.
+struct PeerFilms { const float4* p[15]; int n; };
+__global__ void filmPeerSumKernel(float4* __restrict__ film, PeerFilms pf, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 v[15];
+#pragma unroll
+        for (int k = 0; k < 15; k++) if (k < pf.n) v[k] = __ldcs(pf.p[k] + i);
+        float4 a = film[i];
+#pragma unroll
+        for (int k = 0; k < 15; k++) if (k < pf.n) { a.x += v[k].x; a.y += v[k].y; a.z += v[k].z; a.w += v[k].w; }
+        film[i] = a;
+    }
+}
+
+int spb_film_reduce_peers(spb_ctx* root, spb_ctx* const* others, int32_t n_others) {
+    if (!root) return fail(nullptr, SPB_ERR_INVALID, "spb_film_reduce_peers: root is NULL");
+    RenderState* R = root->render;
+    if (!R || !R->d_film || R->film_pixels <= 0) return fail(root, SPB_ERR_INVALID, "spb_film_reduce_peers: no film (call spb_render_begin)");
+    if (n_others < 0 || (n_others > 0 && !others)) return fail(root, SPB_ERR_INVALID, "spb_film_reduce_peers: bad argument");
+    for (int k = 0; k < n_others; k++) {
+        spb_ctx* o = others[k];
+        if (!o || o == root) return fail(root, SPB_ERR_INVALID, "spb_film_reduce_peers: others[] holds NULL or the root itself");
+        if (!o->render || !o->render->d_film || o->render->film_pixels != R->film_pixels)
+            return fail(root, SPB_ERR_INVALID, "spb_film_reduce_peers: every context needs a film of the root's size");
+        for (int j = 0; j < k; j++) if (others[j] == o) return fail(root, SPB_ERR_INVALID, "spb_film_reduce_peers: a context is listed twice");
+    }
+    // everything queued on any of the contexts is finished first (the other films are only read here)
+    int rc = workerDrain(root, R);
+    if (rc) return rc;
+    for (int k = 0; k < n_others; k++) {
+        spb_ctx* o = others[k];
+        if ((rc = workerDrain(o, o->render))) return fail(root, rc, std::string("spb_film_reduce_peers: a queued call of context ") + std::to_string(k) + " failed: " + o->err);
+        cudaSetDevice(o->device);
+        SPB_CUDA(o, cudaStreamSynchronize(o->stream));
+    }
+    cudaSetDevice(root->device);
+    cudaStream_t st = root->stream;
+    SPB_CUDA(root, cudaEventRecord(R->ev_r0, st));
+    const int64_t n = R->film_pixels;
+    const unsigned grid = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)root->sm_count * 8);
+    PeerFilms pf; pf.n = 0;
+    auto flush = [&]() {
+        if (pf.n > 0) filmPeerSumKernel<<<grid, 256, 0, st>>>(R->d_film, pf, n);
+        pf.n = 0;
+    };
+    for (int k = 0; k < n_others; k++) {
+        spb_ctx* o = others[k];
+        bool direct = o->device == root->device;
+        if (!direct) {
+            int can = 0;
+            SPB_CUDA(root, cudaDeviceCanAccessPeer(&can, root->device, o->device));
+            if (can) {
+                const cudaError_t e = cudaDeviceEnablePeerAccess(o->device, 0);
+                if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+                else SPB_CUDA(root, e);
+                direct = true;
+            }
+        }
+        if (direct) {
+            pf.p[pf.n++] = o->render->d_film;
+            if (pf.n == 15) flush();
+        } else {
+            // not peers: the other film is staged in the root's scratch buffer and added from there
+            void* d = nullptr;
+            if ((rc = scratch(root, R, (size_t)n * sizeof(float4), &d))) return rc;
+            SPB_CUDA(root, cudaMemcpyPeerAsync(d, root->device, o->render->d_film, o->device, (size_t)n * sizeof(float4), st));
+            filmAddKernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(R->d_film, (const float4*)d, n);
+        }
+    }
+    flush();
+    SPB_CUDA(root, cudaGetLastError());
+    SPB_CUDA(root, cudaEventRecord(R->ev_r1, st));
+    SPB_CUDA(root, cudaStreamSynchronize(st));
+    float ms = 0.f;
+    SPB_CUDA(root, cudaEventElapsedTime(&ms, R->ev_r0, R->ev_r1));
+    R->reduce_ms += ms;
+    return SPB_OK;
+}
+
 int spb_comm_destroy(spb_ctx* ctx) {
     if (!ctx) return fail(nullptr, SPB_ERR_INVALID, "ctx is NULL");
     RenderState* R = ctx->render;

@@ -38,6 +38,13 @@ void check(spb_ctx* ctx, int rc, const char* what) {
 // Everything about the GPUs that does not depend on the scene -- CUDA start-up (1.6 s and more on a box without the
 // persistence daemon), one context per GPU, the NCCL communicator -- is started on background threads the moment the number
 // of GPUs is known (hostGpuPrewarm, called from main() before the scene file is even opened) and picked up when needed.
+// How the films of several GPUs are summed: over peer memory by default (spb_film_reduce_peers: one process owns all the
+// contexts, nothing to bring up); SPICA_FILM_REDUCE=nccl takes the communicator path a process-per-GPU job uses.
+static bool filmReduceNccl() {
+    const char* e = getenv("SPICA_FILM_REDUCE");
+    return e && std::strcmp(e, "nccl") == 0;
+}
+
 struct GpuPool {
     int first = 0, G = 0;
     bool started = false;
@@ -62,7 +69,7 @@ void gpuPoolStart(int firstDevice, int G) {
             check(nullptr, spb_ctx_create(p.first + g, &c), "spb_ctx_create");
             { std::lock_guard<std::mutex> lk(p.mu); p.ctx[g] = c; p.ctxDone[g] = 1; }
             p.cv.notify_all();
-            if (p.G > 1) {
+            if (p.G > 1 && filmReduceNccl()) {
                 if (g == 0) {
                     check(nullptr, spb_comm_get_unique_id(p.commId), "spb_comm_get_unique_id");
                     { std::lock_guard<std::mutex> lk(p.mu); p.commDone[0] = -1; }       // the id exists
@@ -93,7 +100,7 @@ spb_ctx* gpuPoolContext(int device, int g) {
 // true when the pool brought (or is bringing) the communicator up for this job; waits for rank g's part of it
 bool gpuPoolCommReady(int device, int G, int g) {
     GpuPool& p = gpuPool();
-    if (!p.started || device != p.first || G != p.G || G < 2) return false;
+    if (!p.started || device != p.first || G != p.G || G < 2 || !filmReduceNccl()) return false;
     std::unique_lock<std::mutex> lk(p.mu);
     p.cv.wait(lk, [&] { return p.commDone[g] == 1; });
     return true;
@@ -258,9 +265,10 @@ public:
         const int G = std::max(1, opt.gpus);
         std::vector<spb_ctx*> ctxs(G, nullptr);
         ctxs[0] = accel->ctx();
-        const bool pooledComm = G > 1 && gpuPool().started && gpuPool().first == accel->device() && gpuPool().G == G;
+        const bool nccl = G > 1 && filmReduceNccl();
+        const bool pooledComm = nccl && gpuPool().started && gpuPool().first == accel->device() && gpuPool().G == G;
         char commId[SPB_COMM_ID_BYTES];
-        if (G > 1 && !pooledComm) check(nullptr, spb_comm_get_unique_id(commId), "spb_comm_get_unique_id");
+        if (nccl && !pooledComm) check(nullptr, spb_comm_get_unique_id(commId), "spb_comm_get_unique_id");
 
         // replicas: scene + BVH on every GPU; the tree is built ONCE (by the accelerator) and copied device to device
         auto replicate = [&](int g) {
@@ -294,13 +302,13 @@ public:
         phaseClock().lap("integrator: lights resolved");
         forEachGpu(replicate);
         phaseClock().lap("replicas: ctx_create + clone");
-        // the NCCL communicator takes a second or two to come up: it does so on its own threads while the scene is uploaded
+        // (SPICA_FILM_REDUCE=nccl) the communicator takes a second or two to come up: it does so on its own threads while the scene is uploaded
         std::vector<std::thread> commThreads;
-        if (G > 1 && !pooledComm) for (int g = 0; g < G; g++) commThreads.emplace_back([&, g]() { check(ctxs[g], spb_comm_init(ctxs[g], commId, G, g), "spb_comm_init"); });
+        if (nccl && !pooledComm) for (int g = 0; g < G; g++) commThreads.emplace_back([&, g]() { check(ctxs[g], spb_comm_init(ctxs[g], commId, G, g), "spb_comm_init"); });
         forEachGpu(setup);
         for (auto& t : commThreads) t.join();
         if (pooledComm) for (int g = 0; g < G; g++) gpuPoolCommReady(accel->device(), G, g);
-        phaseClock().lap("scene upload, comm_init, begin");
+        phaseClock().lap(nccl ? "scene upload, comm_init, begin" : "scene upload, begin");
 
         std::vector<float> rgb((size_t)width * height * 3);
         auto publish = [&](int id) {
@@ -323,25 +331,32 @@ public:
                 publish(i + 1);
             }
         } else {
-            // GPU g renders sample indices g, g+G, ... ; then ONE all-reduce of the RGBW film
+            // GPU g renders sample indices g, g+G, ... ; then ONE sum of the RGBW films into GPU 0's: a kernel on GPU 0 reading
+            // the other films over NVLink peer memory (or, SPICA_FILM_REDUCE=nccl, an ncclReduce)
             std::vector<double> tRender(G, 0.0), tReduce(G, 0.0);
             forEachGpu([&](int g) {
                 const int count = (numSamples - g + G - 1) / G;
                 const auto a = std::chrono::steady_clock::now();
                 check(ctxs[g], spb_render_samples(ctxs[g], g, std::max(count, 0), G), "spb_render_samples");
                 const auto b = std::chrono::steady_clock::now();
-                if (G > 1) check(ctxs[g], spb_film_reduce(ctxs[g], 0), "spb_film_reduce");      // only GPU 0 publishes the frame: ncclReduce, half the traffic of an all-reduce
+                if (nccl) check(ctxs[g], spb_film_reduce(ctxs[g], 0), "spb_film_reduce");      // only GPU 0 publishes the frame: ncclReduce, half the traffic of an all-reduce
                 tRender[g] = std::chrono::duration<double>(b - a).count();
                 tReduce[g] = std::chrono::duration<double>(std::chrono::steady_clock::now() - b).count();   // includes waiting for the slowest GPU
             });
+            if (G > 1 && !nccl) {
+                const auto b = std::chrono::steady_clock::now();
+                check(ctxs[0], spb_film_reduce_peers(ctxs[0], ctxs.data() + 1, G - 1), "spb_film_reduce_peers");
+                const double r = std::chrono::duration<double>(std::chrono::steady_clock::now() - b).count();
+                for (int g = 0; g < G; g++) tReduce[g] = r;
+            }
             const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            double rmax = 0, rmin = 1e30, amin = 1e30;
             if (G > 1) {
-                double rmax = 0, rmin = 1e30, amin = 1e30;
                 for (int g = 0; g < G; g++) { rmax = std::max(rmax, tRender[g]); rmin = std::min(rmin, tRender[g]); amin = std::min(amin, tReduce[g]); }
-                MsgInfo("per-GPU render %.3f .. %.3f s, film all-reduce %.4f s", rmin, rmax, amin);
             }
             spb_render_stats st;
             check(ctxs[0], spb_render_get_stats(ctxs[0], &st), "spb_render_get_stats");
+            if (G > 1) MsgInfo("per-GPU render %.3f .. %.3f s, film sum (%s) %.4f s on the host's clock, %.3f ms on GPU 0", rmin, rmax, nccl ? "ncclReduce" : "peer memory", amin, st.reduce_ms);
             MsgInfo("rendered %d spp at %dx%d on %d GPU(s) in %.3f s: %.2f Msamples/s; GPU0: %.1f Mrays/s", numSamples, width, height, G, sec,
                     1e-6 * width * height * (double)numSamples / sec,
                     st.render_ms > 0 ? 1e-3 * (double)(st.rays_closest + st.rays_shadow + st.rays_mis) / st.render_ms : 0.0);
@@ -349,7 +364,7 @@ public:
             publish(numSamples);
             phaseClock().lap("publish (resolve, encode, save)");
         }
-        forEachGpu([&](int g) { if (G > 1) spb_comm_destroy(ctxs[g]); if (g > 0) spb_ctx_destroy(ctxs[g]); });
+        forEachGpu([&](int g) { if (nccl) spb_comm_destroy(ctxs[g]); if (g > 0) spb_ctx_destroy(ctxs[g]); });
         phaseClock().lap("replicas destroyed");
         printf("Finish!!\n");
     }

@@ -6,9 +6,11 @@
 // (core/film.cc:23-40,60-63), so the output file is written by the reference's film plugin.
 //
 // Environment (the reference CLI has no flags for these): SPICA_DEVICE (first GPU, default 0),
-// SPICA_GPUS (G contexts, samples interleaved, one NCCL all-reduce of the film), SPICA_SEED
+// SPICA_GPUS (G contexts, samples interleaved, the films summed over peer memory; SPICA_FILM_REDUCE=nccl: ncclReduce), SPICA_SEED
 // (default time(0), as core/integrator.cc:51), SPICA_SPP (overrides sampleCount),
 // SPICA_SAVE_PASSES=1 (save after every pass like core/integrator.cc:98).
+#include <cstring>
+
 #include "gpu_scene.h"
 
 // the same source builds plugins/path.so (default) and plugins/directlighting.so (-DSPB_REFPLUGIN_INTEGRATOR=1,
@@ -142,8 +144,10 @@ public:
         const int G = (int)std::max(1L, envInt("SPICA_GPUS", 1));
         std::vector<spb_ctx*> ctxs(G, nullptr);
         ctxs[0] = gs->ctx;
+        const char* how = getenv("SPICA_FILM_REDUCE");
+        const bool nccl = G > 1 && how && std::strcmp(how, "nccl") == 0;     // default: spb_film_reduce_peers, no communicator
         char commId[SPB_COMM_ID_BYTES];
-        if (G > 1) check(nullptr, spb_comm_get_unique_id(commId), "spb_comm_get_unique_id");
+        if (nccl) check(nullptr, spb_comm_get_unique_id(commId), "spb_comm_get_unique_id");
 
         // replicas: scene + BVH on every GPU; the tree is built ONCE (by the accelerator) and copied device to device
         auto replicate = [&](int g) {
@@ -171,9 +175,9 @@ public:
             for (auto& t : th) t.join();
         };
         forEachGpu(replicate);
-        // the NCCL communicator takes a second or two to come up: it does so on its own threads while the scene is uploaded
+        // (SPICA_FILM_REDUCE=nccl) the communicator takes a second or two to come up: it does so on its own threads while the scene is uploaded
         std::vector<std::thread> commThreads;
-        if (G > 1) for (int g = 0; g < G; g++) commThreads.emplace_back([&, g]() { check(ctxs[g], spb_comm_init(ctxs[g], commId, G, g), "spb_comm_init"); });
+        if (nccl) for (int g = 0; g < G; g++) commThreads.emplace_back([&, g]() { check(ctxs[g], spb_comm_init(ctxs[g], commId, G, g), "spb_comm_init"); });
         forEachGpu(setup);
         for (auto& t : commThreads) t.join();
 
@@ -197,12 +201,13 @@ public:
                 publish(i + 1);
             }
         } else {
-            // GPU g renders sample indices g, g+G, ... ; then ONE all-reduce of the RGBW film
+            // GPU g renders sample indices g, g+G, ... ; then ONE sum of the RGBW films into GPU 0's (it alone publishes the frame)
             forEachGpu([&](int g) {
                 const int count = (numSamples - g + G - 1) / G;
                 check(ctxs[g], spb_render_samples(ctxs[g], g, std::max(count, 0), G), "spb_render_samples");
-                if (G > 1) check(ctxs[g], spb_film_reduce(ctxs[g], 0), "spb_film_reduce");      // only GPU 0 publishes the frame: ncclReduce, half the traffic of an all-reduce
+                if (nccl) check(ctxs[g], spb_film_reduce(ctxs[g], 0), "spb_film_reduce");
             });
+            if (G > 1 && !nccl) check(ctxs[0], spb_film_reduce_peers(ctxs[0], ctxs.data() + 1, G - 1), "spb_film_reduce_peers");
             const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
             spb_render_stats st;
             check(ctxs[0], spb_render_get_stats(ctxs[0], &st), "spb_render_get_stats");
@@ -211,7 +216,7 @@ public:
                     st.render_ms > 0 ? 1e-3 * (double)(st.rays_closest + st.rays_shadow + st.rays_mis) / st.render_ms : 0.0);
             publish(numSamples);
         }
-        forEachGpu([&](int g) { if (G > 1) spb_comm_destroy(ctxs[g]); if (g > 0) spb_ctx_destroy(ctxs[g]); });
+        forEachGpu([&](int g) { if (nccl) spb_comm_destroy(ctxs[g]); if (g > 0) spb_ctx_destroy(ctxs[g]); });
         printf("Finish!!\n");
     }
 

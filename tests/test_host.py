@@ -137,11 +137,14 @@ def test_envmap_roughdielectric_ply_scene_matches_reference(tmp_path):
 
 
 @pytest.mark.gpu
-def test_two_gpus_render_the_single_gpu_image(tmp_path):
+@pytest.mark.parametrize("film_reduce", ["peers", "nccl"])
+def test_two_gpus_render_the_single_gpu_image(tmp_path, monkeypatch, film_reduce):
     """`--gpus 2`: the replica's scene and BVH are cloned device to device (spb_ctx_clone_scene), the sample indices are
-    interleaved, the films are summed with one NCCL reduce to GPU 0 -- and the image is the one-GPU image up to float
-    summation order.  (Skipped on a one-GPU box.)"""
+    interleaved, the films are summed into GPU 0's -- by a kernel reading the other film over peer memory (default) or by one
+    NCCL reduce (SPICA_FILM_REDUCE=nccl) -- and the image is the one-GPU image up to float summation order.
+    (Skipped on a one-GPU box.)"""
     from spica_b200 import capi
+    monkeypatch.setenv("SPICA_FILM_REDUCE", film_reduce)
     try:
         capi.Context(1).close()          # (not torch.cuda.device_count(): importing torch after the CUDA libraries of this repo fails)
     except capi.SpbError:

@@ -142,8 +142,9 @@ def test_reference_host_renders_on_the_gpu(tmp_path, variant):
 
 @pytest.mark.gpu
 def test_reference_host_on_two_gpus(tmp_path):
-    """SPICA_GPUS=2 under the unmodified reference host: the replica is cloned from the accelerator's context, the communicator
-    comes up on its own threads, the films meet on GPU 0 -- and the file is the one-GPU file.  (Skipped on a one-GPU box.)"""
+    """SPICA_GPUS=2 under the unmodified reference host: the replica is cloned from the accelerator's context, the films meet on
+    GPU 0 (over peer memory; with SPICA_FILM_REDUCE=nccl through a communicator that comes up on its own threads) -- and the
+    file is the one-GPU file.  (Skipped on a one-GPU box.)"""
     from spica_b200 import capi
     try:
         capi.Context(1).close()          # (not torch.cuda.device_count(): importing torch after the CUDA libraries of this repo fails)
@@ -151,12 +152,13 @@ def test_reference_host_on_two_gpus(tmp_path):
         pytest.skip("needs two GPUs")
     xml = os.path.join(SCENES, "cornell_zoo.xml")
     imgs = []
-    for g in (1, 2):
-        out = str(tmp_path / ("out%d" % g))
-        r = refhost.run(xml, out, str(tmp_path / ("run%d" % g)), REF, env={"SPICA_SEED": 5, "SPICA_GPUS": g})
+    for k, (g, how) in enumerate(((1, "peers"), (2, "peers"), (2, "nccl"))):
+        out = str(tmp_path / ("out%d" % k))
+        r = refhost.run(xml, out, str(tmp_path / ("run%d" % k)), REF, env={"SPICA_SEED": 5, "SPICA_GPUS": g, "SPICA_FILM_REDUCE": how})
         assert r.returncode == 0, r.stderr
         imgs.append(scenes.read_hdr(out + ".hdr"))
-    assert (np.abs(imgs[0] - imgs[1]) <= imgs[0].max(-1, keepdims=True) / 64 + 1e-6).all()      # RGBE quantisation of two float summation orders
+    for other in imgs[1:]:
+        assert (np.abs(imgs[0] - other) <= imgs[0].max(-1, keepdims=True) / 64 + 1e-6).all()      # RGBE quantisation of two float summation orders
 
 
 @pytest.mark.gpu

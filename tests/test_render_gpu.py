@@ -207,6 +207,45 @@ def test_async_render_graph_and_single_rank_reduce(gpu_ctx):
     gpu_ctx.L.spb_comm_destroy(gpu_ctx.h)
 
 
+def test_film_reduce_over_peer_memory(gpu_ctx):
+    """spb_film_reduce_peers: three contexts of one process render interleaved sample indices; one kernel on the root's GPU
+    sums the other films into the root's (peer loads over NVLink when the contexts sit on different GPUs, plain loads on the
+    same GPU -- a one-GPU box runs the latter).  The sum is the one-context film; the other films stay as they were."""
+    capi.cornell_render(gpu_ctx, 96, 80, 6, seed=8, variant="glossy")
+    ref = gpu_ctx.film_read()
+    devices = [0, 0]
+    try:
+        capi.Context(1).close()
+        devices = [1, 0]
+    except capi.SpbError:
+        pass
+    others = [capi.Context(d) for d in devices]
+    try:
+        capi.cornell_render(gpu_ctx, 96, 80, 0, seed=8, variant="glossy")
+        gpu_ctx.render_samples_async(0, 2, 3)
+        for k, o in enumerate(others):
+            capi.cornell_render(o, 96, 80, 0, seed=8, variant="glossy")
+            o.render_samples_async(k + 1, 2, 3)          # still queued when the reduce is called: it waits for them
+        gpu_ctx.film_reduce_peers(others)
+        assert np.allclose(gpu_ctx.film_read(), ref, rtol=1e-4, atol=1e-5)
+        assert gpu_ctx.render_stats()["reduce_ms"] > 0
+        for k, o in enumerate(others):
+            w = o.film_read()[..., 3].mean()                          # two of the six samples per pixel, untouched by the reduce
+            assert abs(w - ref[..., 3].mean() / 3) < 1e-3 * ref[..., 3].mean()
+        gpu_ctx.film_reduce_peers([])                                 # nothing to add
+        assert np.allclose(gpu_ctx.film_read(), ref, rtol=1e-4, atol=1e-5)
+        with pytest.raises(capi.SpbError):
+            gpu_ctx.film_reduce_peers([gpu_ctx])
+        with pytest.raises(capi.SpbError):
+            gpu_ctx.film_reduce_peers([others[0], others[0]])
+        capi.cornell_render(others[1], 64, 64, 1, seed=8)             # a film of another size
+        with pytest.raises(capi.SpbError):
+            gpu_ctx.film_reduce_peers(others)
+    finally:
+        for o in others:
+            o.close()
+
+
 def test_scene_change_invalidates_a_begun_render(gpu_ctx):
     """spb_scene_set_triangles after spb_render_begin used to leave the kernels' parameter block pointing at the
     freed tree.  Now every scene change requires a new spb_render_begin."""
