@@ -250,7 +250,8 @@ def render_frame(torch, dist, capi, partition, scenes, local, rank, world, name,
             traffic = json.load(open(tp)).get("render_dram_bytes_per_sample", {}).get(name)
         out = {"config": "BASELINE configs[%d]: %s, %dx%d, %d spp total, depth %d, spp partitioned over %d GPU(s), NCCL film reduce to rank 0 inside the frame"
                          % (cfg["index"], cfg["what"], W, H, spp_total, depth, world),
-               "triangles": bst["n_tris"], "bvh_build_s": bst["build_seconds"], "setup_s_rank0": setup_s,
+               "triangles": bst["n_tris"], "triangle_records": "float32 (48 B)" if bst["tri_format"] == 0 else "float64 (80 B) + rounded float32 (48 B)",
+               "bvh_build_s": bst["build_seconds"], "setup_s_rank0": setup_s,
                "scaling": "strong", "spp_total": spp_total, "spp_rank0": partition.sample_partition(spp_total, 0, world)[1],
                "seconds": sec, "msamples_s": W * H * spp_total / sec * 1e-6,
                "allreduce_ms": reduce_ms_max, "allreduce": "ncclReduce(sum, f32, root 0) of the %d MB RGBW film; device time incl. waiting for the slowest rank, max over ranks" % (W * H * 16 >> 20),
