@@ -188,7 +188,7 @@ RENDER_CONFIGS = {
 }
 
 
-def render_frame(torch, dist, capi, partition, scenes, local, rank, world, name, spp_total, comm_id, cpu_spp):
+def render_frame(torch, dist, capi, partition, scenes, local, rank, world, name, spp_total, comm_id, cpu_spp, film_reduce="ipc"):
     """One BASELINE render configuration, timed as one frame: every rank renders its share of the sample indices,
     then ONE NCCL reduce of the RGBW film to rank 0.  Wall clock between barriers, max over ranks."""
     cfg = RENDER_CONFIGS[name]
@@ -219,11 +219,32 @@ def render_frame(torch, dist, capi, partition, scenes, local, rank, world, name,
     if world > 1:
         rctx.film_reduce(0)
     rctx.render_begin(W, H, c2w, r2c, max_depth=depth, seed=7, **begin_kw)
+    # How the films meet on rank 0: by default rank 0 maps the other ranks' films through CUDA IPC (once, here) and sums them
+    # with one kernel over NVLink peer memory (spb_film_reduce_imported) behind a barrier of the job; --film-reduce nccl, or
+    # GPUs that cannot map each other, take one ncclReduce (spb_film_reduce) instead
+    how = "nccl"
+    if world > 1 and film_reduce == "ipc":
+        hs = [None] * world
+        dist.all_gather_object(hs, rctx.film_export_handle())
+        ok = 1
+        if rank == 0:
+            try:
+                rctx.film_import_handles(hs[1:])
+                rctx.film_reduce_imported()             # (films are all zero here: warms the kernel and the mappings)
+            except capi.SpbError:
+                ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+        dist.broadcast(flag, 0)
+        how = "ipc" if int(flag.item()) else "nccl"
     sync()
     with ClockSampler(local) as clk:
         t0 = time.perf_counter()
         rctx.render_samples(*partition.sample_partition(spp_total, rank, world))
-        if world > 1:
+        if world > 1 and how == "ipc":
+            dist.barrier()                              # every rank's samples are in its film
+            if rank == 0:
+                rctx.film_reduce_imported()
+        elif world > 1:
             rctx.film_reduce(0)
         sync()
         dt = time.perf_counter() - t0
@@ -254,7 +275,10 @@ def render_frame(torch, dist, capi, partition, scenes, local, rank, world, name,
                "bvh_build_s": bst["build_seconds"], "setup_s_rank0": setup_s,
                "scaling": "strong", "spp_total": spp_total, "spp_rank0": partition.sample_partition(spp_total, 0, world)[1],
                "seconds": sec, "msamples_s": W * H * spp_total / sec * 1e-6,
-               "allreduce_ms": reduce_ms_max, "allreduce": "ncclReduce(sum, f32, root 0) of the %d MB RGBW film; device time incl. waiting for the slowest rank, max over ranks" % (W * H * 16 >> 20),
+               "allreduce_ms": reduce_ms_max,
+               "allreduce": ("ncclReduce(sum, f32, root 0) of the %d MB RGBW film; device time incl. waiting for the slowest rank, max over ranks" if how == "nccl" else
+                             "one kernel on rank 0 that reads the other ranks' %d MB RGBW films through CUDA-IPC peer mappings (NVLink) and adds them to its own, "
+                             "behind a barrier of the job (inside the frame's time, not inside allreduce_ms)") % (W * H * 16 >> 20),
                "render_ms_slowest_rank": render_ms_max, "render_ms_fastest_rank": render_ms_min,
                "rank0": {"rays": rays, "rays_per_sample": rays / P, "mrays_s": rays / (st["render_ms"] * 1e-3) * 1e-6,
                          "iterations": st["iterations"], "kernel_launches": st["kernel_launches"]},
@@ -282,6 +306,10 @@ def render_frame(torch, dist, capi, partition, scenes, local, rank, world, name,
                     out["mean_radiance_cpu_%dspp" % cpu_spp] = float(ref.mean())
             except Exception as exc:      # noqa: BLE001
                 out["cpu_baseline"] = {"error": repr(exc)}
+    if world > 1:                   # the mappings go before the films they map do
+        if rank == 0 and how == "ipc":
+            rctx.film_import_handles([])
+        dist.barrier()
     rctx.close()
     return out
 
@@ -388,6 +416,7 @@ def main():
     ap.add_argument("--c5-spp", type=int, default=-1, help="total spp of the C5 frame (BASELINE configs[4]: 256 on 8 GPUs; -1 = 256 when N = 8, else skip)")
     ap.add_argument("--cpu-render-spp", type=int, default=2, help="spp of the reference renderer's run beside C3 / C4 at N = 1 (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--film-reduce", choices=["ipc", "nccl"], default="ipc", help="N > 1: how the films meet on rank 0 (ipc = a kernel over CUDA-IPC peer mappings, falls back to nccl)")
     ap.add_argument("--chunk", type=int, default=0, help="rays per pipelined chunk of the host-buffer call (0 = library default)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -526,7 +555,7 @@ def main():
                 dist.broadcast_object_list(ids, src=0)
                 comm_id = ids[0]
             renders["render_" + name] = render_frame(torch, dist, capi, partition, scenes, local, rank, world, name, spp_total,
-                                                     comm_id, 0 if args.no_cpu_baseline else args.cpu_render_spp)
+                                                     comm_id, 0 if args.no_cpu_baseline else args.cpu_render_spp, args.film_reduce)
 
     if rank != 0:
         if world > 1:

@@ -230,6 +230,18 @@ int spb_film_allreduce(spb_ctx* ctx);   /* = spb_film_reduce(ctx, -1)           
  * counts the kernel.  (Replaces, like spb_film_reduce, the tile merge into the one Film of SamplerIntegrator::render,
  * core/integrator.cc:64-105, when the samples are spread over GPUs.) */
 int spb_film_reduce_peers(spb_ctx* root, spb_ctx* const* others, int32_t n_others);
+/* The same sum ACROSS PROCESSES (one process per GPU on one node): every other rank exports a handle of its film (CUDA IPC)
+ * after spb_render_begin and ships the bytes to the root by its own means; the root maps them once per job
+ * (spb_film_import_handles; SPB_ERR_UNSUPPORTED when the GPUs are not peers or a handle comes from this very process:
+ * use spb_film_reduce then) and sums the mapped films into its own with the kernel of spb_film_reduce_peers
+ * (spb_film_reduce_imported).  ORDERING IS THE CALLER'S: between the other ranks' last spb_render_samples (synchronous, or
+ * waited for) and the root's spb_film_reduce_imported there must be a barrier of the job (MPI_Barrier,
+ * torch.distributed.barrier), and another one before the other ranks touch their films again.  A handle dies with its
+ * film: export again after a spb_render_begin that changes the film size. */
+#define SPB_FILM_HANDLE_BYTES 96
+int spb_film_export_handle(spb_ctx* ctx, char handle[SPB_FILM_HANDLE_BYTES]);
+int spb_film_import_handles(spb_ctx* root, const char* handles /* n x SPB_FILM_HANDLE_BYTES */, int32_t n);
+int spb_film_reduce_imported(spb_ctx* root);
 int spb_comm_destroy(spb_ctx* ctx);
 
 /* ---- acceleration structure ---------------------------------------------------------------- */

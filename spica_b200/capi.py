@@ -92,7 +92,7 @@ SYMBOLS = [
     "spb_ctx_stream",
     "spb_scene_set_triangle_attributes", "spb_scene_set_materials", "spb_scene_set_lights", "spb_scene_set_envmap",
     "spb_scene_set_textures", "spb_scene_set_material_textures",
-    "spb_render_begin", "spb_render_samples", "spb_render_samples_async", "spb_render_wait", "spb_film_reduce", "spb_film_reduce_async", "spb_film_reduce_peers", "spb_film_read", "spb_film_resolve", "spb_film_resolve_rgbe", "spb_film_resolve_ldr",
+    "spb_render_begin", "spb_render_samples", "spb_render_samples_async", "spb_render_wait", "spb_film_reduce", "spb_film_reduce_async", "spb_film_reduce_peers", "spb_film_export_handle", "spb_film_import_handles", "spb_film_reduce_imported", "spb_film_read", "spb_film_resolve", "spb_film_resolve_rgbe", "spb_film_resolve_ldr",
     "spb_film_add",
     "spb_render_get_stats", "spb_comm_get_unique_id", "spb_comm_init", "spb_film_allreduce", "spb_comm_destroy",
 ]
@@ -142,6 +142,9 @@ def load():
     L.spb_film_reduce.argtypes = [vp, i32]
     L.spb_film_reduce_async.argtypes = [vp, i32]
     L.spb_film_reduce_peers.argtypes = [vp, C.POINTER(vp), i32]
+    L.spb_film_export_handle.argtypes = [vp, C.c_char_p]
+    L.spb_film_import_handles.argtypes = [vp, C.c_char_p, i32]
+    L.spb_film_reduce_imported.argtypes = [vp]
     L.spb_film_read.argtypes = [vp, vp]
     L.spb_film_resolve.argtypes = [vp, vp]
     L.spb_film_add.argtypes = [vp, vp]
@@ -426,6 +429,18 @@ class Context:
         """One process, several GPUs: sums the films of the `others` contexts into this one over peer memory (no communicator)."""
         arr = (C.c_void_p * max(len(others), 1))(*[o.h for o in others])
         self._check(self.L.spb_film_reduce_peers(self.h, arr, len(others)))
+
+    def film_export_handle(self):
+        """96 bytes another process of this node can map this context's film with (CUDA IPC); see include/spica_b200.h."""
+        buf = C.create_string_buffer(96)
+        self._check(self.L.spb_film_export_handle(self.h, buf))
+        return buf.raw
+
+    def film_import_handles(self, handles):
+        self._check(self.L.spb_film_import_handles(self.h, b"".join(handles), len(handles)))
+
+    def film_reduce_imported(self):
+        self._check(self.L.spb_film_reduce_imported(self.h))
 
     def render_samples_async(self, first, count, stride=1):
         self._check(self.L.spb_render_samples_async(self.h, first, count, stride))

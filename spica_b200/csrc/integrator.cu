@@ -170,6 +170,7 @@ struct RenderState {
     RenderWorker* worker = nullptr;
     // nccl
     void* nccl_lib = nullptr; void* comm = nullptr;
+    std::vector<void*> ipc_films;            // other processes' films mapped by spb_film_import_handles (cudaIpcOpenMemHandle)
 };
 
 static void workerStop(RenderState* R);
@@ -730,6 +731,7 @@ void renderStateDestroy(spb_ctx* ctx) {
     if (R->ev_fork) cudaEventDestroy(R->ev_fork);
     if (R->ev_join) cudaEventDestroy(R->ev_join);
     if (R->side) cudaStreamDestroy(R->side);
+    for (void* p : R->ipc_films) cudaIpcCloseMemHandle(p);
     if (R->comm && R->nccl_lib) {
         typedef int (*destroy_t)(void*);
         destroy_t f = (destroy_t)dlsym(R->nccl_lib, "ncclCommDestroy");
@@ -1399,6 +1401,13 @@ int spb_render_wait(spb_ctx* ctx) {
     return workerDrain(ctx, ctx->render);
 }
 
+static int filmArgs(spb_ctx* ctx, const char* who) {
+    if (!ctx) return fail(nullptr, SPB_ERR_INVALID, std::string(who) + ": ctx is NULL");
+    RenderState* R = ctx->render;
+    if (!R || !R->d_film || R->film_pixels <= 0) return fail(ctx, SPB_ERR_INVALID, std::string(who) + ": no film (call spb_render_begin)");
+    return SPB_OK;
+}
+
 static int filmReady(spb_ctx* ctx, const char* who, RenderState** out) {
     RenderState* R = ctx->render;
     if (!R || !R->d_film || R->film_pixels <= 0) return fail(ctx, SPB_ERR_INVALID, std::string(who) + ": no film (call spb_render_begin)");
@@ -1713,6 +1722,83 @@ int spb_film_reduce_peers(spb_ctx* root, spb_ctx* const* others, int32_t n_other
         }
     }
     flush();
+    SPB_CUDA(root, cudaGetLastError());
+    SPB_CUDA(root, cudaEventRecord(R->ev_r1, st));
+    SPB_CUDA(root, cudaStreamSynchronize(st));
+    float ms = 0.f;
+    SPB_CUDA(root, cudaEventElapsedTime(&ms, R->ev_r0, R->ev_r1));
+    R->reduce_ms += ms;
+    return SPB_OK;
+}
+
+// ---- the same sum across PROCESSES (one per GPU, torchrun / MPI style): the other ranks' films mapped through CUDA IPC ----
+// handle = cudaIpcMemHandle_t (64 B) | film pixels (int64) | magic
+static const uint64_t kFilmHandleMagic = 0x53504246494c4d31ull;       // "SPBFILM1"
+int spb_film_export_handle(spb_ctx* ctx, char handle[SPB_FILM_HANDLE_BYTES]) {
+    int rc = filmArgs(ctx, "spb_film_export_handle");
+    if (rc) return rc;
+    if (!handle) return fail(ctx, SPB_ERR_INVALID, "spb_film_export_handle: handle is NULL");
+    static_assert(sizeof(cudaIpcMemHandle_t) + 16 <= SPB_FILM_HANDLE_BYTES, "film handle size");
+    RenderState* R = ctx->render;
+    cudaSetDevice(ctx->device);
+    cudaIpcMemHandle_t h;
+    SPB_CUDA(ctx, cudaIpcGetMemHandle(&h, R->d_film));
+    std::memset(handle, 0, SPB_FILM_HANDLE_BYTES);
+    std::memcpy(handle, &h, sizeof(h));
+    const int64_t px = R->film_pixels;
+    std::memcpy(handle + sizeof(h), &px, 8);
+    std::memcpy(handle + sizeof(h) + 8, &kFilmHandleMagic, 8);
+    return SPB_OK;
+}
+
+int spb_film_import_handles(spb_ctx* root, const char* handles, int32_t n) {
+    int rc = filmArgs(root, "spb_film_import_handles");
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && !handles)) return fail(root, SPB_ERR_INVALID, "spb_film_import_handles: bad argument");
+    RenderState* R = root->render;
+    if ((rc = workerDrain(root, R))) return rc;
+    cudaSetDevice(root->device);
+    for (void* p : R->ipc_films) cudaIpcCloseMemHandle(p);
+    R->ipc_films.clear();
+    for (int k = 0; k < n; k++) {
+        const char* hb = handles + (size_t)k * SPB_FILM_HANDLE_BYTES;
+        cudaIpcMemHandle_t h;
+        int64_t px = 0; uint64_t magic = 0;
+        std::memcpy(&h, hb, sizeof(h));
+        std::memcpy(&px, hb + sizeof(h), 8);
+        std::memcpy(&magic, hb + sizeof(h) + 8, 8);
+        if (magic != kFilmHandleMagic) return fail(root, SPB_ERR_INVALID, "spb_film_import_handles: not a handle of spb_film_export_handle");
+        if (px != R->film_pixels) return fail(root, SPB_ERR_INVALID, "spb_film_import_handles: every film needs the root's size");
+        void* p = nullptr;
+        const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            for (void* q : R->ipc_films) cudaIpcCloseMemHandle(q);
+            R->ipc_films.clear();
+            return fail(root, SPB_ERR_UNSUPPORTED, std::string("spb_film_import_handles: cudaIpcOpenMemHandle: ") + cudaGetErrorString(e) +
+                                                   " (a film of this process, or GPUs that are not peers: use spb_film_reduce)");
+        }
+        R->ipc_films.push_back(p);
+    }
+    return SPB_OK;
+}
+
+int spb_film_reduce_imported(spb_ctx* root) {
+    int rc = filmArgs(root, "spb_film_reduce_imported");
+    if (rc) return rc;
+    RenderState* R = root->render;
+    if ((rc = workerDrain(root, R))) return rc;
+    cudaSetDevice(root->device);
+    cudaStream_t st = root->stream;
+    SPB_CUDA(root, cudaEventRecord(R->ev_r0, st));
+    const int64_t n = R->film_pixels;
+    const unsigned grid = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)root->sm_count * 8);
+    PeerFilms pf; pf.n = 0;
+    for (void* p : R->ipc_films) {
+        pf.p[pf.n++] = (const float4*)p;
+        if (pf.n == 15) { filmPeerSumKernel<<<grid, 256, 0, st>>>(R->d_film, pf, n); pf.n = 0; }
+    }
+    if (pf.n > 0) filmPeerSumKernel<<<grid, 256, 0, st>>>(R->d_film, pf, n);
     SPB_CUDA(root, cudaGetLastError());
     SPB_CUDA(root, cudaEventRecord(R->ev_r1, st));
     SPB_CUDA(root, cudaStreamSynchronize(st));

@@ -246,6 +246,59 @@ def test_film_reduce_over_peer_memory(gpu_ctx):
             o.close()
 
 
+_IPC_CHILD = """
+import sys
+sys.path.insert(0, %r)
+from spica_b200 import capi
+try:
+    ctx = capi.Context(1)
+except capi.SpbError:
+    ctx = capi.Context(0)
+capi.cornell_render(ctx, 96, 80, 0, seed=8, variant="glossy")
+ctx.render_samples(1, 3, 2)                      # the odd sample indices
+print(ctx.film_export_handle().hex(), flush=True)
+sys.stdin.readline()                             # the parent has summed: now the film may go
+ctx.close()
+"""
+
+
+def test_film_reduce_across_processes_over_cuda_ipc(gpu_ctx):
+    """spb_film_export_handle / spb_film_import_handles / spb_film_reduce_imported: another PROCESS (on the second GPU when
+    there is one, else on the same GPU) renders the odd sample indices and ships 96 bytes; this process maps that film and adds
+    it to its own with the peer-sum kernel.  The pipe is the job's barrier."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    capi.cornell_render(gpu_ctx, 96, 80, 6, seed=8, variant="glossy")
+    ref = gpu_ctx.film_read()
+    child = subprocess.Popen([sys.executable, "-c", _IPC_CHILD % root], stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True)
+    try:
+        line = ""
+        while len(line.strip()) != 192:                               # (skips log lines)
+            line = child.stdout.readline()
+            assert line, "the child process died"
+        handle = bytes.fromhex(line.strip())
+        capi.cornell_render(gpu_ctx, 96, 80, 0, seed=8, variant="glossy")
+        gpu_ctx.render_samples(0, 3, 2)                               # the even sample indices
+        gpu_ctx.film_import_handles([handle])
+        gpu_ctx.film_reduce_imported()
+        assert np.allclose(gpu_ctx.film_read(), ref, rtol=1e-4, atol=1e-5)
+        assert gpu_ctx.render_stats()["reduce_ms"] > 0
+        with pytest.raises(capi.SpbError):
+            gpu_ctx.film_import_handles([b"\0" * 96])                 # not a handle
+        with pytest.raises(capi.SpbError):
+            gpu_ctx.film_import_handles([gpu_ctx.film_export_handle()])   # a film of this very process cannot be mapped
+        gpu_ctx.film_import_handles([])
+        gpu_ctx.film_reduce_imported()                                # nothing mapped: the film stays
+        assert np.allclose(gpu_ctx.film_read(), ref, rtol=1e-4, atol=1e-5)
+    finally:
+        try:
+            child.stdin.write("done\n"); child.stdin.flush()
+        except OSError:
+            pass
+        child.wait(timeout=60)
+
+
 def test_scene_change_invalidates_a_begun_render(gpu_ctx):
     """spb_scene_set_triangles after spb_render_begin used to leave the kernels' parameter block pointing at the
     freed tree.  Now every scene change requires a new spb_render_begin."""
