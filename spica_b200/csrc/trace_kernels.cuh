@@ -26,6 +26,7 @@
 //   10+ measurement variants, compiled with `make EXP=1` only (profiles/r01g_kernel_experiments.md).
 #pragma once
 #include <algorithm>
+#include <type_traits>
 
 #include "context.h"
 #include "trace_core.h"
@@ -282,6 +283,7 @@ __device__ __forceinline__ void fetchNodeAhead(const SceneParams& sp, uint32_t n
 // SS > 0: the traversal stack lives in shared memory (SS entries per thread, [entry][thread] layout)
 struct SharedStack {
     uint2* s;
+    uint2* unused;                      // (same initialiser list as DeepStack)
     __device__ __forceinline__ U2 get(int i) const { const uint2 v = s[i * 128]; return U2{v.x, v.y}; }
     __device__ __forceinline__ void set(int i, U2 v) const { s[i * 128] = make_uint2(v.x, v.y); }
 };
@@ -452,7 +454,17 @@ __global__ void __launch_bounds__(128, MINB) traceCoopAheadKernel(SceneParams sp
 // K = 3 2306, K = 4 2310 Mrays/s on C2; K = 3 is also the best of the three on the Cornell renders.
 // What the pooled pre-test needs of a lane (its candidate groups and its culling ray) is parked
 // in shared memory, where any lane can read it; the owner keeps neither in registers.
-template <int FMT, int ANY_, bool COUNT, class RayT, class Out, int REFILL_MIN, int MINB, int SS, int K>
+// The same stack for trees of any depth (variant 5 on a tree deeper than SS - 2 wide levels): the first SS entries in shared
+// memory, the rest in the thread's local memory (only a chain-like tree ever reaches them).
+template <int SS>
+struct DeepStack {
+    uint2* s;
+    uint2* deep;
+    __device__ __forceinline__ U2 get(int i) const { const uint2 v = i < SS ? s[i * 128] : deep[i - SS]; return U2{v.x, v.y}; }
+    __device__ __forceinline__ void set(int i, U2 v) const { if (i < SS) s[i * 128] = make_uint2(v.x, v.y); else deep[i - SS] = make_uint2(v.x, v.y); }
+};
+
+template <int FMT, int ANY_, bool COUNT, class RayT, class Out, int REFILL_MIN, int MINB, int SS, int K, bool DEEP = false>
 __global__ void __launch_bounds__(128, MINB) traceCoopPairKernel(SceneParams sp, const RayT* __restrict__ rays, int64_t n,
                                                                const uint32_t* __restrict__ n_dev, Out out,
                                                                unsigned long long* ctr) {
@@ -461,7 +473,8 @@ __global__ void __launch_bounds__(128, MINB) traceCoopPairKernel(SceneParams sp,
     __shared__ uint2 s_tg[K][4][32];          // (first triangle record, candidate mask) of the K visits
     __shared__ float4 s_cull[2][4][32];       // (cox, coy, coz, ctmax), (fdx, fdy, fdz, -)
     __shared__ uint2 s_stack[SS * 128];
-    const SharedStack sstack = {s_stack + threadIdx.x};
+    uint2 deepEntries[DEEP ? kStackCapacity - SS : 1];
+    const typename std::conditional<DEEP, DeepStack<SS>, SharedStack>::type sstack = {s_stack + threadIdx.x, deepEntries};
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int wid = threadIdx.x >> 5;
@@ -614,10 +627,10 @@ static int launchTraceTyped(spb_ctx* ctx, const RayT* d_rays, int64_t n, const u
                 if (ctx->sp.max_depth <= 14) { kern = traceCoopAheadKernel<FMT, ANY, COUNT, RayT, Out, 8, 0, false, 7, 16>; coop = 11; }
                 else { kern = traceCoopAheadKernel<FMT, ANY, COUNT, RayT, Out, 8, 0, false, 7, 0>; coop = 2; }
             }
-            // 5: three node visits per pooled triangle phase, 6 CTAs per SM (80 registers); same fallbacks as 4
+            // 5: three node visits per pooled triangle phase, 6 CTAs per SM (80 registers); deeper trees: the stack continues in local memory
             if (v == 5) {
                 if (ctx->sp.max_depth <= 14) { kern = traceCoopPairKernel<FMT, ANY, COUNT, RayT, Out, 8, 6, 16, 3>; coop = 15; }
-                else { kern = traceCoopAheadKernel<FMT, ANY, COUNT, RayT, Out, 8, 0, false, 7, 0>; coop = 2; }
+                else { kern = traceCoopPairKernel<FMT, ANY, COUNT, RayT, Out, 8, 6, 16, 3, true>; coop = 20; }
             }
 #ifdef SPB_EXPERIMENTAL_VARIANTS      // measurement variants (trace.cu only; profiles/r01g_kernel_experiments.md)
             if (v == 10) { kern = traceCoopAheadKernel<FMT, ANY, COUNT, RayT, Out, 8, 1, false, 7, 0>; coop = 3; }

@@ -359,9 +359,9 @@ def test_gpu_lbvh_builder_gives_identical_hits(gpu_ctx, golden_torus, golden_cub
     assert st["n_binary_nodes"] == 2 * len(tris) - 1 and st["n_tris"] == len(tris)
 
 
-def test_deep_imported_tree_falls_back_to_the_local_stack(gpu_ctx):
-    """A chain-shaped imported tree is deeper than the shared-memory stack of variants 4 and 5: the launch
-    falls back to variant 3 and the answers are still the reference's."""
+def test_deep_imported_tree_continues_the_stack_in_local_memory(gpu_ctx):
+    """A chain-shaped imported tree is deeper than the shared-memory stack of variants 4 and 5: variant 5 runs with the
+    stack continued in local memory (variant 4 falls back to variant 3) and the answers are still the reference's."""
     from tests.test_traversal_emul import chain_tree
     v, f = scenes.torus_mesh(10, 7)
     tris = scenes.mesh_triangles(v, f)
