@@ -30,11 +30,47 @@ bool cudaOk(spb_ctx* ctx, cudaError_t e, const char* what) {
     return false;
 }
 
+static std::mutex g_poolMutex;
+static cudaMemPool_t g_pools[64] = {};
+static cudaMemPool_t scratchPool(int device) {
+    std::lock_guard<std::mutex> lk(g_poolMutex);
+    if (device < 0 || device >= 64) return nullptr;
+    if (!g_pools[device]) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        cudaMemPool_t pool = nullptr;
+        if (cudaMemPoolCreate(&pool, &props) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        uint64_t keep = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        g_pools[device] = pool;
+    }
+    return g_pools[device];
+}
+cudaError_t scratchAlloc(spb_ctx* ctx, void** p, size_t bytes, cudaStream_t st) {
+    *p = nullptr;
+    if (bytes == 0) bytes = 16;
+    cudaMemPool_t pool = scratchPool(ctx->device);
+    if (!pool) return cudaMalloc(p, bytes);                       // (no pool support: plain allocations; scratchFree copes)
+    return cudaMallocFromPoolAsync(p, bytes, pool, st);
+}
+void scratchFree(void* p, cudaStream_t st) {
+    if (!p) return;
+    if (cudaFreeAsync(p, st) != cudaSuccess) { cudaGetLastError(); cudaFree(p); }
+}
+void scratchRelease(int device) {
+    std::lock_guard<std::mutex> lk(g_poolMutex);
+    if (device >= 0 && device < 64 && g_pools[device]) { cudaDeviceSynchronize(); cudaMemPoolTrimTo(g_pools[device], 0); }
+}
+
 static void freeBvhDevice(spb_ctx* ctx) {
     if (ctx->d_nodes) cudaFree(ctx->d_nodes);
     if (ctx->d_tris) cudaFree(ctx->d_tris);
     if (ctx->d_pre_tris) cudaFree(ctx->d_pre_tris);
     ctx->d_nodes = ctx->d_tris = ctx->d_pre_tris = nullptr;
+    ctx->d_nodes_bytes = ctx->d_tris_bytes = 0;
     ctx->bvh_ready = false;
     // nothing may keep pointing at the freed tree: the kernels' parameter block goes back to "no geometry" and a
     // render that was begun on the old tree needs a new spb_render_begin
@@ -96,6 +132,7 @@ static int uploadBvh(spb_ctx* ctx) {
     if (b.n_tris > 0 && !b.nodes.empty()) {
         SPB_CUDA(ctx, cudaMalloc(&ctx->d_nodes, b.nodes.size() * sizeof(WideNode)));
         SPB_CUDA(ctx, cudaMalloc(&ctx->d_tris, b.tris.size()));
+        ctx->d_nodes_bytes = b.nodes.size() * sizeof(WideNode); ctx->d_tris_bytes = b.tris.size();
         SPB_CUDA(ctx, cudaMemcpyAsync(ctx->d_nodes, b.nodes.data(), b.nodes.size() * sizeof(WideNode), cudaMemcpyHostToDevice, ctx->stream));
         SPB_CUDA(ctx, cudaMemcpyAsync(ctx->d_tris, b.tris.data(), b.tris.size(), cudaMemcpyHostToDevice, ctx->stream));
         SPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -164,6 +201,7 @@ void spb_ctx_destroy(spb_ctx* ctx) {
     cudaDeviceSynchronize();
     renderStateDestroy(ctx);
     freeBvhDevice(ctx);
+    ctx->build_arena.release();
     for (int i = 0; i < spb_ctx::kPipe; i++) {
         if (ctx->d_in[i]) cudaFree(ctx->d_in[i]);
         if (ctx->d_out[i]) cudaFree(ctx->d_out[i]);
@@ -220,9 +258,17 @@ int spb_bvh_build(spb_ctx* ctx, const spb_build_opts* opts) {
     if (o.builder == SPB_BUILDER_DEVICE_SAH && (o.sah_bins != 32 || greedy)) o.builder = SPB_BUILDER_HOST_SAH;
     const auto t0 = std::chrono::steady_clock::now();
     if (o.builder == SPB_BUILDER_DEVICE_SAH) {
+        // a rebuild (an animated mesh, say) keeps the previous tree's two arrays for the builder to fill again when they are
+        // large enough: with the work arrays coming from the scratch pool it then makes no driver allocation at all
+        ctx->spare_nodes = ctx->d_nodes; ctx->spare_nodes_bytes = ctx->d_nodes_bytes;
+        ctx->spare_tris = ctx->d_tris; ctx->spare_tris_bytes = ctx->d_tris_bytes;
+        ctx->d_nodes = ctx->d_tris = nullptr;
         freeBvhDevice(ctx);
         ctx->bin = BinaryBVH();
         const int rc = buildSahDevice(ctx, o.max_leaf_tris);
+        if (ctx->spare_nodes) cudaFree(ctx->spare_nodes);
+        if (ctx->spare_tris) cudaFree(ctx->spare_tris);
+        ctx->spare_nodes = ctx->spare_tris = nullptr; ctx->spare_nodes_bytes = ctx->spare_tris_bytes = 0;
         if (rc) { freeBvhDevice(ctx); return rc; }
         ctx->build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         ctx->builder_used = SPB_BUILDER_DEVICE_SAH;
@@ -295,6 +341,7 @@ int spb_bvh_import_wide(spb_ctx* ctx, const spb_bvh_stats* st, const void* nodes
     if (st->n_tris > 0) {
         SPB_CUDA(ctx, cudaMalloc(&ctx->d_nodes, (size_t)st->node_bytes));
         SPB_CUDA(ctx, cudaMalloc(&ctx->d_tris, (size_t)st->tri_bytes));
+        ctx->d_nodes_bytes = (size_t)st->node_bytes; ctx->d_tris_bytes = (size_t)st->tri_bytes;
         SPB_CUDA(ctx, cudaMemcpyAsync(ctx->d_nodes, nodes, (size_t)st->node_bytes, cudaMemcpyHostToDevice, ctx->stream));
         SPB_CUDA(ctx, cudaMemcpyAsync(ctx->d_tris, tris, (size_t)st->tri_bytes, cudaMemcpyHostToDevice, ctx->stream));
         SPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -333,6 +380,7 @@ int spb_ctx_clone_scene(spb_ctx* dst, spb_ctx* src) {
     if (st.n_tris > 0) {
         SPB_CUDA(dst, cudaMalloc(&dst->d_nodes, (size_t)st.node_bytes));
         SPB_CUDA(dst, cudaMalloc(&dst->d_tris, (size_t)st.tri_bytes));
+        dst->d_nodes_bytes = (size_t)st.node_bytes; dst->d_tris_bytes = (size_t)st.tri_bytes;
         // device to device: over NVLink when the GPUs are peers (mapped above), through the host otherwise (the runtime picks)
         SPB_CUDA(dst, cudaMemcpyPeerAsync(dst->d_nodes, dst->device, src->d_nodes, src->device, (size_t)st.node_bytes, dst->stream));
         SPB_CUDA(dst, cudaMemcpyPeerAsync(dst->d_tris, dst->device, src->d_tris, src->device, (size_t)st.tri_bytes, dst->stream));
@@ -389,6 +437,7 @@ int spb_set_option(spb_ctx* ctx, const char* name, int64_t value) {
     }
     else if (n == "render_graph") ctx->opt_render_graph = value ? 1 : 0;
     else if (n == "wave_slots") { if (value < 1024) return fail(ctx, SPB_ERR_INVALID, "wave_slots too small"); ctx->opt_wave_slots = value; }
+    else if (n == "release_scratch") { cudaSetDevice(ctx->device); cudaDeviceSynchronize(); ctx->build_arena.release(); scratchRelease(ctx->device); }   // the builder's arena and the cached queue memory of this GPU go back to the driver
     else if (n == "chunk_rays") { if (value < 1024) return fail(ctx, SPB_ERR_INVALID, "chunk_rays too small"); ctx->opt_chunk = value; }
     else return fail(ctx, SPB_ERR_INVALID, "spb_set_option: unknown option " + n);
     return SPB_OK;

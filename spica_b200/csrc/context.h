@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdint>
 #include <memory>
 #include <string>
@@ -13,6 +14,35 @@
 #include "bvh_layout.h"
 
 namespace spb { struct RenderState; }
+
+// The device builder's work arrays: a bump allocator over a few large plain allocations that the context keeps, so that a
+// rebuild allocates nothing (26 driver allocations of odd sizes per build cost 3 .. 550 ms, whether from cudaMalloc or from a
+// stream-ordered pool: profiles/r02ae_build_cold.txt, r02ag_build_cold.txt).  reset() at the start of a build; mark() / rewind()
+// give the space of the arrays that die half-way to the second half.  spb_set_option(ctx, "release_scratch", 1) frees it.
+struct ScratchArena {
+    struct Block { char* p; size_t bytes; };
+    std::vector<Block> blocks;
+    size_t cur = 0, off = 0;
+    struct Mark { size_t cur, off; };
+    void reset() { cur = 0; off = 0; }
+    Mark mark() const { return Mark{cur, off}; }
+    void rewind(Mark m) { cur = m.cur; off = m.off; }
+    cudaError_t alloc(void** out, size_t bytes, size_t growBytes) {
+        bytes = (std::max<size_t>(bytes, 16) + 255) & ~(size_t)255;
+        for (; cur < blocks.size(); cur++, off = 0) {
+            if (off + bytes <= blocks[cur].bytes) { *out = blocks[cur].p + off; off += bytes; return cudaSuccess; }
+        }
+        Block b{nullptr, std::max(bytes, growBytes)};
+        cudaError_t e = cudaMalloc((void**)&b.p, b.bytes);
+        if (e != cudaSuccess && b.bytes > bytes) { cudaGetLastError(); b.bytes = bytes; e = cudaMalloc((void**)&b.p, b.bytes); }
+        if (e != cudaSuccess) { *out = nullptr; return e; }
+        blocks.push_back(b);
+        cur = blocks.size() - 1; off = bytes;
+        *out = b.p;
+        return cudaSuccess;
+    }
+    void release() { for (auto& b : blocks) cudaFree(b.p); blocks.clear(); reset(); }
+};
 
 struct spb_ctx {
     int device = 0;
@@ -42,6 +72,9 @@ struct spb_ctx {
 
     void* d_nodes = nullptr;
     void* d_tris = nullptr;
+    size_t d_nodes_bytes = 0, d_tris_bytes = 0;   // sizes of the two allocations (0 = unknown)
+    void* spare_nodes = nullptr; void* spare_tris = nullptr; size_t spare_nodes_bytes = 0, spare_tris_bytes = 0;   // the previous tree's arrays during a device rebuild (re-used when large enough)
+    ScratchArena build_arena;            // sah_build.cu's work arrays, kept between builds
     void* d_pre_tris = nullptr;          // TriF64 scenes: float32-rounded copy for the pre-test (SceneParams::pre_tris)
     spb::SceneParams sp{};
 
@@ -86,6 +119,13 @@ void renderStateDestroy(spb_ctx* ctx);   // integrator.cu
 void renderSceneClone(spb_ctx* dst, spb_ctx* src);   // integrator.cu: materials, lights, textures, environment of src -> dst (host side; uploaded by the next spb_render_begin)
 void renderSceneChanged(spb_ctx* ctx);   // integrator.cu: geometry / attributes changed, a new spb_render_begin is required
 int  buildLbvhDevice(spb_ctx* ctx, BinaryBVH* out);   // lbvh.cu
+// Scratch memory (the render queues): stream-ordered allocations from ONE pool per GPU and process
+// that keeps what is freed (release threshold = max), so a new context re-uses the 8 GB of the one that went away instead of
+// going through the driver's map / unmap (C1 through the host, a context per call: 0.033 / 0.67 / 0.055 s -> 0.027 / 0.028 / 0.025 s).
+// spb_set_option(ctx, "release_scratch", 1) hands the cached memory back.  Not for memory another GPU or process maps.
+cudaError_t scratchAlloc(spb_ctx* ctx, void** p, size_t bytes, cudaStream_t st);
+void        scratchFree(void* p, cudaStream_t st);                    // p may be NULL
+void        scratchRelease(int device);
 int  buildSahDevice(spb_ctx* ctx, int maxLeaf);       // sah_build.cu: the default builder; leaves the 8-wide BVH in ctx->d_nodes / d_tris
 }  // namespace spb
 

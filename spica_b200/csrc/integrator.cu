@@ -718,11 +718,14 @@ void renderStateDestroy(spb_ctx* ctx) {
     freeScene(R); freeEnv(R);
     if (R->graph_exec) cudaGraphExecDestroy(R->graph_exec);
     if (R->d_film) cudaFree(R->d_film);
-    if (R->d_pool) cudaFree(R->d_pool);
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    scratchFree(R->d_pool, ctx->stream);
     if (R->d_ctl) cudaFree(R->d_ctl);
     if (R->d_cursor) cudaFree(R->d_cursor);
     if (R->d_scratch) cudaFree(R->d_scratch);
-    if (R->d_lists) cudaFree(R->d_lists);
+    scratchFree(R->d_lists, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
     if (R->d_list_count) cudaFree(R->d_list_count);
     if (R->h_status) cudaFreeHost(R->h_status);
     for (cudaEvent_t e : R->poll) if (e) cudaEventDestroy(e);
@@ -1024,14 +1027,16 @@ static int uploadEnv(spb_ctx* ctx, RenderState* R) {
 static int allocQueues(spb_ctx* ctx, RenderState* R, int64_t slots) {
     if (R->d_pool && R->slots == slots) return SPB_OK;
     if (R->graph_exec) { cudaGraphExecDestroy(R->graph_exec); R->graph_exec = nullptr; }
-    if (R->d_pool) cudaFree(R->d_pool);
+    if (R->d_pool) { cudaStreamSynchronize(R->side); scratchFree(R->d_pool, ctx->stream); }
     R->d_pool = nullptr; R->slots = 0;
     // per entry: 2 extend queues x (32 B ray + 32 B state) + 16 B hit + 2 x (32 B ray + 16 B contribution) = 240 B
     const size_t per = 2 * 64 + 16 + 2 * 48;
     const size_t bytes = (size_t)slots * per + 4096;
-    cudaError_t e = cudaMalloc(&R->d_pool, bytes);
+    // from the process's scratch pool (context.h): a context created after another one went away re-uses its 8 GB
+    cudaError_t e = scratchAlloc(ctx, &R->d_pool, bytes, ctx->stream);
     if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); return fail(ctx, SPB_ERR_OOM, "out of device memory for the wavefront queues"); }
     SPB_CUDA(ctx, e);
+    SPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));          // (the side stream and the graph use it too)
     char* p = (char*)R->d_pool;
     auto take = [&](size_t b) { void* r = p; p += (b + 255) & ~(size_t)255; return r; };
     for (int k = 0; k < 2; k++) { R->q.ray[k] = (float4*)take((size_t)slots * 32); R->q.state[k] = (float4*)take((size_t)slots * 32); }
@@ -1048,11 +1053,12 @@ static int allocLists(spb_ctx* ctx, RenderState* R) {
     if (!R->sort_materials) return SPB_OK;
     if (R->d_lists && R->list_stride == R->slots) return SPB_OK;
     if (R->graph_exec) { cudaGraphExecDestroy(R->graph_exec); R->graph_exec = nullptr; }
-    if (R->d_lists) cudaFree(R->d_lists);
+    if (R->d_lists) { cudaStreamSynchronize(R->side); scratchFree(R->d_lists, ctx->stream); }
     R->d_lists = nullptr; R->list_stride = 0;
-    cudaError_t e = cudaMalloc(&R->d_lists, (size_t)kNumBuckets * (size_t)R->slots * sizeof(uint32_t));
+    cudaError_t e = scratchAlloc(ctx, (void**)&R->d_lists, (size_t)kNumBuckets * (size_t)R->slots * sizeof(uint32_t), ctx->stream);
     if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); return fail(ctx, SPB_ERR_OOM, "out of device memory for the shading lists"); }
     SPB_CUDA(ctx, e);
+    SPB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (!R->d_list_count) { SPB_CUDA(ctx, cudaMalloc(&R->d_list_count, 16 * sizeof(uint32_t))); }
     SPB_CUDA(ctx, cudaMemset(R->d_list_count, 0, 16 * sizeof(uint32_t)));
     R->list_stride = R->slots;

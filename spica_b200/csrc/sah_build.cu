@@ -647,18 +647,18 @@ struct WideWork { int32_t bnode; int32_t nch; int32_t ch[8]; uint8_t leaf[8]; };
 
 // children of the forest C(b, i) (bvh_host.cpp, collectDp), appended to w->ch in left-to-right order
 __device__ void collectDp(const DNode* __restrict__ nodes, const DpRow* __restrict__ rows, int b0, int i0, WideWork* w) {
-    int fb[64], fi[64]; int nf = 0;
-    fb[nf] = b0; fi[nf] = i0; nf++;
+    int fb[12]; uint8_t fi[12]; int nf = 0;      // the parts of the entries on the stack are >= 1 each and sum to <= 8
+    fb[nf] = b0; fi[nf] = (uint8_t)i0; nf++;
     while (nf > 0) {
         nf--;
-        const int b = fb[nf]; int i = fi[nf];
+        const int b = fb[nf]; int i = (int)fi[nf];
         const DNode& n = nodes[b];
         if (n.left < 0 && n.right < 0) { w->leaf[w->nch] = 1; w->ch[w->nch++] = b; continue; }
         while (i > 1 && rows[b].k[i - 1] == 0) i--;
         if (i == 1) { w->leaf[w->nch] = rows[b].leaf; w->ch[w->nch++] = b; continue; }
         const int k = rows[b].k[i - 1];
-        fb[nf] = n.right; fi[nf] = i - k; nf++;        // popped after the left part
-        fb[nf] = n.left; fi[nf] = k; nf++;
+        fb[nf] = n.right; fi[nf] = (uint8_t)(i - k); nf++;        // popped after the left part
+        fb[nf] = n.left; fi[nf] = (uint8_t)k; nf++;
     }
 }
 
@@ -847,32 +847,37 @@ int buildSahDevice(spb_ctx* ctx, int maxLeaf) {
     int2* d_small = nullptr; uint32_t *d_chunks = nullptr, *d_chunkStart = nullptr; Bin* d_bins = nullptr; void* d_scan = nullptr;
     DpRow* d_rows = nullptr; unsigned int* d_flags = nullptr; WideWork* d_work = nullptr; uint32_t *d_nInner = nullptr, *d_nTris = nullptr, *d_innerScan = nullptr, *d_triScan = nullptr;
     int32_t* d_level[2] = {nullptr, nullptr};
-    WideNode* d_wide = nullptr; void* d_tris = nullptr;
+    WideNode* d_wide = nullptr; void* d_tris = nullptr; size_t trisBytes = 0;
     bool keepWide = false;
+    // work arrays: bumped out of the context's arena (context.h), which keeps its memory for the next build; the triangle
+    // records and the final node array, which other streams, GPUs and processes read, are plain allocations
+    ScratchArena& arena = ctx->build_arena;
+    arena.reset();
+    const size_t arenaGrow = (size_t)n * 480 + ((size_t)64 << 20);      // one build's worth: the peak is ~ 460 B per triangle
     auto freeAll = [&]() {
-        cudaFree(d_verts); cudaFree(d_prims); cudaFree(d_idx[0]); cudaFree(d_idx[1]); cudaFree(d_order); cudaFree(d_parent); cudaFree(d_nodes); cudaFree(d_cbs);
-        cudaFree(d_g); cudaFree(d_large[0]); cudaFree(d_large[1]); cudaFree(d_small); cudaFree(d_chunks); cudaFree(d_chunkStart); cudaFree(d_bins); cudaFree(d_scan);
-        cudaFree(d_rows); cudaFree(d_flags); cudaFree(d_work); cudaFree(d_nInner); cudaFree(d_nTris); cudaFree(d_innerScan); cudaFree(d_triScan);
-        cudaFree(d_level[0]); cudaFree(d_level[1]);
-        if (!keepWide) { cudaFree(d_wide); cudaFree(d_tris); }
+        cudaStreamSynchronize(st);
+        if (!keepWide) { cudaFree(d_tris); d_tris = nullptr; }
     };
+#define SALLOC(ptr, bytes) SB(arena.alloc((void**)&(ptr), (bytes), arenaGrow))
     const int nNodesMax = 2 * n - 1;
     const int maxLarge = n / kSmall + 2;                     // large nodes of one level are disjoint and hold > kSmall primitives each
     const int maxSmallTasks = 2 * maxLarge + 2;              // every small task is the child of a large node (or the root)
-    SB(cudaMalloc(&d_verts, (size_t)n * 9 * sizeof(double)));
-    SB(cudaMalloc(&d_prims, (size_t)n * sizeof(DBox)));
-    SB(cudaMalloc(&d_idx[0], (size_t)n * 4)); SB(cudaMalloc(&d_idx[1], (size_t)n * 4)); SB(cudaMalloc(&d_order, (size_t)n * 4));
-    SB(cudaMalloc(&d_parent, (size_t)nNodesMax * 4));
-    SB(cudaMalloc(&d_nodes, (size_t)nNodesMax * sizeof(DNode)));
-    SB(cudaMalloc(&d_cbs, (size_t)nNodesMax * sizeof(DBox)));
-    SB(cudaMalloc(&d_g, sizeof(BuildGlobals)));
-    SB(cudaMalloc(&d_large[0], (size_t)maxLarge * sizeof(LargeTask))); SB(cudaMalloc(&d_large[1], (size_t)maxLarge * sizeof(LargeTask)));
-    SB(cudaMalloc(&d_small, (size_t)maxSmallTasks * sizeof(int2)));
-    SB(cudaMalloc(&d_chunks, (size_t)(maxLarge + 1) * 4)); SB(cudaMalloc(&d_chunkStart, (size_t)(maxLarge + 1) * 4));
-    SB(cudaMalloc(&d_bins, (size_t)maxLarge * 3 * kBins * sizeof(Bin)));
+    SALLOC(d_verts, (size_t)n * 9 * sizeof(double));
+    SALLOC(d_order, (size_t)n * 4);
+    SALLOC(d_parent, (size_t)nNodesMax * 4);
+    SALLOC(d_nodes, (size_t)nNodesMax * sizeof(DNode));
+    SALLOC(d_g, sizeof(BuildGlobals));
+    SALLOC(d_large[0], (size_t)maxLarge * sizeof(LargeTask)); SALLOC(d_large[1], (size_t)maxLarge * sizeof(LargeTask));
+    SALLOC(d_small, (size_t)maxSmallTasks * sizeof(int2));
+    SALLOC(d_chunks, (size_t)(maxLarge + 1) * 4); SALLOC(d_chunkStart, (size_t)(maxLarge + 1) * 4);
+    const ScratchArena::Mark afterTree = arena.mark();        // what follows dies with the binary tree's construction
+    SALLOC(d_prims, (size_t)n * sizeof(DBox));
+    SALLOC(d_idx[0], (size_t)n * 4); SALLOC(d_idx[1], (size_t)n * 4);
+    SALLOC(d_cbs, (size_t)nNodesMax * sizeof(DBox));
+    SALLOC(d_bins, (size_t)maxLarge * 3 * kBins * sizeof(Bin));
     size_t scanBytes = 0;
     SB(cub::DeviceScan::ExclusiveSum(nullptr, scanBytes, d_chunks, d_chunkStart, std::max(maxLarge + 1, n / 2 + 2), st));
-    SB(cudaMalloc(&d_scan, scanBytes));
+    SALLOC(d_scan, scanBytes);
 
     lap("allocations");
     SB(cudaMemcpyAsync(d_verts, ctx->geo->verts.data(), (size_t)n * 9 * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -935,8 +940,8 @@ int buildSahDevice(spb_ctx* ctx, int maxLeaf) {
     const int nNodes = (int)hg.nodeCounter;
     if (nNodes != nNodesMax) { freeAll(); return fail(ctx, SPB_ERR_CUDA, "internal: the device builder produced " + std::to_string(nNodes) + " nodes for " + std::to_string(n) + " triangles"); }
     // the large-node scratch is dead
-    cudaFree(d_bins); d_bins = nullptr; cudaFree(d_idx[0]); d_idx[0] = nullptr; cudaFree(d_idx[1]); d_idx[1] = nullptr; cudaFree(d_cbs); d_cbs = nullptr;
-    cudaFree(d_prims); d_prims = nullptr;
+    d_bins = nullptr; d_idx[0] = d_idx[1] = nullptr; d_cbs = nullptr; d_prims = nullptr; d_scan = nullptr; scanBytes = 0;
+    arena.rewind(afterTree);
 
     // ---- world box, triangle format, inflation (bvh_host.cpp, encode_wide)
     double wlo[3], whi[3], mag = 0.0;
@@ -962,25 +967,31 @@ int buildSahDevice(spb_ctx* ctx, int maxLeaf) {
     // ---- (3) collapse
     float cTri = 0.7f;
     if (const char* e = std::getenv("SPICA_BVH_CTRI")) cTri = (float)std::atof(e);
-    SB(cudaMalloc(&d_rows, (size_t)nNodes * sizeof(DpRow)));
-    SB(cudaMalloc(&d_flags, (size_t)nNodes * 4));
+    SALLOC(d_rows, (size_t)nNodes * sizeof(DpRow));
+    SALLOC(d_flags, (size_t)nNodes * 4);
     SB(cudaMemsetAsync(d_flags, 0, (size_t)nNodes * 4, st));
     dpRowKernel<<<(nNodes + 255) / 256, 256, 0, st>>>(d_nodes, nNodes, d_parent, d_rows, d_flags, maxLeaf, cTri);
     launches++;
+    lap("collapse: cost rows");
     const size_t triSize = hb.tri_format == 0 ? sizeof(TriF32) : sizeof(TriF64);
     const int wideMax = n + 16;                  // at most one wide node per ... every wide node below the root has >= 2 primitives beneath it
     const int levelMax = n + 16;
-    SB(cudaMalloc(&d_wide, (size_t)wideMax * sizeof(WideNode)));
-    SB(cudaMalloc(&d_tris, (size_t)n * triSize));
-    SB(cudaMalloc(&d_level[0], (size_t)levelMax * 4)); SB(cudaMalloc(&d_level[1], (size_t)levelMax * 4));
-    SB(cudaMalloc(&d_work, (size_t)levelMax * sizeof(WideWork)));
-    SB(cudaMalloc(&d_nInner, (size_t)(levelMax + 1) * 4)); SB(cudaMalloc(&d_nTris, (size_t)(levelMax + 1) * 4));
-    SB(cudaMalloc(&d_innerScan, (size_t)(levelMax + 1) * 4)); SB(cudaMalloc(&d_triScan, (size_t)(levelMax + 1) * 4));
+    SALLOC(d_wide, (size_t)wideMax * sizeof(WideNode));
+    if (ctx->spare_tris && ctx->spare_tris_bytes >= (size_t)n * triSize && ctx->spare_tris_bytes <= 2 * (size_t)n * triSize) {
+        d_tris = ctx->spare_tris; trisBytes = ctx->spare_tris_bytes; ctx->spare_tris = nullptr; ctx->spare_tris_bytes = 0;
+    } else {
+        SB(cudaMalloc(&d_tris, (size_t)n * triSize)); trisBytes = (size_t)n * triSize;
+    }
+    SALLOC(d_level[0], (size_t)levelMax * 4); SALLOC(d_level[1], (size_t)levelMax * 4);
+    SALLOC(d_work, (size_t)levelMax * sizeof(WideWork));
+    SALLOC(d_nInner, (size_t)(levelMax + 1) * 4); SALLOC(d_nTris, (size_t)(levelMax + 1) * 4);
+    SALLOC(d_innerScan, (size_t)(levelMax + 1) * 4); SALLOC(d_triScan, (size_t)(levelMax + 1) * 4);
     {
         size_t need = 0;
         SB(cub::DeviceScan::ExclusiveSum(nullptr, need, d_nInner, d_innerScan, levelMax + 1, st));
-        if (need > scanBytes) { cudaFree(d_scan); d_scan = nullptr; SB(cudaMalloc(&d_scan, need)); scanBytes = need; }
+        if (need > scanBytes) { SALLOC(d_scan, need); scanBytes = need; }
     }
+    lap("emission: allocations");
     const int32_t rootNode = 0;
     SB(cudaMemcpyAsync(d_level[0], &rootNode, 4, cudaMemcpyHostToDevice, st));
     int nLevel = 1, lv = 0, depth = 0;
@@ -1004,7 +1015,7 @@ int buildSahDevice(spb_ctx* ctx, int maxLeaf) {
         nLevel = (int)tot[0];
         lv ^= 1;
     }
-    lap("collapse + emission");
+    lap("emission: levels");
     if ((int64_t)triBase != n64) { freeAll(); return fail(ctx, SPB_ERR_CUDA, "internal: the device collapse emitted " + std::to_string(triBase) + " of " + std::to_string(n) + " triangles"); }
     if (depth > kStackCapacity - 2) { freeAll(); return fail(ctx, SPB_ERR_UNSUPPORTED, "spb_bvh_build: wide tree deeper than the traversal stack (" + std::to_string(depth) + ")"); }
     SB(cudaMemcpyAsync(&hg, d_g, sizeof(hg), cudaMemcpyDeviceToHost, st));
@@ -1016,17 +1027,22 @@ int buildSahDevice(spb_ctx* ctx, int maxLeaf) {
     ctx->kernel_launches += launches;
     // shrink the node array to its size and hand both over
     WideNode* d_fit = nullptr;
-    SB(cudaMalloc(&d_fit, (size_t)levelBase * sizeof(WideNode)));
+    size_t fitBytes = (size_t)levelBase * sizeof(WideNode);
+    if (ctx->spare_nodes && ctx->spare_nodes_bytes >= fitBytes && ctx->spare_nodes_bytes <= 2 * fitBytes) {
+        d_fit = (WideNode*)ctx->spare_nodes; fitBytes = ctx->spare_nodes_bytes; ctx->spare_nodes = nullptr; ctx->spare_nodes_bytes = 0;
+    } else {
+        SB(cudaMalloc(&d_fit, fitBytes));
+    }
     SB(cudaMemcpyAsync(d_fit, d_wide, (size_t)levelBase * sizeof(WideNode), cudaMemcpyDeviceToDevice, st));
     SB(cudaStreamSynchronize(st));
-    cudaFree(d_wide); d_wide = nullptr;
     ctx->d_nodes = d_fit; ctx->d_tris = d_tris;
+    ctx->d_nodes_bytes = fitBytes; ctx->d_tris_bytes = trisBytes;
     keepWide = true;
-    d_wide = nullptr;
     freeAll();
     lap("hand-over + frees");
     return SPB_OK;
 }
+#undef SALLOC
 #undef SB
 
 }  // namespace spb
