@@ -149,6 +149,7 @@ struct RenderState {
     // envmap
     std::vector<float> env_rgb; int env_w = 0, env_h = 0; double env_l2w[16]; double env_scale = 1.0, env_center[3] = {0, 0, 0}, env_radius = 2.0;
     bool env_present = false, env_dirty = false;
+    bool mis_any_hit = false;           // no area light in the scene: every MIS ray only asks whether it escapes (set by spb_render_begin)
     float4* d_env_texels = nullptr; float* d_env_floats = nullptr;
     DeviceScene ds{};
     // film + queues
@@ -1128,7 +1129,12 @@ static int enqueueIteration(spb_ctx* ctx, RenderState* R, int cur, cudaStream_t 
     // the captured graph.
     SPB_CUDA(ctx, cudaEventRecord(R->ev_fork, st));
     SPB_CUDA(ctx, cudaStreamWaitEvent(R->side, R->ev_fork, 0));
-    if ((rc = launchTrace<false>(ctx, (const spb_ray_f32*)R->q.mis, cap, R->q.count + 3, SinkMis{R->q.mis, R->q.misC, R->d_film}, R->d_cursor + 8, R->side, true))) return rc;
+    // a BSDF-sampled MIS ray towards an area light needs the closest hit (is it that emitter's triangle? core/mis.cc:122-125);
+    // towards the environment only whether anything is in the way (mis.cc:126-128): with no area light in the scene the whole
+    // queue takes the any-hit kernel, and SinkMis's "expected primitive -1" test is the same test
+    if (R->mis_any_hit) rc = launchTrace<true>(ctx, (const spb_ray_f32*)R->q.mis, cap, R->q.count + 3, SinkMis{R->q.mis, R->q.misC, R->d_film}, R->d_cursor + 8, R->side, true);
+    else rc = launchTrace<false>(ctx, (const spb_ray_f32*)R->q.mis, cap, R->q.count + 3, SinkMis{R->q.mis, R->q.misC, R->d_film}, R->d_cursor + 8, R->side, true);
+    if (rc) return rc;
     SPB_CUDA(ctx, cudaEventRecord(R->ev_join, R->side));
     if ((rc = launchTrace<true>(ctx, (const spb_ray_f32*)R->q.shadow, cap, R->q.count + 2, SinkShadow{R->q.shadow, R->q.shadowC, R->d_film}, R->d_cursor + 4, st, true))) return rc;
     SPB_CUDA(ctx, cudaStreamWaitEvent(st, R->ev_join, 0));
@@ -1307,6 +1313,8 @@ int spb_render_begin(spb_ctx* ctx, const spb_render_desc* desc) {
     }
     for (int32_t l : ctx->light_id)
         if (l >= (int32_t)R->lights.size()) return fail(ctx, SPB_ERR_INVALID, "spb_render_begin: a triangle refers to a light that was not set");
+    R->mis_any_hit = !R->lights.empty();
+    for (const spb_light& l : R->lights) if (l.type != SPB_LIGHT_ENVMAP) R->mis_any_hit = false;
     if (R->scene_dirty && (rc = uploadScene(ctx, R))) return rc;
     if (R->env_dirty || (R->env_present && !R->ds.env.present)) { if ((rc = uploadEnv(ctx, R))) return rc; }
     R->desc = *desc;
