@@ -334,8 +334,10 @@ int spb_get_counters(spb_ctx* ctx, spb_counters* out);
  * variant returns the same records), "chunk_rays" (rays per pipelined chunk of the host-buffer calls,
  * default 524288), "wave_slots" (capacity of the integrator's queues = paths in flight, 240 B each, default 32 Mi but never more than 64 samples of the image, takes effect at
  * the next spb_render_begin), "render_graph" (0 = plain launches instead of the CUDA graph),
- * "shade_minb" (4/5/6: occupancy the Lambertian-only shade instance is compiled for). Unknown names
- * return SPB_ERR_INVALID.
+ * "shade_minb" (4/5/6: occupancy the Lambertian-only shade instance is compiled for),
+ * "release_scratch" (any value: frees what the context keeps between calls to make them cheap -- the device builder's work
+ * arena, about 460 B per triangle of the largest build, and the process-wide cache of freed queue memory of this GPU).
+ * Unknown names return SPB_ERR_INVALID.
  * Environment read by spb_bvh_build / spb_bvh_import_binary: SPICA_BVH_COLLAPSE=0 selects the greedy
  * 8-wide collapse instead of the cost-optimal one (host builder). */
 int spb_set_option(spb_ctx* ctx, const char* name, int64_t value);
