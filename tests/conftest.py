@@ -80,3 +80,33 @@ def transformed_torus_case(offset, n_incoherent=40000, n_aimed=20000):
     aimed[:, 7] = 1e32
     rays = np.concatenate([scenes.incoherent_rays(n_incoherent, lo, hi, seed=11), aimed])
     return tris, rays, lo, hi
+
+
+def random_soup_cases(seed, n_random=3000, n_aimed=3000):
+    """Random triangle soups (needles, slivers, overlapping and touching triangles) at a random scale and offset: yields
+    (tris float64 [n, 9], rays float32 [m, 8]) twice -- float32-exact vertices, then arbitrary doubles -- with random rays and
+    rays aimed at vertices, edges and interior points of the triangles."""
+    import numpy as np
+    from spica_b200 import scenes
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(1, 400))
+    scale = 10.0 ** rng.uniform(-3, 3)
+    offset = rng.uniform(-1, 1, 3) * scale * 10.0 ** rng.uniform(-1, 2.5)
+    base = rng.uniform(-1, 1, (n, 1, 3))
+    ext = 10.0 ** rng.uniform(-3, 0, (n, 1, 1))
+    shape = rng.normal(size=(n, 3, 3)) * ext
+    k = n // 5                                                                     # slivers
+    shape[:k, 2] = shape[:k, 0] + (shape[:k, 1] - shape[:k, 0]) * rng.uniform(0, 1, (k, 1)) + rng.normal(size=(k, 3)) * 1e-6
+    v64 = (base + shape) * scale + offset
+    for tris in (v64.astype(np.float32).astype(np.float64).reshape(n, 9), v64.reshape(n, 9)):
+        lo, hi = tris.reshape(-1, 3).min(0), tris.reshape(-1, 3).max(0)
+        m = n_aimed
+        tv = tris.reshape(n, 3, 3)[rng.integers(0, n, m)]
+        w = rng.dirichlet([0.3, 0.3, 0.3], m)                                    # near vertices and edges more often than not
+        w[: m // 6] = np.eye(3)[rng.integers(0, 3, m // 6)]                        # exactly at a vertex
+        tgt = (tv * w[:, :, None]).sum(1)
+        aimed = np.zeros((m, 8), np.float32)
+        aimed[:, :3] = lo + (hi - lo) * rng.uniform(-0.5, 1.5, (m, 3))
+        aimed[:, 3:6] = tgt - aimed[:, :3].astype(np.float64)
+        aimed[:, 7] = 1e32
+        yield tris, np.concatenate([scenes.incoherent_rays(n_random, lo, hi, seed=seed), aimed])

@@ -102,6 +102,22 @@ def test_transformed_mesh_double_vertices_on_the_pooled_kernels(gpu_ctx, variant
     gpu_ctx.set_option("trace_variant", DEFAULT_VARIANT)
 
 
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
+def test_random_triangle_soups_against_the_brute_force(gpu_ctx, seed):
+    """tests/test_traversal_emul.py::test_random_triangle_soups_float32_and_double_vertices through the C ABI: slivers, needles,
+    touching triangles, float32 and double vertices, rays aimed at vertices and edges.  The bar is the reference's triangle
+    test run over ALL triangles (its own traversal loses a hit to its box test now and then on such rays)."""
+    from tests.conftest import random_soup_cases
+    for tris, rays in random_soup_cases(seed):
+        pb, tb = ob.trace_bruteforce(tris, rays)
+        gpu_ctx.set_triangles(tris)
+        for builder in (0, 2):
+            gpu_ctx.build(builder=builder, max_leaf_tris=1 + (seed + builder) % 3)
+            _check_closest(gpu_ctx, tris, rays, pb, tb, max_ties=len(rays))      # ties: verified one by one in _check_closest
+        occ = gpu_ctx.trace_any(rays)
+        assert np.array_equal(occ, (pb >= 0).astype(np.uint8))
+
+
 def test_medium_torus_vs_oracle_with_import(gpu_ctx):
     v, f = scenes.torus_mesh(200, 100)
     tris = scenes.mesh_triangles(v, f)

@@ -336,30 +336,11 @@ def test_transformed_mesh_rounded_pretest(offset):
 def test_random_triangle_soups_float32_and_double_vertices(seed):
     """Random triangle soups (needles, slivers, overlapping and touching triangles) at random scales and offsets, once with
     float32-exact and once with arbitrary double vertices, under random rays and rays aimed at vertices, edge midpoints and
-    centroids: every traversal order of the product returns the oracle's t bit for bit, and ids up to exact ties."""
-    rng = np.random.default_rng(1000 + seed)
-    n = int(rng.integers(1, 400))
-    scale = 10.0 ** rng.uniform(-3, 3)
-    offset = rng.uniform(-1, 1, 3) * scale * 10.0 ** rng.uniform(-1, 2.5)
-    base = rng.uniform(-1, 1, (n, 1, 3))
-    ext = 10.0 ** rng.uniform(-3, 0, (n, 1, 1))
-    shape = rng.normal(size=(n, 3, 3)) * ext
-    shape[: n // 5, 2] = shape[: n // 5, 0] + (shape[: n // 5, 1] - shape[: n // 5, 0]) * rng.uniform(0, 1, (n // 5, 1)) \
-        + rng.normal(size=(n // 5, 3)) * 1e-6                                      # slivers
-    v64 = (base + shape) * scale + offset
-    for tris in (v64.astype(np.float32).astype(np.float64).reshape(n, 9), v64.reshape(n, 9)):
-        lo, hi = tris.reshape(-1, 3).min(0), tris.reshape(-1, 3).max(0)
-        m = 3000
-        pick = rng.integers(0, n, m)
-        tv = tris.reshape(n, 3, 3)[pick]
-        w = rng.dirichlet([0.3, 0.3, 0.3], m)                                    # near vertices and edges more often than not
-        w[: m // 6] = np.eye(3)[rng.integers(0, 3, m // 6)]                        # exactly at a vertex
-        tgt = (tv * w[:, :, None]).sum(1)
-        aimed = np.zeros((m, 8), np.float32)
-        aimed[:, :3] = lo + (hi - lo) * rng.uniform(-0.5, 1.5, (m, 3))
-        aimed[:, 3:6] = tgt - aimed[:, :3].astype(np.float64)
-        aimed[:, 7] = 1e32
-        rays = np.concatenate([scenes.incoherent_rays(3000, lo, hi, seed=seed), aimed])
+    centroids: every traversal order of the product returns the brute-force t of the reference's triangle test bit for bit,
+    and ids up to exact ties."""
+    from tests.conftest import random_soup_cases
+    rng = np.random.default_rng(seed)
+    for tris, rays in random_soup_cases(seed):
         nodes = ob.bvh_build(tris)
         p0, t0, _, _ = ob.trace_closest(nodes, tris, rays)
         assert (p0 >= 0).sum() > 500
