@@ -21,6 +21,8 @@ for variant in variants:
             ctx = capi.Context(0)
             ctx.set_option("wave_slots", sl)
             ctx.set_option("render_graph", g)
+            if os.environ.get("SPB_SHADE_MINB"):
+                ctx.set_option("shade_minb", int(os.environ["SPB_SHADE_MINB"]))
             img = capi.cornell_render(ctx, W, H, 8, max_depth=16, seed=1, variant=variant)
             best = 1e9
             for rep in range(2):
@@ -29,7 +31,7 @@ for variant in variants:
                 best = min(best, time.perf_counter() - t0)
             img = ctx.film_resolve()
             st = ctx.render_stats()
-            r = {"scene": variant, "slots": sl, "graph": g, "spp": spp, "msamples_s": W * H * spp / best * 1e-6, "seconds": best,
+            r = {"scene": variant, "slots": sl, "graph": g, "spp": spp, "shade_minb": os.environ.get("SPB_SHADE_MINB", "default"), "msamples_s": W * H * spp / best * 1e-6, "seconds": best,
                  "mean": float(img.mean()), "iterations": st["iterations"], "launches": st["kernel_launches"],
                  "rays_per_sample": (st["rays_closest"] + st["rays_shadow"] + st["rays_mis"]) / max(st["paths"], 1)}
             print(json.dumps(r), flush=True)
