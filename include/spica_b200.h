@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SPB_VERSION 2
+#define SPB_VERSION 3
 
 typedef enum spb_status {
     SPB_OK = 0,

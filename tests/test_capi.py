@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(L, s), "libspica_b200.so does not export " + s
     assert sorted(capi.SYMBOLS) == sorted(s for s in syms), "capi.SYMBOLS out of sync with the header"
-    assert L.spb_version() == 2
+    assert L.spb_version() == 3
 
 
 def test_record_sizes_match_header():
