@@ -102,7 +102,7 @@ def test_transformed_mesh_double_vertices_on_the_pooled_kernels(gpu_ctx, variant
     gpu_ctx.set_option("trace_variant", DEFAULT_VARIANT)
 
 
-@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("seed", [2, 4, 6])          # (2 and 4 hold rays on which the reference's traversal loses a hit; all six run in the CPU emulation test)
 def test_random_triangle_soups_against_the_brute_force(gpu_ctx, seed):
     """tests/test_traversal_emul.py::test_random_triangle_soups_float32_and_double_vertices through the C ABI: slivers, needles,
     touching triangles, float32 and double vertices, rays aimed at vertices and edges.  The bar is the reference's triangle
