@@ -1772,17 +1772,21 @@ int spb_film_import_handles(spb_ctx* root, const char* handles, int32_t n) {
     RenderState* R = root->render;
     if ((rc = workerDrain(root, R))) return rc;
     cudaSetDevice(root->device);
+    // all or nothing: every handle is checked before the first one is opened, and what was mapped before goes either way
     for (void* p : R->ipc_films) cudaIpcCloseMemHandle(p);
     R->ipc_films.clear();
     for (int k = 0; k < n; k++) {
         const char* hb = handles + (size_t)k * SPB_FILM_HANDLE_BYTES;
-        cudaIpcMemHandle_t h;
         int64_t px = 0; uint64_t magic = 0;
-        std::memcpy(&h, hb, sizeof(h));
-        std::memcpy(&px, hb + sizeof(h), 8);
-        std::memcpy(&magic, hb + sizeof(h) + 8, 8);
+        std::memcpy(&px, hb + sizeof(cudaIpcMemHandle_t), 8);
+        std::memcpy(&magic, hb + sizeof(cudaIpcMemHandle_t) + 8, 8);
         if (magic != kFilmHandleMagic) return fail(root, SPB_ERR_INVALID, "spb_film_import_handles: not a handle of spb_film_export_handle");
         if (px != R->film_pixels) return fail(root, SPB_ERR_INVALID, "spb_film_import_handles: every film needs the root's size");
+    }
+    for (int k = 0; k < n; k++) {
+        const char* hb = handles + (size_t)k * SPB_FILM_HANDLE_BYTES;
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, hb, sizeof(h));
         void* p = nullptr;
         const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
         if (e != cudaSuccess) {
