@@ -4,6 +4,9 @@
 // /root/reference/sources); nothing here computes radiance or intersections on the CPU -- the
 // `bvh` accelerator and the `path` integrator forward to libspica_b200.so.
 #pragma once
+#include <algorithm>
+#include <thread>
+#include <type_traits>
 #include <array>
 #include <cmath>
 #include <cstdint>
@@ -18,6 +21,17 @@
 #include "../../include/spica_b200.h"
 
 namespace spica {
+
+// fn(begin, end) over [0, n) on the host cores (mesh loading and flattening of multi-million-triangle scenes)
+template <class F>
+inline void parallelFor(size_t n, F fn, size_t grain = 1 << 16) {
+    size_t nt = std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), 32);
+    nt = std::min(nt, (n + grain - 1) / grain);
+    if (nt <= 1) { fn((size_t)0, n); return; }
+    std::vector<std::thread> th;
+    for (size_t t = 0; t < nt; t++) th.emplace_back([=]() { fn(n * t / nt, n * (t + 1) / nt); });
+    for (auto& t : th) t.join();
+}
 
 // core/common.h:71-115: the reference reports errors by printing and aborting
 [[noreturn]] void FatalError(const char* fmt, ...);
@@ -286,7 +300,20 @@ void registerBuiltinPlugins();      // plugins.cc + gpu_path.cc
 // ---- mesh loading (core/meshio.cc:76-261): one Triangle per face, transformed to world space
 namespace meshio {
 std::vector<Triangle> loadOBJ(const std::string& file, const Transform& objectToWorld);
-std::vector<Triangle> loadPLY(const std::string& file, const Transform& objectToWorld);
+// The triangles of a large mesh in storage that nobody touches before the loader's threads fill it (a std::vector would
+// value-initialise 200 bytes per triangle on one thread first: seconds at ten million triangles).
+struct TriangleBuffer {
+    Triangle* p = nullptr; size_t n = 0;
+    TriangleBuffer() = default;
+    explicit TriangleBuffer(size_t count) : p((Triangle*)std::malloc(sizeof(Triangle) * std::max<size_t>(count, 1))), n(count) { if (!p) FatalError("out of memory for %zu triangles", count); }
+    TriangleBuffer(TriangleBuffer&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    TriangleBuffer& operator=(TriangleBuffer&& o) noexcept { if (this != &o) { std::free(p); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
+    TriangleBuffer(const TriangleBuffer&) = delete;
+    TriangleBuffer& operator=(const TriangleBuffer&) = delete;
+    ~TriangleBuffer() { std::free(p); }
+    static_assert(std::is_trivially_destructible<Triangle>::value && std::is_trivially_copyable<Triangle>::value, "Triangle must stay a plain value");
+};
+TriangleBuffer loadPLY(const std::string& file, const Transform& objectToWorld);
 }
 
 // ---- scene parser (spica/sceneparser.cc)

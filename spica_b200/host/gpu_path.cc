@@ -4,6 +4,7 @@
 //   integrator  "path" (integrators/path/path.h:21-41) -> spb_render_* ; the finished image goes back
 //                                                      through Film::setImage + Film::save (core/film.cc:23-63)
 // Nothing is computed on the CPU here; a missing device is a FatalError (no fallback).
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <cstring>
@@ -138,25 +139,40 @@ void flatten(const std::vector<std::shared_ptr<Primitive>>& prims, FlatScene* f)
         }
         return it->second;
     };
+    // materials and textures in order of first appearance (serial: a pointer comparison per triangle), then the arrays in parallel
+    const SurfaceMaterial* last = nullptr; int lastIndex = -1;
     for (size_t i = 0; i < n; i++) {
-        const Primitive& p = *prims[i];
-        for (int k = 0; k < 3; k++) { f->verts[i * 9 + k * 3] = p.tri.p[k].x; f->verts[i * 9 + k * 3 + 1] = p.tri.p[k].y; f->verts[i * 9 + k * 3 + 2] = p.tri.p[k].z; }
-        if (p.tri.hasNormals) {
-            f->anyNormals = true;
-            for (int k = 0; k < 3; k++) { f->normals[i * 9 + k * 3] = (float)p.tri.n[k].x; f->normals[i * 9 + k * 3 + 1] = (float)p.tri.n[k].y; f->normals[i * 9 + k * 3 + 2] = (float)p.tri.n[k].z; }
-            for (int k = 0; k < 3; k++) { f->uvs[i * 6 + k * 2] = (float)p.tri.uv[k][0]; f->uvs[i * 6 + k * 2 + 1] = (float)p.tri.uv[k][1]; if (p.tri.uv[k][0] != 0.0 || p.tri.uv[k][1] != 0.0) f->anyUV = true; }
+        const SurfaceMaterial* m = prims[i]->material.get();
+        if (!m) { f->material_id[i] = -1; continue; }            // no bsdf: the path passes through (path.cc:71-75)
+        if (m != last) {
+            auto it = matIndex.find(m);
+            if (it == matIndex.end()) {
+                spb_material d; m->describe(&d);
+                const Texture *tkr, *tkt; m->textures(&tkr, &tkt);
+                it = matIndex.emplace(m, (int)f->materials.size()).first;
+                f->materials.push_back(d);
+                f->matTex.push_back(bindTexture(tkr)); f->matTex.push_back(bindTexture(tkt));
+            }
+            last = m; lastIndex = it->second;
         }
-        if (!p.material) { f->material_id[i] = -1; continue; }        // no bsdf: the path passes through (path.cc:71-75)
-        auto it = matIndex.find(p.material.get());
-        if (it == matIndex.end()) {
-            spb_material m; p.material->describe(&m);
-            const Texture *tkr, *tkt; p.material->textures(&tkr, &tkt);
-            it = matIndex.emplace(p.material.get(), (int)f->materials.size()).first;
-            f->materials.push_back(m);
-            f->matTex.push_back(bindTexture(tkr)); f->matTex.push_back(bindTexture(tkt));
-        }
-        f->material_id[i] = it->second;
+        f->material_id[i] = lastIndex;
     }
+    std::atomic<bool> anyN(false), anyUV(false);
+    parallelFor(n, [&](size_t b, size_t e) {
+        bool hasN = false, hasUV = false;
+        for (size_t i = b; i < e; i++) {
+            const Primitive& p = *prims[i];
+            for (int k = 0; k < 3; k++) { f->verts[i * 9 + k * 3] = p.tri.p[k].x; f->verts[i * 9 + k * 3 + 1] = p.tri.p[k].y; f->verts[i * 9 + k * 3 + 2] = p.tri.p[k].z; }
+            if (p.tri.hasNormals) {
+                hasN = true;
+                for (int k = 0; k < 3; k++) { f->normals[i * 9 + k * 3] = (float)p.tri.n[k].x; f->normals[i * 9 + k * 3 + 1] = (float)p.tri.n[k].y; f->normals[i * 9 + k * 3 + 2] = (float)p.tri.n[k].z; }
+                for (int k = 0; k < 3; k++) { f->uvs[i * 6 + k * 2] = (float)p.tri.uv[k][0]; f->uvs[i * 6 + k * 2 + 1] = (float)p.tri.uv[k][1]; if (p.tri.uv[k][0] != 0.0 || p.tri.uv[k][1] != 0.0) hasUV = true; }
+            }
+        }
+        if (hasN) anyN = true;
+        if (hasUV) anyUV = true;
+    });
+    f->anyNormals = anyN; f->anyUV = anyUV;
 }
 
 void uploadGeometry(spb_ctx* ctx, const FlatScene& f) {

@@ -1,7 +1,9 @@
 // Mesh loaders with the reference's behaviour (core/meshio.cc:76-261): one world-space Triangle per
 // face; OBJ through a small reader that reproduces what the reference takes from tinyobjloader
 // (float32 positions widened to double, fan triangulation, per-shape "has normals / has uvs").
+#include <atomic>
 #include <cstring>
+#include <new>
 #include <fstream>
 #include <sstream>
 
@@ -97,7 +99,7 @@ std::vector<Triangle> loadOBJ(const std::string& file, const Transform& o2w) {
     return out;
 }
 
-std::vector<Triangle> loadPLY(const std::string& file, const Transform& o2w) {
+TriangleBuffer loadPLY(const std::string& file, const Transform& o2w) {
     std::ifstream ifs(file, std::ios::in | std::ios::binary);
     if (!ifs.is_open()) FatalError("failed to open file \"%s\" !!", file.c_str());
     std::string line;
@@ -119,23 +121,46 @@ std::vector<Triangle> loadPLY(const std::string& file, const Transform& o2w) {
     SpicaAssert(nv > 0 && nf > 0, "numVerts and numFaces must be positive");
     std::vector<float> v((size_t)nv * 3);
     ifs.read((char*)v.data(), sizeof(float) * v.size());          // the reference reads xyz only (meshio.cc:137-140)
-    std::vector<Triangle> out;
-    out.reserve((size_t)nf);
-    const double uv[3][2] = {{0, 0}, {0, 0}, {0, 0}};
-    Normal3d n[3];
-    for (long i = 0; i < nf; i++) {
-        unsigned char vs; int ii[3];
-        ifs.read((char*)&vs, 1);
-        ifs.read((char*)ii, sizeof(int) * 3);
-        if (!ifs) FatalError("PLY file is truncated: %s", file.c_str());
-        Point3d p[3];
-        for (int k = 0; k < 3; k++) {
-            SpicaAssert(ii[k] >= 0 && ii[k] < nv, "PLY vertex index out of range");
-            p[k] = Point3d(v[(size_t)ii[k] * 3], v[(size_t)ii[k] * 3 + 1], v[(size_t)ii[k] * 3 + 2]);
+    if (!ifs) FatalError("PLY file is truncated: %s", file.c_str());
+    // the face block in one read (13 bytes per triangle; the reference pulls it through the stream field by field, meshio.cc:143-160)
+    const std::streampos at = ifs.tellg();
+    ifs.seekg(0, std::ios::end);
+    const size_t rest = (size_t)(ifs.tellg() - at);
+    ifs.seekg(at);
+    std::vector<unsigned char> fb(rest);
+    ifs.read((char*)fb.data(), (std::streamsize)rest);
+    if (!ifs) FatalError("PLY file is truncated: %s", file.c_str());
+    std::vector<size_t> offset;                                  // only when some face is not a triangle
+    bool allTriangles = rest >= (size_t)nf * 13;
+    if (allTriangles) for (long i = 0; i < nf && allTriangles; i++) allTriangles = fb[(size_t)i * 13] == 3;
+    if (!allTriangles) {                                         // polygons: the first three indices of each, like the reference
+        offset.resize((size_t)nf);
+        size_t o = 0;
+        for (long i = 0; i < nf; i++) {
+            if (o + 13 > rest) FatalError("PLY file is truncated: %s", file.c_str());
+            const unsigned char vs = fb[o];
+            offset[(size_t)i] = o;
+            if (vs > 3) Warning("mesh contains non-triangle polygon (%d vertices) !!", (int)vs);
+            o += 1 + sizeof(int) * (size_t)std::max<int>(vs, 3);
         }
-        out.push_back(makeTriangle(p, n, uv, false, false, o2w));
-        if (vs > 3) { Warning("mesh contains non-triangle polygon (%d vertices) !!", (int)vs); ifs.seekg(sizeof(int) * (vs - 3), std::ios_base::cur); }
     }
+    TriangleBuffer out((size_t)nf);
+    const double uv[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+    std::atomic<bool> bad(false);
+    parallelFor((size_t)nf, [&](size_t b, size_t e) {
+        Normal3d n[3];
+        for (size_t i = b; i < e; i++) {
+            int ii[3];
+            std::memcpy(ii, fb.data() + (allTriangles ? i * 13 : offset[i]) + 1, sizeof(int) * 3);
+            Point3d p[3];
+            for (int k = 0; k < 3; k++) {
+                if (ii[k] < 0 || ii[k] >= nv) { bad = true; ii[k] = 0; }
+                p[k] = Point3d(v[(size_t)ii[k] * 3], v[(size_t)ii[k] * 3 + 1], v[(size_t)ii[k] * 3 + 2]);
+            }
+            new (out.p + i) Triangle(makeTriangle(p, n, uv, false, false, o2w));
+        }
+    });
+    SpicaAssert(!bad, "PLY vertex index out of range");
     return out;
 }
 

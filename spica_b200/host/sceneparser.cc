@@ -1,6 +1,7 @@
 // Mitsuba-0.5-style scene loading with the reference's element semantics
 // (spica/sceneparser.cc:58-334): depth-first walk, children stored before their parent is built,
 // parameters kept in one RenderParams bag, objects made through the plugin manager by type name.
+#include <new>
 #include <cstring>
 #include <ctime>
 #include <filesystem>
@@ -137,11 +138,30 @@ struct SceneParser::Impl {
             if (params.getObject("subsurface", nullptr, true)) FatalError("subsurface materials are outside this host's scope");
             if (params.getObject("medium", nullptr, true)) FatalError("participating media are outside this host's scope");
             const Transform transform = params.getTransform("toWorld", Transform(), true);
-            std::vector<Triangle> tris;
-            if (type == "obj") tris = meshio::loadOBJ(params.getString("filename"), transform);
-            else if (type == "ply") tris = meshio::loadPLY(params.getString("filename"), transform);
+            std::vector<Triangle> objTris; meshio::TriangleBuffer plyTris;
+            const Triangle* tris = nullptr; size_t nTris = 0;
+            if (type == "obj") { objTris = meshio::loadOBJ(params.getString("filename"), transform); tris = objTris.data(); nTris = objTris.size(); }
+            else if (type == "ply") { plyTris = meshio::loadPLY(params.getString("filename"), transform); tris = plyTris.p; nTris = plyTris.n; }
             else FatalError("Failed to load plugin: plugins/%s.so (analytic shapes are outside this host's scope; use obj / ply)", type.c_str());
-            for (const Triangle& t : tris) primitives.push_back(createPrimitive(t, transform, surface));
+            if (nTris >= 4096) hostPhaseLap("mesh file read");
+            if (waitAreaLight || nTris < 4096) {
+                for (size_t i = 0; i < nTris; i++) primitives.push_back(createPrimitive(tris[i], transform, surface));
+            } else {
+                // a large mesh: its primitives in ONE allocation, constructed by all cores and handed out through aliasing pointers
+                // (the plugin surface wants a std::shared_ptr<Primitive> per triangle, core/cobject.h:66-75; ten million
+                // make_shared calls, or one thread touching 2.3 GB first, cost seconds)
+                Primitive* raw = (Primitive*)std::malloc(sizeof(Primitive) * nTris);
+                if (!raw) FatalError("out of memory for %zu primitives", nTris);
+                parallelFor(nTris, [&](size_t b, size_t e) { for (size_t i = b; i < e; i++) { Primitive* q = new (raw + i) Primitive(); q->tri = tris[i]; q->material = surface; } });
+                const size_t count = nTris;
+                std::shared_ptr<Primitive> block(raw, [count](Primitive* q) {       // (may run during static destruction: no threads here)
+                    for (size_t i = 0; i < count; i++) q[i].~Primitive();
+                    std::free(q);
+                });
+                primitives.reserve(primitives.size() + nTris);
+                for (size_t i = 0; i < nTris; i++) primitives.emplace_back(block, raw + i);
+            }
+            if (nTris >= 4096) hostPhaseLap("primitives created");
             waitAreaLight = false;
         } else if (node == "ref") {
             const std::string id = getAttribute(e, "id");

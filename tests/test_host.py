@@ -66,6 +66,36 @@ def test_ply_shape_transform_and_defaults(tmp_path):
     assert (r["width"], r["height"]) == (40, 20)
 
 
+def test_ply_loader_large_mesh_polygons_and_broken_files(tmp_path):
+    """The PLY loader reads the face block in one piece and builds the triangles (and the primitives of a mesh of >= 4096
+    triangles, in one allocation) on all cores: same triangles as the arrays scene; polygons keep their first three indices
+    (core/meshio.cc:143-160); a truncated file and an index out of range abort with the reference's kind of message."""
+    import struct
+    import sys
+    d = str(tmp_path)
+    xml = scenes.write_envscene(d, 64, 64, 4, 4, name="e", nu=100, nv=60)            # 12,000 + 2 triangles: the block path
+    r = host.parse_scene(xml)
+    assert r["n_triangles"] == 12002 and np.array_equal(r["verts"], scenes.envscene_arrays(100, 60)["tris"])
+    ply = os.path.join(d, "e_torus.ply")
+    verts = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1]], np.float32)
+
+    def write(faces, truncate=0):
+        hdr = ("ply\nformat binary_little_endian 1.0\nelement vertex %d\nproperty float x\nproperty float y\nproperty float z\n"
+               "element face %d\nproperty list uchar int vertex_indices\nend_header\n" % (len(verts), len(faces))).encode()
+        body = verts.tobytes() + b"".join(struct.pack("<B%di" % len(f), len(f), *f) for f in faces)
+        open(ply, "wb").write(hdr + (body[:-truncate] if truncate else body))
+
+    write([(0, 1, 2, 3), (0, 1, 4)])                                                 # a quad, then a triangle
+    r = host.parse_scene(xml)
+    assert r["n_triangles"] == 4
+    assert r["verts"][0].tolist() == [0, 0, 0, 1, 0, 0, 1, 1, 0] and r["verts"][1].tolist() == [0, 0, 0, 1, 0, 0, 0, 0, 1]
+    code = "from spica_b200 import host; host.parse_scene(%r)" % xml
+    for faces, truncate, message in (([(0, 1, 2), (0, 1, 4)], 5, "truncated"), ([(0, 1, 9)], 0, "index out of range")):
+        write(faces, truncate)
+        p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT)
+        assert p.returncode != 0 and message in (p.stdout + p.stderr)
+
+
 def test_cli_fails_loudly_without_device_or_scene(tmp_path):
     from tests.conftest import has_cuda_device
     r = subprocess.run([host.CLI_PATH, "-i", str(tmp_path / "missing.xml")], capture_output=True, text=True)
