@@ -22,6 +22,24 @@
 
 namespace spica {
 
+// n values of a plain type in storage that nobody touches before it is filled (std::vector::resize would zero-fill it on one thread)
+template <class T>
+struct RawArray {
+    static_assert(std::is_trivially_copyable<T>::value, "plain values only");
+    T* p = nullptr; size_t n = 0;
+    RawArray() = default;
+    RawArray(const RawArray&) = delete;
+    RawArray& operator=(const RawArray&) = delete;
+    ~RawArray() { std::free(p); }
+    void resize(size_t count) { std::free(p); p = count ? (T*)std::malloc(sizeof(T) * count) : nullptr; n = p ? count : 0; if (count && !p) { fprintf(stderr, "out of memory\n"); abort(); } }
+    T* data() { return p; }
+    const T* data() const { return p; }
+    size_t size() const { return n; }
+    bool empty() const { return n == 0; }
+    T& operator[](size_t i) { return p[i]; }
+    const T& operator[](size_t i) const { return p[i]; }
+};
+
 // fn(begin, end) over [0, n) on the host cores (mesh loading and flattening of multi-million-triangle scenes)
 template <class F>
 inline void parallelFor(size_t n, F fn, size_t grain = 1 << 16) {

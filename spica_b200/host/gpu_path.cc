@@ -113,8 +113,8 @@ void gpuPoolFinish() {
 }
 
 struct FlatScene {              // the primitives as the C ABI takes them
-    std::vector<double> verts;
-    std::vector<float> normals, uvs;
+    RawArray<double> verts;                 // 9 per triangle
+    RawArray<float> normals, uvs;           // 9 / 6 per triangle, only when some triangle carries normals
     std::vector<int32_t> material_id, light_id;
     std::vector<spb_material> materials;
     std::vector<spb_texture> textures;      // + the bitmaps' texels and {kr, kt} bindings per material
@@ -125,7 +125,11 @@ struct FlatScene {              // the primitives as the C ABI takes them
 
 void flatten(const std::vector<std::shared_ptr<Primitive>>& prims, FlatScene* f) {
     const size_t n = prims.size();
-    f->verts.resize(n * 9); f->normals.assign(n * 9, 0.f); f->uvs.assign(n * 6, 0.f);
+    std::atomic<bool> anyN(false), anyUV(false);
+    parallelFor(n, [&](size_t b, size_t e) { bool h = false; for (size_t i = b; i < e; i++) h = h || prims[i]->tri.hasNormals; if (h) anyN = true; });
+    const bool withN = anyN;
+    f->verts.resize(n * 9);
+    if (withN) { f->normals.resize(n * 9); f->uvs.resize(n * 6); } else { f->normals.resize(0); f->uvs.resize(0); }
     f->material_id.resize(n); f->light_id.assign(n, -1);
     std::map<const SurfaceMaterial*, int> matIndex;
     std::map<const Texture*, int> texIndex;
@@ -157,22 +161,23 @@ void flatten(const std::vector<std::shared_ptr<Primitive>>& prims, FlatScene* f)
         }
         f->material_id[i] = lastIndex;
     }
-    std::atomic<bool> anyN(false), anyUV(false);
     parallelFor(n, [&](size_t b, size_t e) {
-        bool hasN = false, hasUV = false;
+        bool hasUV = false;
         for (size_t i = b; i < e; i++) {
             const Primitive& p = *prims[i];
             for (int k = 0; k < 3; k++) { f->verts[i * 9 + k * 3] = p.tri.p[k].x; f->verts[i * 9 + k * 3 + 1] = p.tri.p[k].y; f->verts[i * 9 + k * 3 + 2] = p.tri.p[k].z; }
+            if (!withN) continue;
             if (p.tri.hasNormals) {
-                hasN = true;
                 for (int k = 0; k < 3; k++) { f->normals[i * 9 + k * 3] = (float)p.tri.n[k].x; f->normals[i * 9 + k * 3 + 1] = (float)p.tri.n[k].y; f->normals[i * 9 + k * 3 + 2] = (float)p.tri.n[k].z; }
                 for (int k = 0; k < 3; k++) { f->uvs[i * 6 + k * 2] = (float)p.tri.uv[k][0]; f->uvs[i * 6 + k * 2 + 1] = (float)p.tri.uv[k][1]; if (p.tri.uv[k][0] != 0.0 || p.tri.uv[k][1] != 0.0) hasUV = true; }
+            } else {
+                for (int k = 0; k < 9; k++) f->normals[i * 9 + k] = 0.f;
+                for (int k = 0; k < 6; k++) f->uvs[i * 6 + k] = 0.f;
             }
         }
-        if (hasN) anyN = true;
         if (hasUV) anyUV = true;
     });
-    f->anyNormals = anyN; f->anyUV = anyUV;
+    f->anyNormals = withN; f->anyUV = anyUV;
 }
 
 void uploadGeometry(spb_ctx* ctx, const FlatScene& f) {
